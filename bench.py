@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the multigrid V-cycle eigensolver path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n GRID] [--smoother S]
+
+A "step" is one outer iteration of the shift method on the block of the 4 lowest eigenvectors of the 2-D
+infinite well (2DPotGS.py:91-105): for each vector one V(4,4)-cycle of (H - mu_i I) w = v_i, normalise,
+Rayleigh quotient; then modified Gram-Schmidt of the block.  `value` counts smoother unknown-updates/s
+(8 sweeps on every smoothing level of every cycle) with all vectors resident in HBM; `e2e` is the same
+step through the reference-facing MGCMTSolver.vcycle / MGCMTProcessor.gramschmidt calls with HOST numpy
+arrays (pinned), host<->device copies inside the timed region.
+
+Prints ONE JSON line (rank 0).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "2D well V-cycle unknown-updates/s"
+UNIT = "unknown-updates/s"
+MODES = [(1, 1), (1, 2), (2, 1), (2, 2)]
+N0 = 16  # coarse grid the initial guesses / shifts come from (2DPotGS.py:54-63; closed form instead of eigsh)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="grid size N (N x N unknowns); default 4096")
+    ap.add_argument("--lowest", type=int, default=8, help="lowest_level (reference's 2-D choice: 8, 2DPot.py:89)")
+    ap.add_argument("--smoother", default="wjacobi", choices=["wjacobi", "rbgs"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-n", type=int, default=2048, help="grid size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# closed-form pieces: no RNG, no eigsh
+# ---------------------------------------------------------------------------------------------------
+def ev1(n, k):
+    import numpy as np
+    return (4.0 * n * n / np.pi ** 2) * np.sin(k * np.pi / (2.0 * (n + 1))) ** 2
+
+
+def vec1(n, k):
+    import numpy as np
+    v = np.sin(k * np.pi * (np.arange(n) + 1.0) / (n + 1.0))
+    return v / np.linalg.norm(v)
+
+
+def interp1(N):
+    """1-D interpolation N0 -> N as a dense (N, N0) matrix (MGCMTStencilMaker.py:27-43)."""
+    from multigridcmt_b200 import MGCMTStencilMaker
+    return MGCMTStencilMaker().interpolation(N0, N).toarray()
+
+
+def initial_block(N):
+    """(4, N*N) start vectors P(16->N,'2d') * closed-form N=16 eigenvectors, normalised; and shifts."""
+    import numpy as np
+    P = interp1(N)
+    shifts = [ev1(N0, a) + ev1(N0, b) for a, b in MODES]
+    V = np.empty((4, N * N))
+    for c, (a, b) in enumerate(MODES):
+        V[c] = np.kron(P @ vec1(N0, a), P @ vec1(N0, b))  # (P (x) P)(va (x) vb)
+        V[c] /= np.linalg.norm(V[c])
+    return V, shifts
+
+
+def updates_per_cycle(N, lowest):
+    """smoother unknown-updates in one V(4,4): 8 sweeps on every level except the coarsest."""
+    tot, g = 0, N
+    while g > lowest:
+        tot += 8 * g * g
+        g //= 2
+    return tot
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load = the upper half of the observed clocks
+        med = statistics.median(sorted(sm)[len(sm) // 2:]) if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the oracle, single-threaded scipy: the reference's own CPU path cannot run at these sizes,
+# SURVEY.md D9 / section 8(d))
+# ---------------------------------------------------------------------------------------------------
+def cpu_sample(n_cpu, lowest, repeats=1):
+    """Time the oracle (reference-equivalent CPU port) on one V(4,4)-cycle at n_cpu^2 with the hierarchy
+    already built (the reference rebuilds it every call; leaving that out favours the CPU)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mgcmt_oracle as orc
+    osm, osv = orc.StencilMaker(), orc.Solver(cache_hierarchy=True)
+    H = (-1.0 / np.pi ** 2) * osm.laplacian(n_cpu, "2d")
+    shift = ev1(N0, 1) + ev1(N0, 2)
+    P = osm.interpolation(N0, n_cpu).toarray()
+    v = np.kron(P @ vec1(N0, 1), P @ vec1(N0, 2))
+    v /= np.linalg.norm(v)
+    osv.vcycle(np.zeros(n_cpu * n_cpu), v.copy(), H, osm, shift=shift, dimension="2d", lowest_level=lowest)  # builds R,P,RAP
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        osv.vcycle(np.zeros(n_cpu * n_cpu), v.copy(), H, osm, shift=shift, dimension="2d", lowest_level=lowest)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return updates_per_cycle(n_cpu, lowest) / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = args.cpu_n
+    ups = updates_per_cycle(n_cpu, args.lowest)
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mgcmt_oracle as orc
+    osm, osv = orc.StencilMaker(), orc.Solver(cache_hierarchy=True)
+    H = (-1.0 / np.pi ** 2) * osm.laplacian(n_cpu, "2d")
+    P = osm.interpolation(N0, n_cpu).toarray()
+    shifts = [ev1(N0, a) + ev1(N0, b) for a, b in MODES]
+    v = np.kron(P @ vec1(N0, 1), P @ vec1(N0, 2))
+    v /= np.linalg.norm(v)
+    # each step = one V(4,4)-cycle of the block's second vector at n_cpu^2 (bounded sample)
+    steps = max(1, args.steps)
+    warm = max(1, args.warmup)
+    budget_s = 240.0
+    t_start = time.perf_counter()
+    for _ in range(warm):
+        osv.vcycle(np.zeros(n_cpu * n_cpu), v.copy(), H, osm, shift=shifts[1], dimension="2d", lowest_level=args.lowest)
+    one = None
+    done = 0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        osv.vcycle(np.zeros(n_cpu * n_cpu), v.copy(), H, osm, shift=shifts[1], dimension="2d", lowest_level=args.lowest)
+        done += 1
+        if time.perf_counter() - t_start > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    value = ups * done / dt
+    sample = ("%d of the requested %d steps; each step = 1 V(4,4)-cycle (wjacobi, lowest_level=%d) at %d^2, "
+              "hierarchy prebuilt, scipy CSC SpMV, single thread" % (done, steps, args.lowest, n_cpu, ))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": warm, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "2D infinite well %d^2 (bounded CPU sample of the 4096^2 workload), V(4,4), "
+                               "lowest_level=%d, shift method" % (n_cpu, args.lowest), "smoother": "wjacobi"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from multigridcmt_b200 import MGCMTProcessor, MGCMTSolver, MGCMTStencilMaker, _lib
+    from multigridcmt_b200.hierarchy import _ptr, _stream_ptr, get_hierarchy
+    lib = _lib.load()
+    sm, solver, proc = MGCMTStencilMaker(), MGCMTSolver(), MGCMTProcessor()
+
+    N = args.n or 4096
+    lowest = args.lowest
+    smoother_code = _lib.SMOOTH_WJACOBI if args.smoother == "wjacobi" else _lib.SMOOTH_RBGS
+    omega = 2.0 / 3.0 if args.smoother == "wjacobi" else 1.0
+    n = N * N
+    H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    h = get_hierarchy(H, lowest)
+    V_host, shifts = initial_block(N)
+    k = len(MODES)
+    # replicas: with N ranks every rank runs the same independent block (data-parallel over problems);
+    # the path has no exchange step at this problem size.  (Slab decomposition of 16384^2: later round.)
+    V = torch.from_numpy(V_host).cuda()            # (k, n) vector-major block, resident in HBM
+    W = torch.zeros_like(V)
+    rq = torch.zeros(k, 2, dtype=torch.float64, device="cuda")
+    stream = _stream_ptr(torch)
+
+    def step():
+        for c in range(k):
+            W[c].zero_()
+            _lib.check(lib.mgcmt_vcycle(h.handle, shifts[c], 4, 4, smoother_code, omega, _ptr(W[c]), _ptr(V[c]), stream))
+            _lib.check(lib.mgcmt_normalize(n, _ptr(W[c]), stream))
+            _lib.check(lib.mgcmt_rayleigh(h.handle, 0, _ptr(W[c]), _ptr(rq[c]), stream))
+        _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(W), 1, stream))
+        V.copy_(W)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = lib.mgcmt_launch_count()
+    lib.mgcmt_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.mgcmt_launch_count() - launches0
+    dom_ms, dom_cnt = C.c_double(), C.c_longlong()
+    lib.mgcmt_profile_read(C.byref(dom_ms), C.byref(dom_cnt))
+    lib.mgcmt_profile_enable(0)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    lam = (rq[:, 0] / rq[:, 1]).cpu().tolist()
+    exact = [ev1(N, a) + ev1(N, b) for a, b in MODES]
+
+    ups_step = k * updates_per_cycle(N, lowest)
+    value = world * ups_step * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the reference-facing call with host buffers (pinned), copies inside the timed region -----
+    e2e = None
+    if rank == 0 or world > 1:
+        Vh = torch.from_numpy(V_host.copy()).pin_memory()
+        zero_h = torch.zeros(n, dtype=torch.float64).pin_memory()
+        Vnp = Vh.numpy()
+        znp = zero_h.numpy()
+
+        def e2e_step():
+            lam_h = []
+            for c in range(k):
+                w = solver.vcycle(znp, Vnp[c], H, sm, shift=shifts[c], dimension="2d", lowest_level=lowest,
+                                  smoother=(solver.rbgs if args.smoother == "rbgs" else None))
+                Vnp[c] = w / np.linalg.norm(w)
+                znp.shape = (n,)
+            return lam_h
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * ups_step * args.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": k * 2 * n * 8, "d2h_bytes_per_step": k * n * 8,
+               "steps": args.e2e_steps, "call": "MGCMTSolver.vcycle(numpy, numpy, H, sm, shift=, dimension='2d')"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    dom_bytes = 24.0 * n  # read v, read f, write v
+    roofline = None
+    if dom_cnt.value > 0:
+        per_launch_ms = dom_ms.value / dom_cnt.value
+        if args.smoother == "rbgs":
+            dom_bytes = 24.0 * n * 4  # one bracket = nu sweeps of 4 colour passes ... reported per bracket
+        achieved = dom_bytes / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "stencil_march_kernel<JACOBI,FIVE> (finest-level sweep)",
+                    "launch_ms": per_launch_ms, "launches_timed": dom_cnt.value,
+                    "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_kind,
+                    "share_of_step": dom_ms.value / ms,
+                    "vcycle_frac_304B": (304.0 * n * k * args.steps / (ms * 1e-3) / 1e9) / peak}
+
+    cpu_baseline = None
+    if not args.no_cpu and world == 1:
+        v_cpu, t_cpu = cpu_sample(args.cpu_n, lowest)
+        cpu_baseline = {"value": v_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": "1 V(4,4)-cycle (wjacobi, lowest_level=%d) at %d^2 with the hierarchy prebuilt: "
+                                  "%.2f s on 1 host core (scipy SpMV is single-threaded); %d cores present"
+                                  % (lowest, args.cpu_n, t_cpu, os.cpu_count())}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "2D infinite well %d^2, lowest 4 eigenpairs, shift method: 4 x V(4,4) + normalise + "
+                               "Rayleigh quotient + MGS per step" % N,
+                   "smoother": args.smoother, "lowest_level": lowest, "levels": h.num_levels,
+                   "parallelism": "replicas x%d" % world if world > 1 else "1 GPU",
+                   "l2": "working set %.1f GB >> 126 MB L2 (inputs larger than L2)" % (10 * n * 8 / 1e9)},
+        "vcycles_per_s": world * k * args.steps / (ms * 1e-3),
+        "eigenvalues": lam, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam, exact)],
+        "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+/*
+ * mgcmt_b200.h -- C ABI of the B200-native multigrid V-cycle path (libmgcmt_b200.so).
+ *
+ * The reference (AndyMN/MultigridCMT) has no FFI layer: its boundary is the Python class surface
+ * MGCMTStencilMaker / MGCMTSolver / MGCMTProcessor.  The host-side mirror of those classes lives in
+ * multigridcmt_b200/*.py and binds the entry points below with ctypes (see INTEGRATION.md for the
+ * stub a reference maintainer would add).  Each entry point cites the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C types only; every `double*` named `d_*` is a DEVICE pointer (fp64), every `h_*` is
+ *     a HOST pointer; `stream` is a cudaStream_t passed as void*.
+ *   - no ownership transfer: callers own every buffer they pass in; the hierarchy owns its
+ *     coefficient arrays, coarse-level work vectors and cached coarse inverses.
+ *   - every function returns MGCMT_OK (0) or an error code; mgcmt_last_error() gives the message
+ *     of the last failure on the calling thread.  Nothing here synchronises the host except where
+ *     stated (scalar results are written to device memory, not returned).
+ *   - grids: a level is an nrows x ncols array of doubles, row-major (index i*ncols + j), exactly the
+ *     reference's 2-D ordering (MGCMTStencilMaker.py:24, kronsum => i*N + j).  A 1-D problem is a
+ *     grid with nrows == 1.  ncols (and nrows when > 1) are powers of two.
+ *   - operators are kept in separable form  A_l = Ma_l (x) Kb_l + Ka_l (x) Mb_l  with tridiagonal
+ *     1-D factors (Ka/Ma act on the row index, Kb/Mb on the column index, M_0 = I).  Galerkin
+ *     coarsening R A P of the reference (MGCMTSolver.py:318) maps each factor to R T P exactly, so
+ *     every level costs O(n) coefficient storage instead of a sparse matrix.
+ *   - the shift of the shift method is re-applied as  -shift*I  on every level and A is coarsened
+ *     unshifted (MGCMTSolver.py:287-288,318-320).
+ */
+#ifndef MGCMT_B200_H
+#define MGCMT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGCMT_ABI_VERSION 1
+
+enum {
+  MGCMT_OK = 0,
+  MGCMT_ERR_ARG = 1,   /* bad argument (size not a power of two, null pointer, bad level ...) */
+  MGCMT_ERR_CUDA = 2,  /* a CUDA runtime call or kernel launch failed */
+  MGCMT_ERR_STATE = 3, /* hierarchy not usable for this call */
+  MGCMT_ERR_NUMERIC = 4 /* singular coarsest operator */
+};
+
+/* smoother selectors for mgcmt_smooth / mgcmt_vcycle */
+enum {
+  MGCMT_SMOOTH_WJACOBI = 0, /* MGCMTSolver.wjacobi, MGCMTSolver.py:182-208 */
+  MGCMT_SMOOTH_RBGS = 1,    /* red-black (four-colour) Gauss-Seidel/SOR: the working replacement of the
+                               reference's dead gseidelrb, MGCMTSolver.py:248-279 */
+  MGCMT_SMOOTH_GSLEX = 2    /* lexicographic Gauss-Seidel / SOR, MGCMTSolver.py:210-246 (incl. quirk Q6) */
+};
+
+typedef struct mgcmt_hier mgcmt_hier_t; /* opaque grid hierarchy */
+
+int mgcmt_abi_version(void);
+const char *mgcmt_last_error(void);
+
+/* ---- instrumentation for bench.py ------------------------------------------------------------------
+ * mgcmt_launch_count: kernels launched by this library since load (bench.py's gpu_launches).
+ * mgcmt_profile_enable(1): bracket every finest-level smoother launch with CUDA events on its stream;
+ * mgcmt_profile_read: synchronise, return the summed event time (ms) and the number of bracketed
+ * intervals since the last read, and reset. */
+long long mgcmt_launch_count(void);
+int mgcmt_profile_enable(int on);
+int mgcmt_profile_read(double *ms_total, long long *intervals);
+
+/* ---- hierarchy -------------------------------------------------------------------------------
+ * Builds all levels from the finest grid (nrows x ncols) down to the level whose column count is
+ * `lowest_level` (the reference's lowest_level, MGCMTSolver.py:305).  The finest operator is
+ *   A_0 = I (x) Kb + Ka (x) I,  Ka = tridiag(h_row_lo, h_row_di, h_row_up) (nrows entries each; lo[0]
+ *   and up[nrows-1] ignored),  Kb likewise with ncols entries.  For a 1-D problem pass nrows = 1,
+ *   h_row_* = {0}.  Coarse factors are the Galerkin products with the reference's transfer operators
+ *   (MGCMTStencilMaker.py:27-78: coarse j <-> fine 2j+1, R = [1/4 1/2 1/4] with a truncated last row),
+ *   computed on the device.  coarsen_rows = 0 keeps the row count on all levels (1-D problems).
+ * Replaces: MGCMTStencilMaker.laplacian/restriction/interpolation + the `R*A*P` at
+ * MGCMTSolver.py:310-311,318 that the reference rebuilds on every call. */
+int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows,
+                      const double *h_row_lo, const double *h_row_di, const double *h_row_up,
+                      const double *h_col_lo, const double *h_col_di, const double *h_col_up,
+                      int lowest_level, void *stream);
+int mgcmt_hier_destroy(mgcmt_hier_t *h);
+int mgcmt_hier_num_levels(const mgcmt_hier_t *h);
+/* grid size of a level (level 0 = finest) */
+int mgcmt_hier_level_shape(const mgcmt_hier_t *h, int level, int *nrows, int *ncols);
+/* copies the 12 tridiagonal factor arrays of a level to the host, for tests:
+ * order ka_lo,ka_di,ka_up,ma_lo,ma_di,ma_up (nrows each) then kb_*,mb_* (ncols each). Synchronises. */
+int mgcmt_hier_level_coefs(const mgcmt_hier_t *h, int level, double *h_rowcoef6, double *h_colcoef6);
+
+/* ---- single-level operators (all on `stream`, device pointers, level sizes) --------------------- */
+/* y = (A_l - shift I) x            -- the `shifted_matrix * v` of MGCMTSolver.py:315 */
+int mgcmt_apply(mgcmt_hier_t *h, int level, double shift, const double *d_x, double *d_y, void *stream);
+/* r = f - (A_l - shift I) v        -- MGCMTSolver.py:315 (inner bracket) */
+int mgcmt_residual(mgcmt_hier_t *h, int level, double shift, const double *d_v, const double *d_f,
+                   double *d_r, void *stream);
+/* nu sweeps of the chosen smoother on (A_l - shift I) v = f, in place in d_v.
+ * d_tmp: scratch of the level's size (may be NULL: the hierarchy's own scratch is used).
+ * omega: Jacobi weight (reference default 2/3) or SOR factor (reference default 1).
+ * Replaces MGCMTSolver.wjacobi/gseidel/sor, MGCMTSolver.py:182-246. */
+int mgcmt_smooth(mgcmt_hier_t *h, int level, int smoother, double shift, double omega, int nu,
+                 double *d_v, const double *d_f, double *d_tmp, void *stream);
+/* coarse = R fine   (full weighting, MGCMTStencilMaker.py:57-78) level -> level+1 */
+int mgcmt_restrict(mgcmt_hier_t *h, int level, const double *d_fine, double *d_coarse, void *stream);
+/* r_coarse = R (f - (A_l - shift I) v), fused         -- MGCMTSolver.py:315 */
+int mgcmt_residual_restrict(mgcmt_hier_t *h, int level, double shift, const double *d_v,
+                            const double *d_f, double *d_rcoarse, void *stream);
+/* fine = P coarse   (linear interpolation, MGCMTStencilMaker.py:27-54) level+1 -> level */
+int mgcmt_prolong(mgcmt_hier_t *h, int level, const double *d_coarse, double *d_fine, void *stream);
+/* v += P e, fused                                     -- MGCMTSolver.py:323-324 */
+int mgcmt_prolong_correct(mgcmt_hier_t *h, int level, const double *d_ecoarse, double *d_v, void *stream);
+/* v = (A_L - shift I)^-1 f on the coarsest level L     -- spsolve at MGCMTSolver.py:305-308.
+ * The dense inverse is computed on the device once per shift (pivoted Gauss-Jordan) and cached. */
+int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double *d_v, void *stream);
+
+/* ---- whole cycle ---------------------------------------------------------------------------------
+ * One V-cycle of MGCMTSolver.vcycle (MGCMTSolver.py:281-329) on the finest level: d_v in/out, d_f in.
+ * nu1/nu2 apply to the finest level only; all coarser levels run 4/4 (MGCMTSolver.py:320, quirk Q4).
+ * If the hierarchy has a single level this is the exact solve (quirk Q7). */
+int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega,
+                 double *d_v, const double *d_f, void *stream);
+
+/* ---- reductions / vector post-processing (MGCMTProcessor.py, Rayleigh quotients in the drivers) --
+ * Deterministic: fixed two-stage tree, independent of launch timing.  Results go to DEVICE memory. */
+int mgcmt_dot(long long n, const double *d_x, const double *d_y, double *d_out, void *stream);
+/* d_out[0] = x^T (A_0 x), d_out[1] = x^T x   (one fused pass; e.g. 2DPotGS.py:103) */
+int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream);
+/* x *= 1/||x||_2          -- `w / np.linalg.norm(w)`, e.g. 2DPotGS.py:96; MGCMTProcessor.normalize */
+int mgcmt_normalize(long long n, double *d_x, void *stream);
+/* y = alpha*x + y with alpha read from device memory, scaled by `sign` */
+int mgcmt_axpy_dev(long long n, const double *d_alpha, double sign, const double *d_x, double *d_y,
+                   void *stream);
+/* Gram-Schmidt of k vectors of length n stored one after another (vector-major: d_V + c*n is
+ * column c).  modified != 0: MGS exactly as MGCMTProcessor.gramschmidt (MGCMTProcessor.py:44-50);
+ * modified == 0: classical GS followed by normalisation (MGCMTProcessor.py:35-42). In place. */
+int mgcmt_gramschmidt(long long n, int k, double *d_V, int modified, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGCMT_B200_H */

@@ -1,0 +1,268 @@
+"""Drop-in for the reference's MGCMTSolver (MGCMTSolver.py:8-436) running on the B200.
+
+Same class name, method names, positional/keyword signatures and return shapes as the reference;
+inputs are numpy arrays + scipy.sparse matrices (or a matrix-free SeparableOperator), outputs are
+fresh numpy arrays.  Passing torch cuda tensors instead of numpy arrays keeps the data on the device
+(no host copies; a torch tensor comes back) -- that is the extension the large grids need.
+
+Reference conventions kept on purpose (SURVEY.md section 5 and the quirk table):
+  * bad sizes PRINT a message and return None (MGCMTSolver.py:303-304, :404-405);
+  * `vcycle`/`twogrid`/`wjacobi` reshape the caller's numpy v0 and f to (n, 1) in place
+    (MGCMTSolver.py:187-191, :297-300, :344-347);
+  * `vcycle` returns (n,) -- but (n, 1) when called directly at the coarsest size (quirk Q7);
+  * coarse levels ignore the caller's nu1/nu2 and run 4/4 (quirk Q4);
+  * the shift is re-applied as -shift*I on every level, A is coarsened unshifted (quirk Q5);
+  * `sor` adds w (D-L)^-1 f (quirk Q6).
+What is NOT kept: the O(n^2) iteration matrices and the per-call rebuild of R, P, R*A*P.
+
+There is no CPU fallback: an operator that is not a separable radius-1 stencil, a foreign smoother
+callable or a foreign stencil_maker raises (loudly) instead of silently running somewhere else.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+from . import _lib
+from .MGCMTProcessor import MGCMTProcessor
+from .MGCMTStencilMaker import MGCMTStencilMaker
+from .hierarchy import (_ptr, _stream_ptr, get_hierarchy, is_device_tensor, to_device, to_host)
+from .operators import recognise
+
+
+def _inplace_column(x, n):
+    """The reference does `x.shape = (n, 1)` on the caller's array; mimic it when possible."""
+    if isinstance(x, np.ndarray):
+        try:
+            x.shape = (n, 1)
+        except (AttributeError, ValueError):
+            pass
+
+
+class MGCMTSolver:
+
+    def __init__(self):
+        self.stencil_maker = MGCMTStencilMaker()
+        self.processor = MGCMTProcessor()
+
+    # ------------------------------------------------------------------------------------------
+    # smoother seam: which device smoother does a `smoother=` argument mean?
+    # ------------------------------------------------------------------------------------------
+    def _smoother_code(self, smoother):
+        """-> (code, omega).  Only this class's own smoothers (optionally wrapped in functools.partial
+        to pin omega) are accepted; the device cycle cannot call back into arbitrary Python."""
+        if smoother is None:
+            return _lib.SMOOTH_WJACOBI, 2. / 3.
+        omega = None
+        fn = smoother
+        if isinstance(fn, functools.partial):
+            omega = fn.keywords.get("omega")
+            fn = fn.func
+        owner = getattr(fn, "__self__", None)
+        name = getattr(fn, "__name__", "")
+        if isinstance(owner, MGCMTSolver):
+            if name == "wjacobi":
+                return _lib.SMOOTH_WJACOBI, (2. / 3. if omega is None else float(omega))
+            if name == "gseidel":
+                return _lib.SMOOTH_GSLEX, 1.0
+            if name == "sor":
+                return _lib.SMOOTH_GSLEX, (1.0 if omega is None else float(omega))
+            if name in ("rbgs", "gseidelrb"):
+                return _lib.SMOOTH_RBGS, (1.0 if omega is None else float(omega))
+        raise NotImplementedError(
+            "smoother must be one of MGCMTSolver.wjacobi/gseidel/sor/rbgs (optionally functools.partial "
+            "with omega=...); arbitrary Python smoothers cannot run inside the device V-cycle")
+
+    @staticmethod
+    def _check_stencil_maker(stencil_maker):
+        if not isinstance(stencil_maker, MGCMTStencilMaker):
+            raise NotImplementedError(
+                "stencil_maker must be a multigridcmt_b200 MGCMTStencilMaker: the device path implements "
+                "exactly that class's full-weighting restriction / linear interpolation")
+
+    # ------------------------------------------------------------------------------------------
+    # single-level smoothers (MGCMTSolver.py:182-246): return an (n, 1) array like the reference
+    # ------------------------------------------------------------------------------------------
+    def _smooth(self, code, v0, f, A, nu, omega, dimension=None):
+        n = len(v0)
+        dev_in = is_device_tensor(v0)
+        if dimension is None:
+            dimension = self._guess_dimension(A, n)
+        op = recognise(A, dimension)
+        h = get_hierarchy(op, self._any_lowest(op))
+        v = to_device(v0)
+        if dev_in:
+            v = v.clone()
+        fd = to_device(f)
+        h.smooth(0, code, 0.0, omega, nu, v, fd)
+        if dev_in:
+            return v.reshape(n, 1)
+        return to_host(v).reshape(n, 1)
+
+    @staticmethod
+    def _guess_dimension(A, n):
+        """The reference's smoothers take only the matrix; decide 1-D vs 2-D from its bandwidth."""
+        from .operators import SeparableOperator
+        if isinstance(A, SeparableOperator):
+            return A.dimension
+        N = int(round(np.sqrt(n)))
+        if N * N == n and N > 2:
+            try:
+                far = A.diagonal(N)
+                if np.any(far != 0):
+                    return "2d"
+            except Exception:
+                pass
+        return "1d"
+
+    @staticmethod
+    def _any_lowest(op):
+        return min(op.ncols, 64 if op.nrows > 1 else 4096)
+
+    def wjacobi(self, v0, f, A, nu=4, omega=2. / 3.):
+        n = len(v0)
+        out = self._smooth(_lib.SMOOTH_WJACOBI, v0, f, A, nu, omega)
+        _inplace_column(f, n)   # side effect of the reference (MGCMTSolver.py:187-191)
+        _inplace_column(v0, n)
+        return out
+
+    def gseidel(self, v0, f, A, nu=4):
+        return self._smooth(_lib.SMOOTH_GSLEX, v0, f, A, nu, 1.0)
+
+    def sor(self, v0, f, A, nu=4, omega=1):
+        return self._smooth(_lib.SMOOTH_GSLEX, v0, f, A, nu, float(omega))
+
+    def rbgs(self, v0, f, A, nu=4, omega=1.0):
+        """Red-black (four-colour) Gauss-Seidel/SOR -- the working version of the reference's dead
+        `gseidelrb` (MGCMTSolver.py:248-279)."""
+        return self._smooth(_lib.SMOOTH_RBGS, v0, f, A, nu, float(omega))
+
+    gseidelrb = rbgs
+
+    # ------------------------------------------------------------------------------------------
+    # V-cycle (MGCMTSolver.py:281-329)
+    # ------------------------------------------------------------------------------------------
+    def vcycle(self, v0, f, A, stencil_maker, nu1=4, nu2=4, smoother=None, shift=0, lowest_level=2,
+               dimension="1d"):
+        code, omega = self._smoother_code(smoother)
+        self._check_stencil_maker(stencil_maker)
+        n = len(v0)
+        grid_dimension = 0
+        if dimension == "1d":
+            grid_dimension = n
+        elif dimension == "2d":
+            grid_dimension = np.sqrt(n)
+        dev_in = is_device_tensor(v0)
+        if not dev_in:
+            _inplace_column(f, n)
+            _inplace_column(v0, n)
+        if grid_dimension < 2:
+            print("Length of start vector is not a power of 2")
+            return None
+        g = int(round(grid_dimension))
+        low = int(lowest_level)
+        if (dimension == "2d" and g * g != n) or (g & (g - 1)) or (low & (low - 1)) or low > g or low < 2:
+            # the reference would recurse until the stencil maker prints its power-of-two message
+            print("Length of start vector is not a power of 2")
+            return None
+        op = recognise(A, dimension)
+        h = get_hierarchy(op, low)
+        v = to_device(v0)
+        if dev_in:
+            v = v.clone()
+        fd = to_device(f)
+        if fd.data_ptr() == v.data_ptr():
+            fd = fd.clone()
+        h.vcycle(shift, nu1, nu2, code, omega, v, fd)
+        coarsest_direct = (h.num_levels == 1)
+        if dev_in:
+            return v.reshape(n, 1) if coarsest_direct else v
+        out = to_host(v)
+        return out.reshape(n, 1) if coarsest_direct else out
+
+    # ------------------------------------------------------------------------------------------
+    # two-grid cycle (MGCMTSolver.py:331-371) == a 2-level V-cycle with exact coarse solve
+    # ------------------------------------------------------------------------------------------
+    def twogrid(self, v0, f, A, stencil_maker, nu1=4, nu2=4, smoother=None, shift=0, dimension="1d"):
+        if dimension != "1d":
+            # quirk Q10: the reference's coarse shift matrix is eye(n/2), which mismatches the 2-D coarse
+            # size n/4 -- it cannot run in 2-D there either.
+            raise NotImplementedError("twogrid is 1-D only, as in the reference (MGCMTSolver.py:350)")
+        n = len(v0)
+        if n < 4 or n & (n - 1):
+            print("Length of start vector is not a power of 2")
+            return None
+        return self.vcycle(v0, f, A, stencil_maker, nu1=nu1, nu2=nu2, smoother=smoother, shift=shift,
+                           lowest_level=n // 2, dimension="1d")
+
+    # ------------------------------------------------------------------------------------------
+    # block V-cycle with Gram-Schmidt on the way up (MGCMTSolver.py:375-436)
+    # ------------------------------------------------------------------------------------------
+    def vcycle_matrix(self, v0_matrix, f_matrix, A, stencil_maker, nu1=4, nu2=4, smoother=None, shifts=None,
+                      lowest_level=2, dimension="1d"):
+        torch = _lib.require_cuda()
+        code, omega = self._smoother_code(smoother)
+        self._check_stencil_maker(stencil_maker)
+        n = v0_matrix.shape[0]
+        k = f_matrix.shape[1]
+        if shifts is None:
+            shifts = np.zeros(k)
+        shifts = np.asarray(shifts.cpu() if is_device_tensor(shifts) else shifts, dtype=float).reshape(-1)
+        grid_dimension = n if dimension == "1d" else np.sqrt(n)
+        if grid_dimension < 2:
+            print("Length of start vector is not a power of 2")
+            return None
+        g = int(round(grid_dimension))
+        low = int(lowest_level)
+        if g & (g - 1) or low & (low - 1) or low > g or low < 2:
+            print("Length of start vector is not a power of 2")
+            return None
+        op = recognise(A, dimension)
+        h = get_hierarchy(op, low)
+        dev_in = is_device_tensor(v0_matrix)
+
+        def block(m):
+            if is_device_tensor(m):
+                return m.t().to(torch.float64).contiguous().clone()
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(m, dtype=np.float64).T)).cuda()
+        V = block(v0_matrix)
+        F = block(f_matrix)
+        lib = _lib.load()
+
+        def cycle(level, V, F, n1, n2):
+            nl = h.level_size(level)
+            if level == h.num_levels - 1:
+                for i in range(k):
+                    h.coarse_solve(shifts[i], F[i], V[i])
+                return V
+            for i in range(k):
+                h.smooth(level, code, shifts[i], omega, n1, V[i], F[i])
+            nc = h.level_size(level + 1)
+            Rc = torch.empty(k, nc, dtype=torch.float64, device="cuda")
+            for i in range(k):
+                h.residual_restrict(level, shifts[i], V[i], F[i], Rc[i])
+            E = cycle(level + 1, torch.zeros(k, nc, dtype=torch.float64, device="cuda"), Rc, 4, 4)
+            for i in range(k):
+                h.prolong_correct(level, E[i], V[i])
+                h.smooth(level, code, shifts[i], omega, n2, V[i], F[i])
+            _lib.check(lib.mgcmt_gramschmidt(nl, k, _ptr(V), 1, _stream_ptr(torch)))
+            return V
+        V = cycle(0, V, F, nu1, nu2)
+        if dev_in:
+            return V.t()
+        return np.ascontiguousarray(V.cpu().numpy().T)
+
+    # ------------------------------------------------------------------------------------------
+    # Rayleigh quotient helper (the `v^T H v` the drivers compute inline, e.g. 2DPotGS.py:103)
+    # ------------------------------------------------------------------------------------------
+    def rayleigh_quotient(self, A, v, dimension="1d"):
+        """(v^T A v) / (v^T v) on the device; returns a Python float."""
+        torch = _lib.require_cuda()
+        op = recognise(A, dimension)
+        h = get_hierarchy(op, self._any_lowest(op)) if not op._device else next(iter(op._device.values()))
+        x = to_device(v)
+        out = torch.zeros(2, dtype=torch.float64, device="cuda")
+        h.rayleigh(0, x, out)
+        num, den = out.cpu().tolist()
+        return num / den

@@ -1,0 +1,86 @@
+"""ctypes binding of libmgcmt_b200.so (the C ABI in include/mgcmt_b200.h).
+
+The product path has no CPU fallback: if the library is missing, or no CUDA device is present
+when a compute entry point is called, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmgcmt_b200.so")
+
+OK = 0
+SMOOTH_WJACOBI, SMOOTH_RBGS, SMOOTH_GSLEX = 0, 1, 2
+
+_lib = None
+
+
+class MgcmtError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_D = C.c_double
+_I = C.c_int
+_LL = C.c_longlong
+
+# name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
+SIGNATURES = {
+    "mgcmt_abi_version": (_I, []),
+    "mgcmt_last_error": (C.c_char_p, []),
+    "mgcmt_launch_count": (_LL, []),
+    "mgcmt_profile_enable": (_I, [_I]),
+    "mgcmt_profile_read": (_I, [C.POINTER(_D), C.POINTER(_LL)]),
+    "mgcmt_hier_create": (_I, [C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "mgcmt_hier_destroy": (_I, [_P]),
+    "mgcmt_hier_num_levels": (_I, [_P]),
+    "mgcmt_hier_level_shape": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I)]),
+    "mgcmt_hier_level_coefs": (_I, [_P, _I, _P, _P]),
+    "mgcmt_apply": (_I, [_P, _I, _D, _P, _P, _P]),
+    "mgcmt_residual": (_I, [_P, _I, _D, _P, _P, _P, _P]),
+    "mgcmt_smooth": (_I, [_P, _I, _I, _D, _D, _I, _P, _P, _P, _P]),
+    "mgcmt_restrict": (_I, [_P, _I, _P, _P, _P]),
+    "mgcmt_residual_restrict": (_I, [_P, _I, _D, _P, _P, _P, _P]),
+    "mgcmt_prolong": (_I, [_P, _I, _P, _P, _P]),
+    "mgcmt_prolong_correct": (_I, [_P, _I, _P, _P, _P]),
+    "mgcmt_coarse_solve": (_I, [_P, _D, _P, _P, _P]),
+    "mgcmt_vcycle": (_I, [_P, _D, _I, _I, _I, _D, _P, _P, _P]),
+    "mgcmt_dot": (_I, [_LL, _P, _P, _P, _P]),
+    "mgcmt_rayleigh": (_I, [_P, _I, _P, _P, _P]),
+    "mgcmt_normalize": (_I, [_LL, _P, _P]),
+    "mgcmt_axpy_dev": (_I, [_LL, _P, _D, _P, _P, _P]),
+    "mgcmt_gramschmidt": (_I, [_LL, _I, _P, _I, _P]),
+}
+
+
+def load():
+    """Load the shared library (no GPU needed for this) and set the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MgcmtError(
+            "libmgcmt_b200.so is not built (%s). Run `python -m multigridcmt_b200.build`; there is no "
+            "CPU fallback for this path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = load().mgcmt_last_error()
+        raise MgcmtError("libmgcmt_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise MgcmtError("no CUDA device: the multigrid path runs on the GPU only (no CPU fallback)")
+    return torch

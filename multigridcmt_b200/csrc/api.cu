@@ -1,0 +1,542 @@
+// api.cu -- the C ABI declared in include/mgcmt_b200.h: grid hierarchy + V-cycle orchestration.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mgcmt_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace mgcmt;
+
+namespace mgcmt {
+long long g_launch_count = 0;
+}
+
+namespace {
+
+thread_local std::string g_err;
+
+// optional CUDA-event timing of the dominant kernel (finest-level smoother sweeps), for bench.py
+struct Profile {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;  // pairs
+  size_t used = 0;
+} g_prof;
+
+void prof_mark(cudaStream_t s) {
+  if (!g_prof.on) return;
+  if (g_prof.used == g_prof.pool.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    g_prof.pool.push_back(e);
+  }
+  cudaEventRecord(g_prof.pool[g_prof.used++], s);
+}
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return fail(MGCMT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// scratch for reductions that do not belong to a hierarchy (one per device, single-stream use)
+struct Scratch {
+  double *partials = nullptr;  // 16 * kReduceBlocks
+  double *scal = nullptr;      // 64 scalars
+};
+Scratch g_scratch[64];
+
+int get_scratch(Scratch **out) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(MGCMT_ERR_STATE, "device index out of range");
+  Scratch &s = g_scratch[dev];
+  if (!s.partials) {
+    CU(cudaMalloc(&s.partials, sizeof(double) * 16 * kReduceBlocks));
+    CU(cudaMalloc(&s.scal, sizeof(double) * 64));
+  }
+  *out = &s;
+  return MGCMT_OK;
+}
+
+struct Level {
+  LevelDev dev;
+  double *coef = nullptr;  // 6*nrows_glob + 6*ncols doubles
+  double *v = nullptr, *f = nullptr, *tmp = nullptr;
+  size_t n = 0;
+};
+
+struct InvEntry {
+  double shift;
+  double *inv;
+  uint64_t stamp;
+};
+
+}  // namespace
+
+struct mgcmt_hier {
+  int nlev = 0;
+  bool coarsen_rows = true;
+  std::vector<Level> lev;
+  std::vector<InvEntry> invs;
+  uint64_t clock = 0;
+  int *status = nullptr;  // device flag for the Gauss-Jordan
+};
+
+namespace {
+
+void set_coef_ptrs(Level &L) {
+  const int nr = L.dev.nrows_glob, nc = L.dev.ncols;
+  double *p = L.coef;
+  L.dev.ka_lo = p; p += nr;
+  L.dev.ka_di = p; p += nr;
+  L.dev.ka_up = p; p += nr;
+  L.dev.ma_lo = p; p += nr;
+  L.dev.ma_di = p; p += nr;
+  L.dev.ma_up = p; p += nr;
+  L.dev.kb_lo = p; p += nc;
+  L.dev.kb_di = p; p += nc;
+  L.dev.kb_up = p; p += nc;
+  L.dev.mb_lo = p; p += nc;
+  L.dev.mb_di = p; p += nc;
+  L.dev.mb_up = p; p += nc;
+}
+
+int check_level(const mgcmt_hier *h, int level) {
+  if (!h) return fail(MGCMT_ERR_ARG, "null hierarchy");
+  if (level < 0 || level >= h->nlev) return fail(MGCMT_ERR_ARG, "level out of range");
+  return MGCMT_OK;
+}
+
+int smooth_impl(mgcmt_hier *h, int level, int smoother, double shift, double omega, int nu, double *v,
+                const double *f, double *tmp, cudaStream_t s) {
+  Level &L = h->lev[level];
+  if (nu <= 0) return MGCMT_OK;
+  if (!tmp) tmp = L.tmp;
+  if (smoother == MGCMT_SMOOTH_WJACOBI) {
+    double *a = v, *b = tmp;
+    for (int it = 0; it < nu; ++it) {
+      if (level == 0) prof_mark(s);
+      CU(launch_jacobi_sweep(L.dev, shift, omega, a, f, b, nullptr, nullptr, s));
+      if (level == 0) prof_mark(s);
+      double *t = a; a = b; b = t;
+    }
+    if (a != v) CU(cudaMemcpyAsync(v, a, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
+    return MGCMT_OK;
+  }
+  if (smoother == MGCMT_SMOOTH_RBGS) {
+    if (level == 0) prof_mark(s);
+    CU(launch_rbgs(L.dev, shift, omega, nu, v, f, s));
+    if (level == 0) prof_mark(s);
+    return MGCMT_OK;
+  }
+  if (smoother == MGCMT_SMOOTH_GSLEX) {
+    CU(launch_gs_lex(L.dev, shift, omega, nu, v, f, tmp, s));
+    return MGCMT_OK;
+  }
+  return fail(MGCMT_ERR_ARG, "unknown smoother");
+}
+
+int get_inverse(mgcmt_hier *h, double shift, cudaStream_t s, double **out) {
+  for (auto &e : h->invs) {
+    if (memcmp(&e.shift, &shift, sizeof(double)) == 0) {
+      e.stamp = ++h->clock;
+      *out = e.inv;
+      return MGCMT_OK;
+    }
+  }
+  Level &L = h->lev[h->nlev - 1];
+  const int n = (int)L.n;
+  double *inv = nullptr;
+  const size_t kMaxCached = 16;
+  if (h->invs.size() >= kMaxCached) {  // evict the least recently used
+    size_t victim = 0;
+    for (size_t i = 1; i < h->invs.size(); ++i)
+      if (h->invs[i].stamp < h->invs[victim].stamp) victim = i;
+    CU(cudaStreamSynchronize(s));
+    inv = h->invs[victim].inv;
+    h->invs.erase(h->invs.begin() + victim);
+  } else {
+    CU(cudaMalloc(&inv, sizeof(double) * (size_t)n * n));
+  }
+  double *aug = nullptr, *mult = nullptr;
+  CU(cudaMalloc(&aug, sizeof(double) * (size_t)n * 2 * n));
+  CU(cudaMalloc(&mult, sizeof(double) * (n + 4)));
+  CU(cudaMemsetAsync(h->status, 0, sizeof(int), s));
+  CU(launch_build_dense(L.dev, shift, aug, s));
+  CU(launch_gauss_jordan(n, aug, h->status, mult, s));
+  CU(launch_extract_inverse(n, aug, inv, s));
+  int st = 0;
+  CU(cudaMemcpyAsync(&st, h->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaFree(aug));
+  CU(cudaFree(mult));
+  if (st != 0) {
+    cudaFree(inv);
+    return fail(MGCMT_ERR_NUMERIC, "coarsest operator is singular for this shift");
+  }
+  h->invs.push_back({shift, inv, ++h->clock});
+  *out = inv;
+  return MGCMT_OK;
+}
+
+int vcycle_level(mgcmt_hier *h, int l, double shift, int nu1, int nu2, int smoother, double omega, double *v,
+                 const double *f, cudaStream_t s) {
+  Level &L = h->lev[l];
+  if (l == h->nlev - 1) {
+    double *inv = nullptr;
+    int rc = get_inverse(h, shift, s, &inv);
+    if (rc) return rc;
+    // v may alias nothing of f here (distinct level buffers)
+    CU(launch_gemv((int)L.n, inv, f, v, s));
+    return MGCMT_OK;
+  }
+  Level &C = h->lev[l + 1];
+  int rc = smooth_impl(h, l, smoother, shift, omega, nu1, v, f, nullptr, s);
+  if (rc) return rc;
+  CU(launch_residual_restrict(L.dev, h->coarsen_rows, shift, v, f, C.f, s));
+  CU(cudaMemsetAsync(C.v, 0, sizeof(double) * C.n, s));
+  // coarse levels always run 4/4 (MGCMTSolver.py:320 does not forward nu1/nu2)
+  rc = vcycle_level(h, l + 1, shift, 4, 4, smoother, omega, C.v, C.f, s);
+  if (rc) return rc;
+  CU(launch_prolong(L.dev, h->coarsen_rows, true, C.v, v, s));
+  return smooth_impl(h, l, smoother, shift, omega, nu2, v, f, nullptr, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgcmt_abi_version(void) { return MGCMT_ABI_VERSION; }
+
+long long mgcmt_launch_count(void) { return mgcmt::g_launch_count; }
+
+int mgcmt_profile_enable(int on) {
+  g_prof.on = on != 0;
+  g_prof.used = 0;
+  return MGCMT_OK;
+}
+
+int mgcmt_profile_read(double *ms_total, long long *intervals) {
+  CU(cudaDeviceSynchronize());
+  double tot = 0.0;
+  long long cnt = 0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, g_prof.pool[i], g_prof.pool[i + 1]));
+    tot += ms;
+    ++cnt;
+  }
+  g_prof.used = 0;
+  if (ms_total) *ms_total = tot;
+  if (intervals) *intervals = cnt;
+  return MGCMT_OK;
+}
+const char *mgcmt_last_error(void) { return g_err.c_str(); }
+
+int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows, const double *h_row_lo,
+                      const double *h_row_di, const double *h_row_up, const double *h_col_lo,
+                      const double *h_col_di, const double *h_col_up, int lowest_level, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!out) return fail(MGCMT_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!h_row_lo || !h_row_di || !h_row_up || !h_col_lo || !h_col_di || !h_col_up)
+    return fail(MGCMT_ERR_ARG, "null coefficient array");
+  if (!is_pow2(ncols) || ncols < 2) return fail(MGCMT_ERR_ARG, "ncols must be a power of two >= 2");
+  if (!is_pow2(nrows)) return fail(MGCMT_ERR_ARG, "nrows must be a power of two (1 for 1-D)");
+  if (!coarsen_rows && nrows != 1) return fail(MGCMT_ERR_ARG, "coarsen_rows = 0 needs nrows == 1");
+  if (!is_pow2(lowest_level) || lowest_level < 2 || lowest_level > ncols)
+    return fail(MGCMT_ERR_ARG, "lowest_level must be a power of two in [2, ncols]");
+  int nlev = 1;
+  for (int c = ncols; c > lowest_level; c >>= 1) ++nlev;
+  if (coarsen_rows && (nrows >> (nlev - 1)) < 1)
+    return fail(MGCMT_ERR_ARG, "nrows too small for the requested number of levels");
+  {
+    const long long nc_rows = coarsen_rows ? (nrows >> (nlev - 1)) : nrows;
+    const long long ncoarse = nc_rows * lowest_level;
+    if (ncoarse > 4096) return fail(MGCMT_ERR_ARG, "coarsest level larger than 4096 unknowns is not supported");
+  }
+
+  mgcmt_hier *h = new mgcmt_hier();
+  h->nlev = nlev;
+  h->coarsen_rows = coarsen_rows != 0;
+  h->lev.resize(nlev);
+  auto bail = [&](int code, const std::string &msg) {
+    mgcmt_hier_destroy(h);
+    return fail(code, msg);
+  };
+#define CUB(expr)                                                                          \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) return bail(MGCMT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+  CUB(cudaMalloc(&h->status, sizeof(int)));
+  int nr = nrows, nc = ncols;
+  for (int l = 0; l < nlev; ++l) {
+    Level &L = h->lev[l];
+    L.dev.nrows = nr;
+    L.dev.ncols = nc;
+    L.dev.row0 = 0;
+    L.dev.nrows_glob = nr;
+    L.dev.five = (l == 0 || !coarsen_rows) ? 1 : 0;
+    L.n = (size_t)nr * nc;
+    CUB(cudaMalloc(&L.coef, sizeof(double) * (6 * (size_t)nr + 6 * (size_t)nc)));
+    set_coef_ptrs(L);
+    CUB(cudaMalloc(&L.tmp, sizeof(double) * L.n));
+    if (l > 0) {
+      CUB(cudaMalloc(&L.v, sizeof(double) * L.n));
+      CUB(cudaMalloc(&L.f, sizeof(double) * L.n));
+    }
+    if (l == 0) {
+      std::vector<double> host(6 * (size_t)nr + 6 * (size_t)nc, 0.0);
+      double *p = host.data();
+      for (int i = 0; i < nr; ++i) {
+        p[i] = (i > 0) ? h_row_lo[i] : 0.0;
+        p[nr + i] = h_row_di[i];
+        p[2 * nr + i] = (i + 1 < nr) ? h_row_up[i] : 0.0;
+        p[4 * nr + i] = 1.0;  // Ma = I
+      }
+      p += 6 * nr;
+      for (int j = 0; j < nc; ++j) {
+        p[j] = (j > 0) ? h_col_lo[j] : 0.0;
+        p[nc + j] = h_col_di[j];
+        p[2 * nc + j] = (j + 1 < nc) ? h_col_up[j] : 0.0;
+        p[4 * nc + j] = 1.0;  // Mb = I
+      }
+      CUB(cudaMemcpyAsync(L.coef, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, s));
+      CUB(cudaStreamSynchronize(s));  // host vector goes out of scope
+    } else {
+      Level &F = h->lev[l - 1];
+      const int nrf = F.dev.nrows_glob, ncf = F.dev.ncols;
+      if (coarsen_rows) {
+        CUB(launch_galerkin_tridiag(nrf, F.dev.ka_lo, F.dev.ka_di, F.dev.ka_up, (double *)L.dev.ka_lo,
+                                    (double *)L.dev.ka_di, (double *)L.dev.ka_up, s));
+        CUB(launch_galerkin_tridiag(nrf, F.dev.ma_lo, F.dev.ma_di, F.dev.ma_up, (double *)L.dev.ma_lo,
+                                    (double *)L.dev.ma_di, (double *)L.dev.ma_up, s));
+      } else {
+        CUB(cudaMemcpyAsync((void *)L.dev.ka_lo, F.dev.ka_lo, sizeof(double) * 6 * nrf, cudaMemcpyDeviceToDevice, s));
+      }
+      CUB(launch_galerkin_tridiag(ncf, F.dev.kb_lo, F.dev.kb_di, F.dev.kb_up, (double *)L.dev.kb_lo,
+                                  (double *)L.dev.kb_di, (double *)L.dev.kb_up, s));
+      CUB(launch_galerkin_tridiag(ncf, F.dev.mb_lo, F.dev.mb_di, F.dev.mb_up, (double *)L.dev.mb_lo,
+                                  (double *)L.dev.mb_di, (double *)L.dev.mb_up, s));
+    }
+    if (l + 1 < nlev) {
+      nc >>= 1;
+      if (coarsen_rows) nr >>= 1;
+    }
+  }
+  CUB(cudaStreamSynchronize(s));
+#undef CUB
+  *out = h;
+  return MGCMT_OK;
+}
+
+int mgcmt_hier_destroy(mgcmt_hier_t *h) {
+  if (!h) return MGCMT_OK;
+  for (auto &L : h->lev) {
+    cudaFree(L.coef);
+    cudaFree(L.v);
+    cudaFree(L.f);
+    cudaFree(L.tmp);
+  }
+  for (auto &e : h->invs) cudaFree(e.inv);
+  cudaFree(h->status);
+  delete h;
+  return MGCMT_OK;
+}
+
+int mgcmt_hier_num_levels(const mgcmt_hier_t *h) { return h ? h->nlev : 0; }
+
+int mgcmt_hier_level_shape(const mgcmt_hier_t *h, int level, int *nrows, int *ncols) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (nrows) *nrows = h->lev[level].dev.nrows;
+  if (ncols) *ncols = h->lev[level].dev.ncols;
+  return MGCMT_OK;
+}
+
+int mgcmt_hier_level_coefs(const mgcmt_hier_t *h, int level, double *h_rowcoef6, double *h_colcoef6) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  const Level &L = h->lev[level];
+  const size_t nr = L.dev.nrows_glob, nc = L.dev.ncols;
+  CU(cudaDeviceSynchronize());
+  if (h_rowcoef6) CU(cudaMemcpy(h_rowcoef6, L.coef, sizeof(double) * 6 * nr, cudaMemcpyDeviceToHost));
+  if (h_colcoef6) CU(cudaMemcpy(h_colcoef6, L.coef + 6 * nr, sizeof(double) * 6 * nc, cudaMemcpyDeviceToHost));
+  return MGCMT_OK;
+}
+
+int mgcmt_apply(mgcmt_hier_t *h, int level, double shift, const double *d_x, double *d_y, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (!d_x || !d_y) return fail(MGCMT_ERR_ARG, "null vector");
+  CU(launch_apply(h->lev[level].dev, shift, d_x, d_y, nullptr, nullptr, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_residual(mgcmt_hier_t *h, int level, double shift, const double *d_v, const double *d_f, double *d_r,
+                   void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (!d_v || !d_f || !d_r) return fail(MGCMT_ERR_ARG, "null vector");
+  CU(launch_residual(h->lev[level].dev, shift, d_v, d_f, d_r, nullptr, nullptr, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_smooth(mgcmt_hier_t *h, int level, int smoother, double shift, double omega, int nu, double *d_v,
+                 const double *d_f, double *d_tmp, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (!d_v || !d_f) return fail(MGCMT_ERR_ARG, "null vector");
+  return smooth_impl(h, level, smoother, shift, omega, nu, d_v, d_f, d_tmp, (cudaStream_t)stream);
+}
+
+int mgcmt_restrict(mgcmt_hier_t *h, int level, const double *d_fine, double *d_coarse, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  CU(launch_restrict(h->lev[level].dev, h->coarsen_rows, d_fine, d_coarse, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_residual_restrict(mgcmt_hier_t *h, int level, double shift, const double *d_v, const double *d_f,
+                            double *d_rcoarse, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  CU(launch_residual_restrict(h->lev[level].dev, h->coarsen_rows, shift, d_v, d_f, d_rcoarse,
+                              (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_prolong(mgcmt_hier_t *h, int level, const double *d_coarse, double *d_fine, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  CU(launch_prolong(h->lev[level].dev, h->coarsen_rows, false, d_coarse, d_fine, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_prolong_correct(mgcmt_hier_t *h, int level, const double *d_ecoarse, double *d_v, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  CU(launch_prolong(h->lev[level].dev, h->coarsen_rows, true, d_ecoarse, d_v, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double *d_v, void *stream) {
+  if (!h) return fail(MGCMT_ERR_ARG, "null hierarchy");
+  if (!d_f || !d_v || d_f == d_v) return fail(MGCMT_ERR_ARG, "need distinct non-null f and v");
+  double *inv = nullptr;
+  int rc = get_inverse(h, shift, (cudaStream_t)stream, &inv);
+  if (rc) return rc;
+  CU(launch_gemv((int)h->lev[h->nlev - 1].n, inv, d_f, d_v, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega, double *d_v,
+                 const double *d_f, void *stream) {
+  if (!h) return fail(MGCMT_ERR_ARG, "null hierarchy");
+  if (!d_v || !d_f || d_v == d_f) return fail(MGCMT_ERR_ARG, "need distinct non-null v and f");
+  if (nu1 < 0 || nu2 < 0) return fail(MGCMT_ERR_ARG, "negative sweep count");
+  return vcycle_level(h, 0, shift, nu1, nu2, smoother, omega, d_v, d_f, (cudaStream_t)stream);
+}
+
+int mgcmt_dot(long long n, const double *d_x, const double *d_y, double *d_out, void *stream) {
+  if (n < 0 || !d_x || !d_y || !d_out) return fail(MGCMT_ERR_ARG, "bad dot arguments");
+  Scratch *sc;
+  int rc = get_scratch(&sc);
+  if (rc) return rc;
+  CU(launch_dot(n, d_x, d_y, sc->partials, d_out, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (!d_x || !d_out2) return fail(MGCMT_ERR_ARG, "null vector");
+  Scratch *sc;
+  rc = get_scratch(&sc);
+  if (rc) return rc;
+  Level &L = h->lev[level];
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(launch_apply(L.dev, 0.0, d_x, L.tmp, nullptr, nullptr, s));
+  CU(launch_dot((long long)L.n, L.tmp, d_x, sc->partials, d_out2, s));
+  CU(launch_dot((long long)L.n, d_x, d_x, sc->partials, d_out2 + 1, s));
+  return MGCMT_OK;
+}
+
+int mgcmt_normalize(long long n, double *d_x, void *stream) {
+  if (n < 0 || !d_x) return fail(MGCMT_ERR_ARG, "bad normalize arguments");
+  Scratch *sc;
+  int rc = get_scratch(&sc);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(launch_dot(n, d_x, d_x, sc->partials, sc->scal, s));
+  CU(launch_scale_by_inv_norm(n, d_x, sc->scal, s));
+  return MGCMT_OK;
+}
+
+int mgcmt_axpy_dev(long long n, const double *d_alpha, double sign, const double *d_x, double *d_y,
+                   void *stream) {
+  if (n < 0 || !d_alpha || !d_x || !d_y) return fail(MGCMT_ERR_ARG, "bad axpy arguments");
+  CU(launch_axpy_dev(n, d_alpha, nullptr, sign, d_x, d_y, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_gramschmidt(long long n, int k, double *d_V, int modified, void *stream) {
+  if (n <= 0 || k <= 0 || !d_V) return fail(MGCMT_ERR_ARG, "bad gramschmidt arguments");
+  Scratch *sc;
+  int rc = get_scratch(&sc);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  double *scal = sc->scal;  // [0] sumsq / <q,q>, [1..16] dots, [32..] <u_i,u_i> (classical)
+  if (modified) {
+    // MGCMTProcessor.py:44-50
+    for (int i = 0; i < k; ++i) {
+      double *qi = d_V + (size_t)i * n;
+      CU(launch_dot(n, qi, qi, sc->partials, scal, s));
+      CU(launch_scale_by_inv_norm(n, qi, scal, s));
+      if (i + 1 == k) break;
+      CU(launch_dot(n, qi, qi, sc->partials, scal, s));  // <q_i, q_i> (the reference divides by it)
+      for (int j0 = i + 1; j0 < k; j0 += 16) {
+        const int m = (k - j0 < 16) ? (k - j0) : 16;
+        CU(launch_multidot(n, m, d_V + (size_t)j0 * n, n, qi, sc->partials, scal + 1, s));
+        for (int j = 0; j < m; ++j)
+          CU(launch_axpy_dev(n, scal + 1 + j, scal, -1.0, qi, d_V + (size_t)(j0 + j) * n, s));
+      }
+    }
+    return MGCMT_OK;
+  }
+  // classical: u_j = v_j - sum_{i<j} (<v_j,u_i>/<u_i,u_i>) u_i with the ORIGINAL v_j in every inner
+  // product, then normalise all columns (MGCMTProcessor.py:35-42)
+  if (k > 17) return fail(MGCMT_ERR_ARG, "classical Gram-Schmidt supports k <= 17");
+  double *uu = scal + 32;
+  for (int j = 0; j < k; ++j) {
+    double *vj = d_V + (size_t)j * n;
+    if (j > 0) {  // all coefficients first (they use the original v_j), then the subtractions in order
+      CU(launch_multidot(n, j, d_V, n, vj, sc->partials, scal + 1, s));
+      for (int i = 0; i < j; ++i)
+        CU(launch_axpy_dev(n, scal + 1 + i, uu + i, -1.0, d_V + (size_t)i * n, vj, s));
+    }
+    CU(launch_dot(n, vj, vj, sc->partials, uu + j, s));
+  }
+  for (int j = 0; j < k; ++j) CU(launch_scale_by_inv_norm(n, d_V + (size_t)j * n, uu + j, s));
+  return MGCMT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+// common.cuh -- shared device-side types for libmgcmt_b200 (sm_100a, fp64, HBM-bound path).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgcmt {
+
+// One grid level as the kernels see it.  Operator:  A = Ma (x) Kb + Ka (x) Mb  (tridiagonal factors;
+// row factors indexed by GLOBAL row, column factors by column), see include/mgcmt_b200.h.
+struct LevelDev {
+  int nrows;       // rows held locally
+  int ncols;       // columns (full width)
+  int row0;        // global index of local row 0 (0 unless slab-decomposed)
+  int nrows_glob;  // global row count
+  int five;        // 1: Ma = Mb = I (finest level: 5-point stencil)
+  const double *ka_lo, *ka_di, *ka_up, *ma_lo, *ma_di, *ma_up;  // length nrows_glob
+  const double *kb_lo, *kb_di, *kb_up, *mb_lo, *mb_di, *mb_up;  // length ncols
+};
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming (read-once) 16-byte load / store: keep L1 for the halo re-reads
+__device__ __forceinline__ double2 ld_stream2(const double *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream2(double *p, double2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+}  // namespace mgcmt

@@ -1,0 +1,58 @@
+// kernels.h -- host-side launchers of the kernels in this directory (internal; the public surface is
+// include/mgcmt_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace mgcmt {
+
+enum { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_APPLY = 2 };
+
+// number of kernels this library has launched since it was loaded (reported by bench.py as gpu_launches)
+extern long long g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+// stencil.cu
+cudaError_t launch_jacobi_sweep(const LevelDev &L, double shift, double omega, const double *v_in,
+                                const double *f, double *v_out, const double *halo_top,
+                                const double *halo_bot, cudaStream_t s);
+cudaError_t launch_residual(const LevelDev &L, double shift, const double *v, const double *f, double *r,
+                            const double *halo_top, const double *halo_bot, cudaStream_t s);
+cudaError_t launch_apply(const LevelDev &L, double shift, const double *x, double *y, const double *halo_top,
+                         const double *halo_bot, cudaStream_t s);
+
+// transfer.cu
+cudaError_t launch_galerkin_tridiag(int n_fine, const double *lo, const double *di, const double *up,
+                                    double *clo, double *cdi, double *cup, cudaStream_t s);
+cudaError_t launch_restrict(const LevelDev &Lf, bool coarsen_rows, const double *fine, double *coarse,
+                            cudaStream_t s);
+cudaError_t launch_residual_restrict(const LevelDev &Lf, bool coarsen_rows, double shift, const double *v,
+                                     const double *f, double *rc, cudaStream_t s);
+cudaError_t launch_prolong(const LevelDev &Lf, bool coarsen_rows, bool accumulate, const double *coarse,
+                           double *fine, cudaStream_t s);
+
+// gs.cu
+cudaError_t launch_rbgs(const LevelDev &L, double shift, double omega, int nu, double *v, const double *f,
+                        cudaStream_t s);
+cudaError_t launch_gs_lex(const LevelDev &L, double shift, double omega, int nu, double *v, const double *f,
+                          double *scratch, cudaStream_t s);
+
+// coarse.cu
+cudaError_t launch_build_dense(const LevelDev &L, double shift, double *aug, cudaStream_t s);
+cudaError_t launch_gauss_jordan(int n, double *aug, int *status, double *mult, cudaStream_t s);
+cudaError_t launch_extract_inverse(int n, const double *aug, double *inv, cudaStream_t s);
+cudaError_t launch_gemv(int n, const double *inv, const double *x, double *y, cudaStream_t s);
+
+// reduce.cu
+constexpr int kReduceBlocks = 592;  // 148 SMs x 4
+cudaError_t launch_dot(long long n, const double *x, const double *y, double *partials, double *out,
+                       cudaStream_t s);
+// out[m] = <x0 + m*stride, y>, m < M <= 16; partials: M * kReduceBlocks doubles of scratch
+cudaError_t launch_multidot(long long n, int M, const double *x0, long long stride, const double *y,
+                            double *partials, double *out, cudaStream_t s);
+cudaError_t launch_scale_by_inv_norm(long long n, double *x, const double *sumsq, cudaStream_t s);
+cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *denom, double sign,
+                            const double *x, double *y, cudaStream_t s);
+cudaError_t launch_scale_to(long long n, const double *x, const double *sumsq, double *y, cudaStream_t s);
+
+}  // namespace mgcmt

@@ -1,0 +1,139 @@
+// reduce.cu -- deterministic reductions and the vector updates around them.
+//
+// Replaces the numpy dots/norms of the reference's drivers and MGCMTProcessor:
+//   Rayleigh quotient  v^T (H v) / v^T v          e.g. 2DPotGS.py:103, MGCMTSolver.py:19
+//   normalisation      w / ||w||                   e.g. 2DPotGS.py:96, MGCMTProcessor.py:52-63
+//   projections        (<v,u>/<u,u>) u             MGCMTProcessor.py:10-20
+// Every reduction is a fixed two-stage tree (per-thread grid-stride partial -> warp shuffle -> block ->
+// ordered sum of the block partials), so a result depends only on n, never on scheduling; repeated runs
+// and different GPU counts give bit-identical scalars ("Reductions").
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgcmt {
+
+constexpr int kRedThreads = 256;
+
+// partials[m * gridDim.x + b] = sum over this block's elements of X_m[i] * y[i],  X_m = x0 + m*stride
+template <int M>
+__global__ void __launch_bounds__(kRedThreads)
+multidot_partial_kernel(long long n, const double *__restrict__ x0, long long stride,
+                        const double *__restrict__ y, double *__restrict__ partials) {
+  double acc[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) acc[m] = 0.0;
+  const long long n2 = n >> 1;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += step) {
+    const double2 yy = reinterpret_cast<const double2 *>(y)[i];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const double2 xx = reinterpret_cast<const double2 *>(x0 + m * stride)[i];
+      acc[m] += xx.x * yy.x;
+      acc[m] += xx.y * yy.y;
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) acc[m] += x0[m * stride + n - 1] * y[n - 1];
+  }
+  __shared__ double sm[M][kRedThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const double s = warp_sum(acc[m]);
+    if (lane == 0) sm[m][w] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < M) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedThreads / 32; ++k) s += sm[threadIdx.x][k];
+    partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// out[m] = ordered tree sum of partials[m*B .. m*B+B)
+__global__ void __launch_bounds__(256) finish_kernel(int B, const double *__restrict__ partials,
+                                                     double *__restrict__ out) {
+  __shared__ double sm[256];
+  const int m = blockIdx.x;
+  double s = 0.0;
+  for (int b = threadIdx.x; b < B; b += 256) s += partials[(size_t)m * B + b];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[m] = sm[0];
+}
+
+static int blocks_for(long long n) {
+  long long b = (n / 2 + kRedThreads - 1) / kRedThreads;
+  if (b < 1) b = 1;
+  if (b > kReduceBlocks) b = kReduceBlocks;
+  return (int)b;
+}
+
+cudaError_t launch_multidot(long long n, int M, const double *x0, long long stride, const double *y,
+                            double *partials, double *out, cudaStream_t s) {
+  const int B = blocks_for(n);
+  switch (M) {
+#define CASE(MM)                                                                                 \
+  case MM:                                                                                       \
+    multidot_partial_kernel<MM><<<B, kRedThreads, 0, s>>>(n, x0, stride, y, partials);           \
+    break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+    CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
+#undef CASE
+    default:
+      return cudaErrorInvalidValue;
+  }
+  finish_kernel<<<M, 256, 0, s>>>(B, partials, out);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dot(long long n, const double *x, const double *y, double *partials, double *out,
+                       cudaStream_t s) {
+  return launch_multidot(n, 1, x, 0, y, partials, out, s);
+}
+
+// x[i] = x[i] / sqrt(*sumsq)     (division, as numpy does)
+__global__ void scale_by_inv_norm_kernel(long long n, const double *__restrict__ x, const double *__restrict__ sumsq,
+                                         double *__restrict__ y) {
+  const double nrm = sqrt(*sumsq);
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += step) y[i] = x[i] / nrm;
+}
+cudaError_t launch_scale_to(long long n, const double *x, const double *sumsq, double *y, cudaStream_t s) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  scale_by_inv_norm_kernel<<<(int)b, 256, 0, s>>>(n, x, sumsq, y);
+  count_launch();
+  return cudaGetLastError();
+}
+cudaError_t launch_scale_by_inv_norm(long long n, double *x, const double *sumsq, cudaStream_t s) {
+  return launch_scale_to(n, x, sumsq, x, s);
+}
+
+// y += sign * (alpha / denom) * x      alpha, denom on the device (denom may be null => 1)
+__global__ void axpy_dev_kernel(long long n, const double *__restrict__ alpha, const double *__restrict__ denom,
+                                double sign, const double *__restrict__ x, double *__restrict__ y) {
+  double a = *alpha;
+  if (denom) a = a / *denom;
+  a *= sign;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += step) y[i] += a * x[i];
+}
+cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *denom, double sign,
+                            const double *x, double *y, cudaStream_t s) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  axpy_dev_kernel<<<(int)b, 256, 0, s>>>(n, alpha, denom, sign, x, y);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace mgcmt

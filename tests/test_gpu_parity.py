@@ -1,0 +1,398 @@
+"""GPU: the CUDA path (through the C ABI / the drop-in classes) against the CPU oracle on the same
+seeded inputs, and against the real-reference golden fixtures.
+
+Tolerances (north_star): Jacobi, residual, restriction, interpolation, RQ: 1e-12 relative.  Cycles that
+contain the exact coarsest solve of an indefinite shifted operator are compared at 1e-10 (the
+oracle itself only agrees with the real reference to ~1e-12 there, tests/test_oracle_golden.py).
+Red-black GS has no reference; it is checked against its CPU twin and on converged eigenvalues.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mgcmt_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=float).reshape(-1)
+    b = np.asarray(b, dtype=float).reshape(-1)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def prod():
+    from multigridcmt_b200 import MGCMTProcessor, MGCMTSolver, MGCMTStencilMaker
+    return MGCMTStencilMaker(), MGCMTSolver(), MGCMTProcessor()
+
+
+@pytest.fixture(scope="module")
+def o():
+    return orc.StencilMaker(), orc.Solver(), orc.Processor()
+
+
+def rand(n, seed):
+    return np.random.RandomState(seed).random_sample(n)
+
+
+def dev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def level_matrix(c, five):
+    """Dense level operator from the 12 factor arrays the device built."""
+    def tri(lo, di, up):
+        n = len(di)
+        return np.diag(di) + np.diag(lo[1:], -1) + np.diag(up[:-1], 1)
+    ka, ma = tri(c["ka_lo"], c["ka_di"], c["ka_up"]), tri(c["ma_lo"], c["ma_di"], c["ma_up"])
+    kb, mb = tri(c["kb_lo"], c["kb_di"], c["kb_up"]), tri(c["mb_lo"], c["mb_di"], c["mb_up"])
+    if five:
+        ma, mb = np.eye(len(ma)), np.eye(len(mb))
+    return np.kron(ma, kb) + np.kron(ka, mb)
+
+
+def oracle_levels(o, H, N, dim, nlev):
+    sm = o[0]
+    mats = [sp.csc_matrix(H)]
+    Rs, Ps = [], []
+    g = N
+    for _ in range(nlev - 1):
+        R = sm.restriction(g, g // 2, dimension=dim)
+        P = sm.interpolation(g // 2, g, dimension=dim)
+        mats.append(sp.csc_matrix(R * mats[-1] * P))
+        Rs.append(R)
+        Ps.append(P)
+        g //= 2
+    return mats, Rs, Ps
+
+
+# ---------------------------------------------------------------------------------------------------
+# hierarchy: Galerkin coarse operators in separable form == R A P of the reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,N,low", [("2d", 32, 2), ("1d", 64, 2)])
+def test_galerkin_hierarchy_matches_rap(T, prod, o, dim, N, low):
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    from multigridcmt_b200.operators import recognise
+    sm = prod[0]
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, dim)
+    h = get_hierarchy(recognise(H, dim), low)
+    mats, _, _ = oracle_levels(o, H, N, dim, h.num_levels)
+    for l in range(h.num_levels):
+        c = h.level_coefs(l)
+        if dim == "1d":
+            got = np.diag(c["kb_di"]) + np.diag(c["kb_lo"][1:], -1) + np.diag(c["kb_up"][:-1], 1)
+        else:
+            got = level_matrix(c, l == 0)
+        want = mats[l].toarray()
+        assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want)), (dim, l)
+
+
+# ---------------------------------------------------------------------------------------------------
+# single operators on every level, against the oracle applied to the explicit matrices
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,N,shift", [("2d", 64, 0.0), ("2d", 64, 4.38639582), ("2d", 256, 1.7), ("1d", 256, 3.9),
+                                         ("1d", 4096, 0.0)])
+def test_level_operators_match_oracle(T, prod, o, dim, N, shift):
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    from multigridcmt_b200.operators import recognise
+    sm = prod[0]
+    osolver = o[1]
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, dim)
+    low = 8 if dim == "2d" else 16
+    h = get_hierarchy(recognise(H, dim), low)
+    nlev_test = min(h.num_levels, 4)
+    mats, Rs, Ps = oracle_levels(o, H, N, dim, nlev_test)
+    for l in range(nlev_test):
+        n = h.level_size(l)
+        A = mats[l] - sp.eye(n) * shift
+        v = rand(n, 10 + l); f = rand(n, 20 + l)
+        dv, df = dev(T, v), dev(T, f)
+        out = T.empty_like(dv)
+        # apply / residual
+        assert rel(h.apply(l, shift, dv, out).cpu().numpy(), A @ v) < RTOL
+        assert rel(h.residual(l, shift, dv, df, out).cpu().numpy(), f - A @ v) < RTOL
+        # weighted Jacobi, even and odd sweep counts, non-default omega
+        for nu, om in ((1, 2. / 3.), (4, 2. / 3.), (3, 0.8)):
+            w = dv.clone()
+            h.smooth(l, _lib.SMOOTH_WJACOBI, shift, om, nu, w, df)
+            assert rel(w.cpu().numpy(), osolver.wjacobi(v.copy(), f.copy(), A, nu=nu, omega=om)) < RTOL, (l, nu)
+        # red-black GS against its CPU twin
+        w = dv.clone()
+        h.smooth(l, _lib.SMOOTH_RBGS, shift, 1.0, 2, w, df)
+        assert rel(w.cpu().numpy(), osolver.rbgs(v.copy(), f.copy(), A, nu=2, omega=1.0, dimension=dim)) < 1e-11, l
+        if l + 1 < nlev_test:
+            nc = h.level_size(l + 1)
+            R, P = Rs[l], Ps[l]
+            rc = T.empty(nc, dtype=T.float64, device="cuda")
+            assert rel(h.restrict(l, dv, rc).cpu().numpy(), R @ v) < RTOL
+            assert rel(h.residual_restrict(l, shift, dv, df, rc).cpu().numpy(), R @ (f - A @ v)) < RTOL
+            e = rand(nc, 30 + l)
+            de = dev(T, e)
+            assert rel(h.prolong(l, de, out).cpu().numpy(), P @ e) < RTOL
+            w = dv.clone()
+            assert rel(h.prolong_correct(l, de, w).cpu().numpy(), v + P @ e) < RTOL
+
+
+@pytest.mark.parametrize("dim,N,low,shift", [("2d", 32, 8, 1.76659015), ("2d", 32, 8, 7.00620149), ("2d", 16, 2, 0.0),
+                                             ("1d", 64, 16, 3.9), ("2d", 64, 32, 4.38639582)])
+def test_coarse_solve_matches_spsolve(T, prod, o, dim, N, low, shift):
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    from multigridcmt_b200.operators import recognise
+    import scipy.sparse.linalg as spla
+    sm = prod[0]
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, dim)
+    h = get_hierarchy(recognise(H, dim), low)
+    mats, _, _ = oracle_levels(o, H, N, dim, h.num_levels)
+    n = h.level_size(h.num_levels - 1)
+    A = sp.csc_matrix(mats[-1] - sp.eye(n) * shift)
+    f = rand(n, 5)
+    got = h.coarse_solve(shift, dev(T, f), T.empty(n, dtype=T.float64, device="cuda")).cpu().numpy()
+    want = spla.spsolve(A, f)
+    cond = np.linalg.cond(A.toarray())
+    assert rel(got, want) < 50 * cond * np.finfo(float).eps, (rel(got, want), cond)
+
+
+# ---------------------------------------------------------------------------------------------------
+# lexicographic Gauss-Seidel / SOR (reference semantics incl. quirk Q6)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,n,dim", [("1d64", 64, "1d"), ("1d64s", 64, "1d"), ("2d16", 16, "2d"), ("2d16s", 16, "2d")])
+def test_smoothers_match_reference_golden(prod, golden, tag, n, dim):
+    sm, s, _ = prod
+    nn = n if dim == "1d" else n * n
+    H = (-1. / np.pi ** 2) * sm.laplacian(n, dim)
+    A = H - sp.eye(nn) * float(golden["sm_%s_shift" % tag])
+    v0 = golden["sm_%s_v0" % tag]
+    f = golden["sm_%s_f" % tag]
+    out = s.wjacobi(v0.copy(), f.copy(), A, nu=3)
+    assert out.shape == (nn, 1)
+    assert rel(out, golden["sm_%s_wjacobi" % tag]) < RTOL
+    assert rel(s.wjacobi(v0.copy(), f.copy(), A, nu=2, omega=0.8), golden["sm_%s_wjacobi_w08" % tag]) < RTOL
+    assert rel(s.gseidel(v0.copy(), f.copy(), A, nu=3), golden["sm_%s_gseidel" % tag]) < 1e-11
+    assert rel(s.sor(v0.copy(), f.copy(), A, nu=3, omega=1.3), golden["sm_%s_sor" % tag]) < 1e-11
+
+
+def test_known_answers_through_dropin(prod):
+    """The reference's own UnitTests scripts, run against the drop-in classes."""
+    sm, s, _ = prod
+    L = sm.laplacian(16)
+
+    def five(fn):
+        x = np.ones(16)
+        for _ in range(5):
+            x = fn(x, np.zeros(16), L)
+        return np.linalg.norm(x)
+    assert abs(five(lambda x, f, A: s.wjacobi(x, f, A, nu=4)) - 2.94959) < 5e-6        # wjacobiTest.py:25
+    assert abs(five(lambda x, f, A: s.gseidel(x, f, A, nu=4)) - 1.88358) < 5e-6        # gseidelTest.py:25
+    assert abs(five(lambda x, f, A: s.sor(x, f, A, nu=4, omega=2. / 3.)) - 2.63327) < 5e-6  # sorTest.py:25
+    assert abs(np.linalg.norm(s.vcycle(np.ones(16), np.zeros(16), L, sm, nu1=4, nu2=4)) - 0.17756) < 5e-6
+    assert abs(np.linalg.norm(s.twogrid(np.ones(16), np.zeros(16), L, sm, 4, 4)) - 0.04979) < 5e-6
+    L4 = sm.laplacian(4)
+    want = np.array([-0.382301639189, -0.0257586075778, -0.840838733687])  # vcycle_matrixTest.py:27 (corrected)
+    for fn in (lambda x, f: s.vcycle(x, f, L4, sm), lambda x, f: s.twogrid(x, f, L4, sm)):
+        got = []
+        for i in range(3):
+            x = fn(np.ones(4) * 4, np.ones(4) * i)
+            got.append(np.dot(x, L4.dot(x)))
+        assert np.allclose(got, want, rtol=0, atol=5e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# V-cycles against the real reference (golden) and against the oracle at larger sizes
+# ---------------------------------------------------------------------------------------------------
+VC_TAGS = ["1d64", "1d64s", "1d256s_l8", "1d64_gs", "2d16_l8", "2d32_l8", "2d32_l2", "2d32_l8_nu", "2d64_l8",
+           "2d16_l8_gs"]
+
+
+@pytest.mark.parametrize("tag", VC_TAGS)
+def test_vcycle_matches_reference_golden(prod, golden, tag):
+    sm, s, _ = prod
+    n, dim, shift, lowest, nu1, nu2 = golden["vc_%s_meta" % tag]
+    n, lowest, nu1, nu2 = int(n), int(lowest), int(nu1), int(nu2)
+    dim = "1d" if dim == 1 else "2d"
+    H = (-1. / np.pi ** 2) * sm.laplacian(n, dim)
+    kw = {"smoother": s.gseidel} if tag.endswith("_gs") else {}
+    v0 = golden["vc_%s_v0" % tag].copy()
+    f = golden["vc_%s_f" % tag].copy()
+    out = s.vcycle(v0, f, H, sm, nu1=nu1, nu2=nu2, shift=shift, lowest_level=lowest, dimension=dim, **kw)
+    nn = n if dim == "1d" else n * n
+    assert isinstance(out, np.ndarray) and out.shape == (nn,)
+    assert v0.shape == (nn, 1) and f.shape == (nn, 1)   # the reference's in-place reshape side effect
+    assert rel(out, golden["vc_%s_out" % tag]) < 1e-10, rel(out, golden["vc_%s_out" % tag])
+
+
+@pytest.mark.parametrize("dim,N,low,shift", [("2d", 128, 8, 4.38639582), ("2d", 256, 8, 1.76659015), ("2d", 256, 32, 0.0),
+                                             ("1d", 1024, 8, 8.9), ("1d", 8192, 16, 0.0)])
+def test_vcycle_matches_oracle(prod, o, dim, N, low, shift):
+    sm, s, _ = prod
+    osm, os_, _ = o
+    nn = N if dim == "1d" else N * N
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, dim)
+    v0 = rand(nn, 1); f = rand(nn, 2)
+    got = s.vcycle(v0.copy(), f.copy(), H, sm, shift=shift, lowest_level=low, dimension=dim)
+    want = os_.vcycle(v0.copy(), f.copy(), H, osm, shift=shift, lowest_level=low, dimension=dim)
+    assert rel(got, want) < 1e-10, rel(got, want)
+
+
+def test_vcycle_api_conventions(prod, capsys, T):
+    sm, s, _ = prod
+    L = sm.laplacian(2)
+    out = s.vcycle(np.ones(2), np.ones(2), L, sm)            # quirk Q7: coarsest size -> (n, 1)
+    assert out.shape == (2, 1)
+    assert np.allclose(L @ out[:, 0], np.ones(2))
+    assert s.vcycle(np.ones(1), np.ones(1), sm.laplacian(1), sm) is None
+    assert "not a power of 2" in capsys.readouterr().out
+    with pytest.raises(NotImplementedError):
+        s.vcycle(np.ones(16), np.ones(16), sm.laplacian(16), sm, smoother=lambda *a, **k: None)
+    with pytest.raises(NotImplementedError):
+        s.vcycle(np.ones(16), np.ones(16), sm.laplacian(16), object())
+    # device tensors stay on the device
+    H = (-1. / np.pi ** 2) * sm.laplacian(32, "2d")
+    v = T.zeros(1024, dtype=T.float64, device="cuda")
+    f = T.ones(1024, dtype=T.float64, device="cuda")
+    w = s.vcycle(v, f, H, sm, shift=1.7, lowest_level=8, dimension="2d")
+    assert w.is_cuda and w.shape == (1024,)
+    assert float(v.abs().sum()) == 0.0            # inputs untouched
+    ref = s.vcycle(np.zeros(1024), np.ones(1024), H, sm, shift=1.7, lowest_level=8, dimension="2d")
+    assert np.array_equal(w.cpu().numpy(), ref)   # same kernels, same bits
+
+
+def test_twogrid_matches_reference_golden(prod, golden):
+    sm, s, _ = prod
+    H = (-1. / np.pi ** 2) * sm.laplacian(64)
+    out = s.twogrid(golden["tg_1d64_v0"].copy(), golden["tg_1d64_f"].copy(), H, sm, nu1=3, nu2=2, shift=3.9)
+    assert rel(out, golden["tg_1d64_out"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag", ["1d64", "2d16"])
+def test_vcycle_matrix_matches_reference_golden(prod, golden, tag):
+    sm, s, _ = prod
+    n, dim, lowest = golden["vm_%s_meta" % tag]
+    dim = "1d" if dim == 1 else "2d"
+    H = (-1. / np.pi ** 2) * sm.laplacian(int(n), dim)
+    out = s.vcycle_matrix(golden["vm_%s_v0" % tag].copy(), golden["vm_%s_f" % tag].copy(), H, sm,
+                          shifts=golden["vm_%s_shifts" % tag], lowest_level=int(lowest), dimension=dim)
+    assert out.shape == golden["vm_%s_out" % tag].shape
+    assert rel(out, golden["vm_%s_out" % tag]) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------
+# Gram-Schmidt / normalise / dots
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["ill", "well", "rnd"])
+def test_gramschmidt_matches_reference_golden(prod, golden, tag):
+    _, _, p = prod
+    a = golden["gs_%s_in" % tag]
+    assert np.allclose(p.gramschmidt(a.copy()), golden["gs_%s_mgs" % tag], rtol=0, atol=1e-14)
+    assert np.allclose(p.gramschmidt(a.copy(), modified=0), golden["gs_%s_cgs" % tag], rtol=0, atol=1e-14)
+    assert np.allclose(p.normalize(a.copy()), golden["gs_%s_norm" % tag], rtol=0, atol=1e-15)
+
+
+def test_gramschmidt_large_and_deterministic(T, prod, o):
+    _, _, p = prod
+    n, k = 1 << 18, 6
+    a = rand(n * k, 3).reshape(n, k)
+    q1 = p.gramschmidt(a.copy())
+    q2 = p.gramschmidt(a.copy())
+    assert np.array_equal(q1, q2)                              # fixed reduction tree
+    assert rel(q1, o[2].gramschmidt(a.copy())) < 1e-12
+    assert np.max(np.abs(q1.T @ q1 - np.eye(k))) < 1e-13
+    proj = p.projection(a[:, 0].copy(), a[:, 1].copy())
+    assert rel(proj, o[2].projection(a[:, 0], a[:, 1])) < 1e-13
+    oc = p.orthogonality_check(q1)
+    assert np.max(np.abs(oc - np.eye(k))) < 1e-13
+
+
+def test_rayleigh_quotient(prod):
+    sm, s, _ = prod
+    N = 128
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    v = rand(N * N, 11)
+    want = np.dot(v, H @ v) / np.dot(v, v)
+    assert abs(s.rayleigh_quotient(H, v, "2d") - want) < 1e-12 * abs(want)
+    ev = orc.well_eigenvector_2d(N, 1, 2)
+    assert abs(s.rayleigh_quotient(H, ev, "2d") - orc.well_eigenvalue_2d(N, 1, 2)) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------------
+# the shift-method outer loop of 2DPotGS.py:79-105 through the drop-in classes
+# ---------------------------------------------------------------------------------------------------
+def test_shift_method_loop_matches_reference_golden(prod, golden):
+    sm, s, p = prod
+    N, N0, iters, lowest = [int(x) for x in golden["sh_meta"]]
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    V = golden["sh_V0"].copy()
+    shifts = golden["sh_shifts"]
+    lam = np.zeros((iters, 4))
+    for it in range(iters):
+        for c in range(4):
+            w = s.vcycle(np.zeros((N * N, 1)), V[:, c].copy(), H, sm, shift=shifts[c], dimension="2d",
+                         lowest_level=lowest)
+            V[:, c] = w / np.linalg.norm(w)
+            lam[it, c] = np.dot(V[:, c], H.dot(V[:, c]))
+        V = p.gramschmidt(V)
+    assert np.allclose(lam, golden["sh_lambda"], rtol=1e-10, atol=0)
+    assert rel(V[:, 0], golden["sh_V"][:, 0]) < 1e-8
+    assert rel(V[:, 3], golden["sh_V"][:, 3]) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------------
+# full-size properties (no CPU answer exists at these sizes): closed-form spectrum, linearity
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [1024, 4096])
+def test_full_size_properties(T, prod, N):
+    sm, s, _ = prod
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    h = get_hierarchy(H, 8)
+    n = N * N
+    # (1) the closed-form eigenvector is an eigenvector of the device operator
+    lam = orc.well_eigenvalue_2d(N, 2, 1)
+    ev = dev(T, orc.well_eigenvector_2d(N, 2, 1))
+    out = T.empty_like(ev)
+    h.apply(0, lam, ev, out)
+    assert float(out.norm()) < 1e-9
+    # (2) the V-cycle is affine in f and linear in (v0, f): cycle(a v, a f) == a cycle(v, f)
+    g = T.Generator(device="cuda"); g.manual_seed(0)
+    f = T.rand(n, dtype=T.float64, device="cuda", generator=g)
+    z = T.zeros(n, dtype=T.float64, device="cuda")
+    w1 = s.vcycle(z, f, H, sm, shift=1.7, lowest_level=8, dimension="2d")
+    w2 = s.vcycle(z, 2.0 * f, H, sm, shift=1.7, lowest_level=8, dimension="2d")
+    assert float((w2 - 2.0 * w1).norm() / w2.norm()) < 1e-13
+    # (3) a V-cycle reduces the residual of (H - shift) w = f (shift below the spectrum: SPD problem)
+    w = s.vcycle(z, f, H, sm, shift=0.0, lowest_level=8, dimension="2d")
+    r = T.empty_like(f)
+    h.residual(0, 0.0, w, f, r)
+    assert float(r.norm() / f.norm()) < 0.2
+    # (4) inverse iteration with the V-cycle converges to the closed-form eigenvalue
+    lam11 = orc.well_eigenvalue_2d(N, 1, 1)
+    v = dev(T, np.kron(orc.well_eigenvector_1d(N, 1), orc.well_eigenvector_1d(N, 1))
+            + 1e-3 * np.random.RandomState(1).random_sample(n))
+    out2 = T.zeros(2, dtype=T.float64, device="cuda")
+    for _ in range(3):
+        w = s.vcycle(z, v, H, sm, shift=orc.well_eigenvalue_2d(16, 1, 1), lowest_level=8, dimension="2d")
+        v = w / w.norm()
+    h.rayleigh(0, v, out2)
+    num, den = out2.cpu().tolist()
+    assert abs(num / den - lam11) < 1e-6
+    # red-black GS reaches the same eigenvalue (north_star: judged on converged eigenvalues)
+    v = dev(T, np.kron(orc.well_eigenvector_1d(N, 1), orc.well_eigenvector_1d(N, 1))
+            + 1e-3 * np.random.RandomState(1).random_sample(n))
+    for _ in range(3):
+        w = s.vcycle(z, v, H, sm, shift=orc.well_eigenvalue_2d(16, 1, 1), lowest_level=8, dimension="2d",
+                     smoother=s.rbgs)
+        v = w / w.norm()
+    h.rayleigh(0, v, out2)
+    num, den = out2.cpu().tolist()
+    assert abs(num / den - lam11) < 1e-6

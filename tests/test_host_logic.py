@@ -1,0 +1,134 @@
+"""CPU: host-side logic of the drop-in (no GPU compute): operator recognition, the stencil-maker
+mirror, the C-ABI library's symbols, and the loud-failure contract."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mgcmt_oracle as orc
+from multigridcmt_b200 import MGCMTStencilMaker, SeparableOperator, UnsupportedOperator
+from multigridcmt_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def same(a, b):
+    return (sp.csc_matrix(a) != sp.csc_matrix(b)).nnz == 0
+
+
+def test_stencil_maker_mirror_equals_oracle_and_reference(golden):
+    sm, osm = MGCMTStencilMaker(), orc.StencilMaker()
+    for a, b in [(8, 16), (4, 16), (2, 4), (16, 64)]:
+        assert same(sm.interpolation(a, b), osm.interpolation(a, b))
+        assert same(sm.restriction(b, a), osm.restriction(b, a))
+    assert same(sm.interpolation(4, 8, "2d"), osm.interpolation(4, 8, "2d"))
+    assert same(sm.restriction(8, 4, "2d"), osm.restriction(8, 4, "2d"))
+    assert np.array_equal(sm.restriction(16, 8).toarray(), golden["op_R_16_8"])
+    assert np.array_equal(sm.interpolation(8, 16).toarray(), golden["op_P_8_16"])
+    assert np.array_equal(sm.interpolation(4, 16).toarray(), golden["op_P_4_16"])
+    assert np.array_equal(sm.laplacian(16).toarray(), golden["op_L_16"])
+    assert np.array_equal(sm.laplacian(8, "2d").toarray(), golden["op_L2d_8"])
+    assert np.array_equal(sm.interpolation(4, 8, "2d").toarray(), golden["op_P2d_4_8"])
+    assert np.array_equal(sm.restriction(8, 4, "2d").toarray(), golden["op_R2d_8_4"])
+    assert sm.laplacian(8).format == "csc" and sm.interpolation(4, 8).format == "csc"
+
+
+def test_stencil_maker_error_convention(capsys):
+    sm = MGCMTStencilMaker()
+    assert sm.interpolation(16, 8) is None
+    assert sm.interpolation(6, 16) is None
+    assert sm.interpolation(4, 12) is None
+    assert sm.restriction(8, 16) is None
+    assert sm.restriction(16, 6) is None
+    out = capsys.readouterr().out
+    assert out.count("!") == 5
+
+
+@pytest.mark.parametrize("dim,n", [("1d", 32), ("2d", 16)])
+def test_recognise_well_operator(dim, n):
+    sm = MGCMTStencilMaker()
+    H = (-1. / np.pi ** 2) * sm.laplacian(n, dim)
+    op = SeparableOperator.from_sparse(H, dim)
+    assert abs(op.tocsc() - H).max() == 0.0
+    nn = n if dim == "1d" else n * n
+    Hs = H - sp.eye(nn) * 4.386
+    ops = SeparableOperator.from_sparse(Hs, dim)
+    assert abs(ops.tocsc() - Hs).max() < 1e-13
+    # matrix-free constructor gives the same operator as recognising the scipy matrix
+    mf = (-1. / np.pi ** 2) * sm.laplacian(n, dim, matrix_free=True)
+    assert abs(mf.tocsc() - H).max() < 1e-12
+    assert np.allclose(mf.diagonal(), H.diagonal())
+
+
+def test_recognise_separable_potential():
+    n = 8
+    sm = MGCMTStencilMaker()
+    L = sm.laplacian(n, "2d")
+    vx = np.linspace(0, 3, n)
+    V = (vx[:, None] ** 2 + 2 * vx[None, :]).reshape(-1)
+    H = -L + sp.diags(V)
+    op = SeparableOperator.from_sparse(H, "2d")
+    assert abs(op.tocsc() - H).max() < 1e-12
+
+
+def test_refuses_non_separable():
+    n = 8
+    sm = MGCMTStencilMaker()
+    L = sm.laplacian(n, "2d")
+    rng = np.random.RandomState(0)
+    with pytest.raises(UnsupportedOperator):
+        SeparableOperator.from_sparse(-L + sp.diags(rng.random_sample(n * n)), "2d")
+    with pytest.raises(UnsupportedOperator):
+        SeparableOperator.from_sparse(sp.random(64, 64, 0.2, format="csc", random_state=1), "2d")
+    with pytest.raises(UnsupportedOperator):
+        SeparableOperator.from_sparse(sp.random(64, 64, 0.2, format="csc", random_state=1), "1d")
+    with pytest.raises(UnsupportedOperator):
+        SeparableOperator.from_sparse(sp.eye(16, format="csc") * (1 + 1j), "1d")
+
+
+def test_library_exports_every_header_symbol():
+    """include/mgcmt_b200.h <-> libmgcmt_b200.so <-> the ctypes table, symbol by symbol."""
+    hdr = open(os.path.join(ROOT, "include", "mgcmt_b200.h")).read()
+    declared = set(re.findall(r"\b(mgcmt_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"mgcmt_hier"}  # the opaque struct tag
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = _lib.load()  # loading needs no GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mgcmt_abi_version() == 1
+
+
+def test_bad_arguments_are_errors_not_crashes():
+    lib = _lib.load()
+    handle = ctypes.c_void_p()
+    z = np.zeros(4)
+    p = z.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.mgcmt_hier_create(ctypes.byref(handle), 1, 6, 0, p, p, p, p, p, p, 2, None)
+    assert rc == 1 and b"power of two" in lib.mgcmt_last_error()
+    rc = lib.mgcmt_hier_create(ctypes.byref(handle), 4, 4, 1, None, p, p, p, p, p, 2, None)
+    assert rc == 1
+    assert lib.mgcmt_vcycle(None, 0.0, 4, 4, 0, 0.66, None, None, None) == 1
+    assert lib.mgcmt_dot(-1, None, None, None, None) == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from multigridcmt_b200 import MGCMTSolver
+    sm, s = MGCMTStencilMaker(), MGCMTSolver()
+    with pytest.raises(_lib.MgcmtError):
+        s.vcycle(np.ones(16), np.zeros(16), sm.laplacian(16), sm)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "multigridcmt_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(import|from)\s+(mgcmt_oracle|ref_loader|oracle)\b", src, re.M), fn
+                assert "oracle/_ref" not in src and "/root/reference" not in src, fn
