@@ -36,7 +36,7 @@ N0 = 16  # coarse grid the initial guesses / shifts come from (2DPotGS.py:54-63;
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=0, help="grid size N (N x N unknowns); default 4096")
@@ -114,9 +114,14 @@ class Clocks:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -126,7 +131,9 @@ class Clocks:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t_begin is not None and not (t_begin <= ts <= t_end + 0.1):
+                continue
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -137,8 +144,7 @@ class Clocks:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        # samples under load = the upper half of the observed clocks
-        med = statistics.median(sorted(sm)[len(sm) // 2:]) if sm else None
+        med = statistics.median(sm) if sm else None
         return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
@@ -263,23 +269,26 @@ def run_ours(args):
         _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(W), 1, stream))
         V.copy_(W)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
+        clocks.wait_first()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = lib.mgcmt_launch_count()
     lib.mgcmt_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.time()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
@@ -287,7 +296,7 @@ def run_ours(args):
     dom_ms, dom_cnt = C.c_double(), C.c_longlong()
     lib.mgcmt_profile_read(C.byref(dom_ms), C.byref(dom_cnt))
     lib.mgcmt_profile_enable(0)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -300,20 +309,18 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing call with host buffers (pinned), copies inside the timed region -----
     e2e = None
-    if rank == 0 or world > 1:
+    if args.e2e_steps > 0:
         Vh = torch.from_numpy(V_host.copy()).pin_memory()
         zero_h = torch.zeros(n, dtype=torch.float64).pin_memory()
         Vnp = Vh.numpy()
         znp = zero_h.numpy()
 
         def e2e_step():
-            lam_h = []
             for c in range(k):
                 w = solver.vcycle(znp, Vnp[c], H, sm, shift=shifts[c], dimension="2d", lowest_level=lowest,
                                   smoother=(solver.rbgs if args.smoother == "rbgs" else None))
                 Vnp[c] = w / np.linalg.norm(w)
                 znp.shape = (n,)
-            return lam_h
         e2e_step()
         torch.cuda.synchronize()
         t0 = time.perf_counter()

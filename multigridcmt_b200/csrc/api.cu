@@ -49,6 +49,14 @@ int fail(int code, const std::string &msg) {
   } while (0)
 
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+// grid vectors are read as double2: they must be 16-byte aligned
+bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+#define NEED_ALIGNED(...)                                                                       \
+  do {                                                                                          \
+    const void *ps__[] = {__VA_ARGS__};                                                         \
+    for (const void *p__ : ps__)                                                                \
+      if (!p__ || !al16(p__)) return fail(MGCMT_ERR_ARG, "grid vectors must be non-null and 16-byte aligned"); \
+  } while (0)
 
 // scratch for reductions that do not belong to a hierarchy (one per device, single-stream use)
 struct Scratch {
@@ -382,7 +390,7 @@ int mgcmt_hier_level_coefs(const mgcmt_hier_t *h, int level, double *h_rowcoef6,
 int mgcmt_apply(mgcmt_hier_t *h, int level, double shift, const double *d_x, double *d_y, void *stream) {
   int rc = check_level(h, level);
   if (rc) return rc;
-  if (!d_x || !d_y) return fail(MGCMT_ERR_ARG, "null vector");
+  NEED_ALIGNED(d_x, d_y);
   CU(launch_apply(h->lev[level].dev, shift, d_x, d_y, nullptr, nullptr, (cudaStream_t)stream));
   return MGCMT_OK;
 }
@@ -391,7 +399,7 @@ int mgcmt_residual(mgcmt_hier_t *h, int level, double shift, const double *d_v, 
                    void *stream) {
   int rc = check_level(h, level);
   if (rc) return rc;
-  if (!d_v || !d_f || !d_r) return fail(MGCMT_ERR_ARG, "null vector");
+  NEED_ALIGNED(d_v, d_f, d_r);
   CU(launch_residual(h->lev[level].dev, shift, d_v, d_f, d_r, nullptr, nullptr, (cudaStream_t)stream));
   return MGCMT_OK;
 }
@@ -400,7 +408,8 @@ int mgcmt_smooth(mgcmt_hier_t *h, int level, int smoother, double shift, double 
                  const double *d_f, double *d_tmp, void *stream) {
   int rc = check_level(h, level);
   if (rc) return rc;
-  if (!d_v || !d_f) return fail(MGCMT_ERR_ARG, "null vector");
+  NEED_ALIGNED(d_v, d_f);
+  if (d_tmp && !al16(d_tmp)) return fail(MGCMT_ERR_ARG, "d_tmp must be 16-byte aligned");
   return smooth_impl(h, level, smoother, shift, omega, nu, d_v, d_f, d_tmp, (cudaStream_t)stream);
 }
 
@@ -408,6 +417,7 @@ int mgcmt_restrict(mgcmt_hier_t *h, int level, const double *d_fine, double *d_c
   int rc = check_level(h, level);
   if (rc) return rc;
   if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  NEED_ALIGNED(d_fine, d_coarse);
   CU(launch_restrict(h->lev[level].dev, h->coarsen_rows, d_fine, d_coarse, (cudaStream_t)stream));
   return MGCMT_OK;
 }
@@ -417,6 +427,7 @@ int mgcmt_residual_restrict(mgcmt_hier_t *h, int level, double shift, const doub
   int rc = check_level(h, level);
   if (rc) return rc;
   if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  NEED_ALIGNED(d_v, d_f, d_rcoarse);
   CU(launch_residual_restrict(h->lev[level].dev, h->coarsen_rows, shift, d_v, d_f, d_rcoarse,
                               (cudaStream_t)stream));
   return MGCMT_OK;
@@ -426,6 +437,7 @@ int mgcmt_prolong(mgcmt_hier_t *h, int level, const double *d_coarse, double *d_
   int rc = check_level(h, level);
   if (rc) return rc;
   if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  NEED_ALIGNED(d_coarse, d_fine);
   CU(launch_prolong(h->lev[level].dev, h->coarsen_rows, false, d_coarse, d_fine, (cudaStream_t)stream));
   return MGCMT_OK;
 }
@@ -434,6 +446,7 @@ int mgcmt_prolong_correct(mgcmt_hier_t *h, int level, const double *d_ecoarse, d
   int rc = check_level(h, level);
   if (rc) return rc;
   if (level + 1 >= h->nlev) return fail(MGCMT_ERR_ARG, "no coarser level");
+  NEED_ALIGNED(d_ecoarse, d_v);
   CU(launch_prolong(h->lev[level].dev, h->coarsen_rows, true, d_ecoarse, d_v, (cudaStream_t)stream));
   return MGCMT_OK;
 }
@@ -452,6 +465,7 @@ int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, 
                  const double *d_f, void *stream) {
   if (!h) return fail(MGCMT_ERR_ARG, "null hierarchy");
   if (!d_v || !d_f || d_v == d_f) return fail(MGCMT_ERR_ARG, "need distinct non-null v and f");
+  NEED_ALIGNED(d_v, d_f);
   if (nu1 < 0 || nu2 < 0) return fail(MGCMT_ERR_ARG, "negative sweep count");
   return vcycle_level(h, 0, shift, nu1, nu2, smoother, omega, d_v, d_f, (cudaStream_t)stream);
 }
@@ -468,7 +482,8 @@ int mgcmt_dot(long long n, const double *d_x, const double *d_y, double *d_out, 
 int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream) {
   int rc = check_level(h, level);
   if (rc) return rc;
-  if (!d_x || !d_out2) return fail(MGCMT_ERR_ARG, "null vector");
+  if (!d_out2) return fail(MGCMT_ERR_ARG, "null output");
+  NEED_ALIGNED(d_x);
   Scratch *sc;
   rc = get_scratch(&sc);
   if (rc) return rc;

@@ -15,7 +15,9 @@ namespace mgcmt {
 constexpr int kRedThreads = 256;
 
 // partials[m * gridDim.x + b] = sum over this block's elements of X_m[i] * y[i],  X_m = x0 + m*stride
-template <int M>
+// VEC: all operands 16-byte aligned (base pointers and stride), so pairs can be loaded as double2;
+// the summation order is the same either way.
+template <int M, bool VEC>
 __global__ void __launch_bounds__(kRedThreads)
 multidot_partial_kernel(long long n, const double *__restrict__ x0, long long stride,
                         const double *__restrict__ y, double *__restrict__ partials) {
@@ -25,10 +27,14 @@ multidot_partial_kernel(long long n, const double *__restrict__ x0, long long st
   const long long n2 = n >> 1;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += step) {
-    const double2 yy = reinterpret_cast<const double2 *>(y)[i];
+    double2 yy;
+    if (VEC) yy = reinterpret_cast<const double2 *>(y)[i];
+    else yy = make_double2(y[2 * i], y[2 * i + 1]);
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-      const double2 xx = reinterpret_cast<const double2 *>(x0 + m * stride)[i];
+      double2 xx;
+      if (VEC) xx = reinterpret_cast<const double2 *>(x0 + m * stride)[i];
+      else xx = make_double2(x0[m * stride + 2 * i], x0[m * stride + 2 * i + 1]);
       acc[m] += xx.x * yy.x;
       acc[m] += xx.y * yy.y;
     }
@@ -79,10 +85,13 @@ static int blocks_for(long long n) {
 cudaError_t launch_multidot(long long n, int M, const double *x0, long long stride, const double *y,
                             double *partials, double *out, cudaStream_t s) {
   const int B = blocks_for(n);
+  const bool vec = ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                   (M == 1 || (stride & 1) == 0);
   switch (M) {
 #define CASE(MM)                                                                                 \
   case MM:                                                                                       \
-    multidot_partial_kernel<MM><<<B, kRedThreads, 0, s>>>(n, x0, stride, y, partials);           \
+    if (vec) multidot_partial_kernel<MM, true><<<B, kRedThreads, 0, s>>>(n, x0, stride, y, partials);  \
+    else multidot_partial_kernel<MM, false><<<B, kRedThreads, 0, s>>>(n, x0, stride, y, partials);     \
     break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
     CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)

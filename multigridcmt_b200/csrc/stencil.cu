@@ -2,8 +2,12 @@
 //
 // One thread owns two adjacent columns and marches down a chunk of rows with a three-row window in
 // registers, so every grid value is read from HBM once per sweep (plus one halo row per chunk, which
-// the neighbouring CTA has just pulled through L2).  Left/right neighbours come from warp shuffles;
-// only the two edge lanes of a warp issue an extra (L1-resident) scalar load.
+// the neighbouring CTA has just pulled through L2).  Rows are prefetched kPF deep with cp.async
+// (LDGSTS) into a per-thread shared-memory ring -- each thread only ever reads the slots it filled
+// itself, so the ring needs no barrier, costs no registers, and keeps ~kPF x 32 B per thread in
+// flight (what hides HBM latency at the low occupancy a register-windowed fp64 kernel has).
+// Left/right neighbours come from warp shuffles; the two edge lanes of each warp prefetch the one
+// extra value they need through the same ring.
 //
 // Reference arithmetic being restated (paths relative to the reference root):
 //   weighted Jacobi   MGCMTSolver.py:182-208   v <- (I - w D^-1 A) v + w D^-1 f
@@ -15,53 +19,82 @@
 
 namespace mgcmt {
 
+constexpr int kPF = 8;  // prefetch depth in rows (power of two)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;  // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 struct Row4 {
   double xl, x0, x1, xr;
 };
 
-// value pair of local row i (i may be -1 or nrows: halo row or Dirichlet zero), plus the two
-// horizontal neighbours
-__device__ __forceinline__ Row4 load_row(const LevelDev &L, const double *__restrict__ v,
-                                         const double *__restrict__ halo_top,
-                                         const double *__restrict__ halo_bot, int i, int j0, bool active,
-                                         int lane) {
-  const double *src;
-  if (i < 0)
-    src = halo_top;
-  else if (i >= L.nrows)
-    src = halo_bot;
-  else
-    src = v + (size_t)i * L.ncols;
-  Row4 r;
-  double2 x = make_double2(0.0, 0.0);
-  const bool ok = (src != nullptr) && active;
-  if (ok) x = *reinterpret_cast<const double2 *>(src + j0);
-  r.x0 = x.x;
-  r.x1 = x.y;
-  r.xl = __shfl_up_sync(0xffffffffu, x.y, 1);
-  r.xr = __shfl_down_sync(0xffffffffu, x.x, 1);
-  if (lane == 0) r.xl = (ok && j0 > 0) ? src[j0 - 1] : 0.0;
-  if (lane == 31) r.xr = (ok && j0 + 2 < L.ncols) ? src[j0 + 2] : 0.0;
-  return r;
-}
-
-// row-direction ("horizontal") factor applied to a row: t = Kb row, s = Mb row at the two columns
+// horizontal factors applied to a row: t = Kb row, s = Mb row at the thread's two columns
 struct HV {
   double t0, t1, s0, s1, x0, x1;
 };
 
-template <int OP, bool FIVE>
-__global__ void __launch_bounds__(128)
+template <int OP, bool FIVE, int TPB>
+__global__ void __launch_bounds__(TPB)
 stencil_march_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v,
                      const double *__restrict__ f, double *__restrict__ out,
                      const double *__restrict__ halo_top, const double *__restrict__ halo_bot,
                      int rows_per_cta) {
-  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  __shared__ double2 ring_v[kPF][TPB];
+  __shared__ double2 ring_f[kPF][TPB];
+  __shared__ double ring_e[kPF][TPB / 32][2];
+
+  const int tid = threadIdx.x;
+  const int j0 = (blockIdx.x * TPB + tid) * 2;
   const bool active = j0 < L.ncols;
-  const int lane = threadIdx.x & 31;
+  const int lane = tid & 31, warp = tid >> 5;
   const int i_begin = blockIdx.y * rows_per_cta;
   const int i_end = min(i_begin + rows_per_cta, L.nrows);
   const int jc = active ? j0 : 0;
+
+  // issue the asynchronous copies of local row i (v row i, and f row i when it is an interior row of
+  // this chunk); rows -1 / nrows come from the halo pointers (or are Dirichlet zeros)
+  auto issue = [&](int i) {
+    const int slot = (i + 1) & (kPF - 1);
+    const double *src;
+    if (i < 0) src = halo_top;
+    else if (i >= L.nrows) src = halo_bot;
+    else src = v + (size_t)i * L.ncols;
+    const bool ok = active && src != nullptr && i <= i_end;
+    const double *s = ok ? src : v;
+    cp_async16(&ring_v[slot][tid], s + jc, ok);
+    if (lane == 0) cp_async8(&ring_e[slot][warp][0], s + (jc > 0 ? jc - 1 : 0), ok && jc > 0);
+    if (lane == 31) cp_async8(&ring_e[slot][warp][1], s + (jc + 2 < L.ncols ? jc + 2 : 0), ok && jc + 2 < L.ncols);
+    if (OP != OP_APPLY) {
+      const bool okf = active && i >= i_begin && i < i_end;
+      cp_async16(&ring_f[slot][tid], f + (okf ? (size_t)i * L.ncols + jc : 0), okf);
+    }
+    cp_async_commit();
+  };
+  auto fetch = [&](int i) {
+    const int slot = (i + 1) & (kPF - 1);
+    const double2 x = ring_v[slot][tid];
+    Row4 r;
+    r.x0 = x.x;
+    r.x1 = x.y;
+    r.xl = __shfl_up_sync(0xffffffffu, x.y, 1);
+    r.xr = __shfl_down_sync(0xffffffffu, x.x, 1);
+    if (lane == 0) r.xl = ring_e[slot][warp][0];
+    if (lane == 31) r.xr = ring_e[slot][warp][1];
+    return r;
+  };
 
   const double kbl0 = L.kb_lo[jc], kbd0 = L.kb_di[jc], kbu0 = L.kb_up[jc];
   const double kbl1 = L.kb_lo[jc + 1], kbd1 = L.kb_di[jc + 1], kbu1 = L.kb_up[jc + 1];
@@ -70,7 +103,6 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
     mbl0 = L.mb_lo[jc]; mbd0 = L.mb_di[jc]; mbu0 = L.mb_up[jc];
     mbl1 = L.mb_lo[jc + 1]; mbd1 = L.mb_di[jc + 1]; mbu1 = L.mb_up[jc + 1];
   }
-
   auto horiz = [&](const Row4 &r) {
     HV h;
     h.x0 = r.x0;
@@ -87,30 +119,25 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
     return h;
   };
 
+  // prologue: rows i_begin-1 .. i_begin+kPF-2 in flight (one commit group per row)
+#pragma unroll
+  for (int d = 0; d < kPF; ++d) issue(i_begin - 1 + d);
+
   HV p, c, n;
-  if (FIVE) {
-    // 5-point: only the centre row needs its horizontal part
-    Row4 rp = load_row(L, v, halo_top, halo_bot, i_begin - 1, j0, active, lane);
-    p.x0 = rp.x0; p.x1 = rp.x1; p.s0 = rp.x0; p.s1 = rp.x1; p.t0 = p.t1 = 0;
-  } else {
-    p = horiz(load_row(L, v, halo_top, halo_bot, i_begin - 1, j0, active, lane));
-  }
-  c = horiz(load_row(L, v, halo_top, halo_bot, i_begin, j0, active, lane));
+  cp_async_wait<kPF - 2>();  // rows i_begin-1 and i_begin have landed
+  p = horiz(fetch(i_begin - 1));
+  c = horiz(fetch(i_begin));
 
   double last_kad = 0, last_mad = 0, winv0 = 0, winv1 = 0;
   bool have_w = false;
 
   for (int i = i_begin; i < i_end; ++i) {
-    Row4 rn = load_row(L, v, halo_top, halo_bot, i + 1, j0, active, lane);
+    // slot of row i-1 is free now: refill it with row i-1+kPF, then wait for row i+1
+    issue(i - 1 + kPF);
+    cp_async_wait<kPF - 2>();
+    n = horiz(fetch(i + 1));
     double2 ff = make_double2(0.0, 0.0);
-    if (OP != OP_APPLY && active) ff = *reinterpret_cast<const double2 *>(f + (size_t)i * L.ncols + j0);
-    if (FIVE) {
-      n.x0 = rn.x0; n.x1 = rn.x1; n.s0 = rn.x0; n.s1 = rn.x1; n.t0 = n.t1 = 0;
-      n.t0 = kbl0 * rn.xl + kbd0 * rn.x0 + kbu0 * rn.x1;  // becomes the centre row next iteration
-      n.t1 = kbl1 * rn.x0 + kbd1 * rn.x1 + kbu1 * rn.xr;
-    } else {
-      n = horiz(rn);
-    }
+    if (OP != OP_APPLY) ff = ring_f[(i + 1) & (kPF - 1)][tid];
     const int gi = L.row0 + i;
     const double kal = L.ka_lo[gi], kad = L.ka_di[gi], kau = L.ka_up[gi];
     double av0, av1, mad = 1.0;
@@ -141,37 +168,40 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
       o.x = av0;
       o.y = av1;
     }
-    if (active) *reinterpret_cast<double2 *>(out + (size_t)i * L.ncols + j0) = o;
+    if (active) st_stream2(out + (size_t)i * L.ncols + j0, o);
     p = c;
     c = n;
   }
+  cp_async_wait<0>();
 }
 
-static inline int pick_rows_per_cta(int nrows, int col_blocks) {
-  // enough CTAs to fill 148 SMs x 16 resident 128-thread CTAs, but >= 16 rows per chunk so the
-  // re-read halo rows stay <= 12.5 % (and those mostly hit L2)
-  int r = 64;
-  while (r > 16 && (long long)col_blocks * ((nrows + r - 1) / r) < 148LL * 8) r >>= 1;
-  if (r > nrows) r = nrows;
-  return r < 1 ? 1 : r;
+// launch geometry: CTAs of 32/64/128 threads (2 columns per thread); rows per CTA chosen so the grid
+// has a few CTAs per SM even on small levels, but chunks stay long enough on big ones that the two
+// re-read halo rows are a few per cent (and those come from L2)
+template <int OP, int TPB>
+static cudaError_t launch_march_t(const LevelDev &L, double shift, double omega, const double *v,
+                                  const double *f, double *out, const double *halo_top,
+                                  const double *halo_bot, cudaStream_t s) {
+  const int col_blocks = (L.ncols / 2 + TPB - 1) / TPB;
+  int rpc = 32;
+  while (rpc > 2 && (long long)col_blocks * ((L.nrows + rpc - 1) / rpc) < 148LL * 4) rpc >>= 1;
+  if (rpc > L.nrows) rpc = L.nrows;
+  dim3 grid(col_blocks, (L.nrows + rpc - 1) / rpc);
+  if (L.five)
+    stencil_march_kernel<OP, true, TPB><<<grid, TPB, 0, s>>>(L, shift, omega, v, f, out, halo_top, halo_bot, rpc);
+  else
+    stencil_march_kernel<OP, false, TPB><<<grid, TPB, 0, s>>>(L, shift, omega, v, f, out, halo_top, halo_bot, rpc);
+  count_launch();
+  return cudaGetLastError();
 }
 
 template <int OP>
 static cudaError_t launch_march(const LevelDev &L, double shift, double omega, const double *v,
                                 const double *f, double *out, const double *halo_top,
                                 const double *halo_bot, cudaStream_t s) {
-  int threads = L.ncols / 2;
-  if (threads > 128) threads = 128;
-  if (threads < 32) threads = 32;
-  const int col_blocks = (L.ncols / 2 + threads - 1) / threads;
-  const int rpc = pick_rows_per_cta(L.nrows, col_blocks);
-  dim3 grid(col_blocks, (L.nrows + rpc - 1) / rpc);
-  if (L.five)
-    stencil_march_kernel<OP, true><<<grid, threads, 0, s>>>(L, shift, omega, v, f, out, halo_top, halo_bot, rpc);
-  else
-    stencil_march_kernel<OP, false><<<grid, threads, 0, s>>>(L, shift, omega, v, f, out, halo_top, halo_bot, rpc);
-  count_launch();
-  return cudaGetLastError();
+  if (L.ncols >= 1024) return launch_march_t<OP, 128>(L, shift, omega, v, f, out, halo_top, halo_bot, s);
+  if (L.ncols >= 256) return launch_march_t<OP, 64>(L, shift, omega, v, f, out, halo_top, halo_bot, s);
+  return launch_march_t<OP, 32>(L, shift, omega, v, f, out, halo_top, halo_bot, s);
 }
 
 cudaError_t launch_jacobi_sweep(const LevelDev &L, double shift, double omega, const double *v_in,

@@ -154,6 +154,8 @@ def to_device(x, n=None):
         t = x.reshape(-1)
         if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous():
             t = t.to(device="cuda", dtype=torch.float64).contiguous()
+        if t.data_ptr() % 16:
+            t = t.clone()  # the kernels read grid vectors as double2
         return t
     a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
     src = torch.from_numpy(a)

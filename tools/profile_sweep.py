@@ -1,0 +1,32 @@
+"""Runs a few launches of one kernel family on the 4096^2 well so `ncu -k regex:...` can capture it.
+
+  python tools/profile_sweep.py [jacobi|vcycle|down|up] [N]
+"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from multigridcmt_b200 import MGCMTStencilMaker, _lib
+from multigridcmt_b200.hierarchy import get_hierarchy
+
+what = sys.argv[1] if len(sys.argv) > 1 else "jacobi"
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+sm = MGCMTStencilMaker()
+H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+h = get_hierarchy(H, 8)
+g = torch.Generator(device="cuda"); g.manual_seed(0)
+v = torch.rand(N * N, dtype=torch.float64, device="cuda", generator=g)
+f = torch.rand(N * N, dtype=torch.float64, device="cuda", generator=g)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+reps = 5
+for it in range(2):
+    e0.record()
+    for _ in range(reps):
+        if what == "jacobi":
+            h.smooth(0, _lib.SMOOTH_WJACOBI, 1.7, 2.0 / 3.0, 4, v, f)
+        else:
+            h.vcycle(1.7, 4, 4, _lib.SMOOTH_WJACOBI, 2.0 / 3.0, v, f)
+    e1.record()
+    torch.cuda.synchronize()
+print(what, N, "ms per call:", e0.elapsed_time(e1) / reps)
