@@ -262,8 +262,8 @@ def run_ours(args):
 
     def step():
         for c in range(k):
-            W[c].zero_()
-            _lib.check(lib.mgcmt_vcycle(h.handle, shifts[c], 4, 4, smoother_code, omega, _ptr(W[c]), _ptr(V[c]), stream))
+            # w0 = 0 as in the reference's drivers (2DPotGS.py:94): flagged, so the zero vector is not read
+            _lib.check(lib.mgcmt_vcycle(h.handle, shifts[c], 4, 4, smoother_code, omega, _ptr(W[c]), _ptr(V[c]), 1, stream))
             _lib.check(lib.mgcmt_normalize(n, _ptr(W[c]), stream))
             _lib.check(lib.mgcmt_rayleigh(h.handle, 0, _ptr(W[c]), _ptr(rq[c]), stream))
         _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(W), 1, stream))

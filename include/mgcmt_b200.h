@@ -114,9 +114,25 @@ int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double 
 /* ---- whole cycle ---------------------------------------------------------------------------------
  * One V-cycle of MGCMTSolver.vcycle (MGCMTSolver.py:281-329) on the finest level: d_v in/out, d_f in.
  * nu1/nu2 apply to the finest level only; all coarser levels run 4/4 (MGCMTSolver.py:320, quirk Q4).
- * If the hierarchy has a single level this is the exact solve (quirk Q7). */
+ * If the hierarchy has a single level this is the exact solve (quirk Q7).
+ * v0_is_zero != 0: the caller guarantees the initial guess is zero (the shift-method drivers always
+ * start from w0 = 0, e.g. 2DPotGS.py:94); d_v is then not read. */
 int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega,
-                 double *d_v, const double *d_f, void *stream);
+                 double *d_v, const double *d_f, int v0_is_zero, void *stream);
+
+/* One fused pass over a 2-D level (what mgcmt_vcycle is made of when the smoother is weighted Jacobi):
+ * nu (0..4) Jacobi sweeps fused with the neighbouring grid transfer, out of place (d_vin != d_vout).
+ *   mode 0: d_vout = J^nu(d_vin)                                       MGCMTSolver.py:313 / :326
+ *   mode 1: d_vout = J^nu(d_vin),  d_rcoarse = R (f - A_s d_vout)      MGCMTSolver.py:313-315
+ *   mode 2: as mode 1 with d_vin == 0 (d_vin is not read; the zero start of every coarse level, :316)
+ *   mode 3: d_vout = J^nu(d_vin + P d_ecoarse)                         MGCMTSolver.py:323-326
+ * For nu == 0, modes 1/2 leave d_vout untouched (the residual is taken of d_vin). */
+int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, double omega,
+                    const double *d_vin, const double *d_f, double *d_vout, const double *d_ecoarse,
+                    double *d_rcoarse, void *stream);
+/* runtime switches, for tests and A/B timing: "fused" (1/0), "fused_min_cols" (smallest level width
+ * that uses the fused legs) */
+int mgcmt_set_option(const char *name, int value);
 
 /* ---- reductions / vector post-processing (MGCMTProcessor.py, Rayleigh quotients in the drivers) --
  * Deterministic: fixed two-stage tree, independent of launch timing.  Results go to DEVICE memory. */

@@ -27,6 +27,10 @@ struct Profile {
   size_t used = 0;
 } g_prof;
 
+// runtime switches (mgcmt_set_option): fused legs on/off, smallest level width that uses them
+int g_opt_fused = 1;
+int g_opt_fused_min_cols = 64;
+
 void prof_mark(cudaStream_t s) {
   if (!g_prof.on) return;
   if (g_prof.used == g_prof.pool.size()) {
@@ -199,24 +203,88 @@ int get_inverse(mgcmt_hier *h, double shift, cudaStream_t s, double **out) {
   return MGCMT_OK;
 }
 
+bool use_fused(const mgcmt_hier *h, int l, int smoother) {
+  const Level &L = h->lev[l];
+  return g_opt_fused && smoother == MGCMT_SMOOTH_WJACOBI && h->coarsen_rows && L.dev.nrows >= 16 &&
+         L.dev.ncols >= g_opt_fused_min_cols && L.dev.row0 == 0;
+}
+
+// down leg with the fused kernels: nu1 sweeps (in passes of <= 4) + residual + restriction into C.f.
+// Returns in *cur the buffer that holds the smoothed iterate (v or L.tmp).
+int fused_down(mgcmt_hier *h, int l, double shift, double omega, int nu1, double *v, const double *f,
+               bool v_zero, double **cur, cudaStream_t s) {
+  Level &L = h->lev[l];
+  Level &C = h->lev[l + 1];
+  double *a = v, *b = L.tmp;
+  int left = nu1;
+  while (left > 4) {
+    if (l == 0) prof_mark(s);
+    CU(launch_fused_leg(L.dev, FUSED_SMOOTH, 4, shift, omega, a, f, b, nullptr, nullptr, s));
+    if (l == 0) prof_mark(s);
+    double *t = a; a = b; b = t;
+    left -= 4;
+    v_zero = false;
+  }
+  if (v_zero && left == 0) CU(cudaMemsetAsync(a, 0, sizeof(double) * L.n, s));
+  if (l == 0) prof_mark(s);
+  CU(launch_fused_leg(L.dev, (v_zero && left > 0) ? FUSED_DOWN_ZERO : FUSED_DOWN, left, shift, omega, a, f, b,
+                      nullptr, C.f, s));
+  if (l == 0) prof_mark(s);
+  if (left > 0) { double *t = a; a = b; b = t; }
+  *cur = a;
+  return MGCMT_OK;
+}
+
+// up leg: cur (+ P e) -> nu2 sweeps; result must end in v
+int fused_up(mgcmt_hier *h, int l, double shift, double omega, int nu2, double *v, const double *f, double *cur,
+             const double *e, cudaStream_t s) {
+  Level &L = h->lev[l];
+  double *a = cur, *b = (cur == v) ? L.tmp : v;
+  int left = nu2;
+  const int first = left > 4 ? 4 : left;
+  if (l == 0) prof_mark(s);
+  CU(launch_fused_leg(L.dev, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
+  if (l == 0) prof_mark(s);
+  { double *t = a; a = b; b = t; }
+  left -= first;
+  while (left > 0) {
+    const int nu = left > 4 ? 4 : left;
+    if (l == 0) prof_mark(s);
+    CU(launch_fused_leg(L.dev, FUSED_SMOOTH, nu, shift, omega, a, f, b, nullptr, nullptr, s));
+    if (l == 0) prof_mark(s);
+    double *t = a; a = b; b = t;
+    left -= nu;
+  }
+  if (a != v) CU(cudaMemcpyAsync(v, a, sizeof(double) * L.n, cudaMemcpyDeviceToDevice, s));
+  return MGCMT_OK;
+}
+
 int vcycle_level(mgcmt_hier *h, int l, double shift, int nu1, int nu2, int smoother, double omega, double *v,
-                 const double *f, cudaStream_t s) {
+                 const double *f, bool v_zero, cudaStream_t s) {
   Level &L = h->lev[l];
   if (l == h->nlev - 1) {
     double *inv = nullptr;
     int rc = get_inverse(h, shift, s, &inv);
     if (rc) return rc;
-    // v may alias nothing of f here (distinct level buffers)
     CU(launch_gemv((int)L.n, inv, f, v, s));
     return MGCMT_OK;
   }
   Level &C = h->lev[l + 1];
-  int rc = smooth_impl(h, l, smoother, shift, omega, nu1, v, f, nullptr, s);
+  int rc;
+  if (use_fused(h, l, smoother)) {
+    double *cur = nullptr;
+    rc = fused_down(h, l, shift, omega, nu1, v, f, v_zero, &cur, s);
+    if (rc) return rc;
+    // coarse levels always run 4/4 (MGCMTSolver.py:320 does not forward nu1/nu2); their start is zero
+    rc = vcycle_level(h, l + 1, shift, 4, 4, smoother, omega, C.v, C.f, true, s);
+    if (rc) return rc;
+    return fused_up(h, l, shift, omega, nu2, v, f, cur, C.v, s);
+  }
+  if (v_zero) CU(cudaMemsetAsync(v, 0, sizeof(double) * L.n, s));
+  rc = smooth_impl(h, l, smoother, shift, omega, nu1, v, f, nullptr, s);
   if (rc) return rc;
   CU(launch_residual_restrict(L.dev, h->coarsen_rows, shift, v, f, C.f, s));
-  CU(cudaMemsetAsync(C.v, 0, sizeof(double) * C.n, s));
-  // coarse levels always run 4/4 (MGCMTSolver.py:320 does not forward nu1/nu2)
-  rc = vcycle_level(h, l + 1, shift, 4, 4, smoother, omega, C.v, C.f, s);
+  rc = vcycle_level(h, l + 1, shift, 4, 4, smoother, omega, C.v, C.f, true, s);
   if (rc) return rc;
   CU(launch_prolong(L.dev, h->coarsen_rows, true, C.v, v, s));
   return smooth_impl(h, l, smoother, shift, omega, nu2, v, f, nullptr, s);
@@ -461,13 +529,37 @@ int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double 
   return MGCMT_OK;
 }
 
+int mgcmt_set_option(const char *name, int value) {
+  if (!name) return fail(MGCMT_ERR_ARG, "null option name");
+  if (!strcmp(name, "fused")) { g_opt_fused = value; return MGCMT_OK; }
+  if (!strcmp(name, "fused_min_cols")) { g_opt_fused_min_cols = value; return MGCMT_OK; }
+  return fail(MGCMT_ERR_ARG, std::string("unknown option ") + name);
+}
+
+int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, double omega, const double *d_vin,
+                    const double *d_f, double *d_vout, const double *d_ecoarse, double *d_rcoarse, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (level + 1 >= h->nlev && mode != FUSED_SMOOTH) return fail(MGCMT_ERR_ARG, "no coarser level");
+  if (!h->coarsen_rows || h->lev[level].dev.nrows < 2) return fail(MGCMT_ERR_ARG, "fused legs are 2-D only");
+  if (nu < 0 || nu > 4 || mode < 0 || mode > 3) return fail(MGCMT_ERR_ARG, "bad fused leg mode / nu");
+  if (d_vin == d_vout) return fail(MGCMT_ERR_ARG, "fused legs are out of place");
+  NEED_ALIGNED(d_f, d_vout);
+  if (mode != FUSED_DOWN_ZERO) NEED_ALIGNED(d_vin);
+  if (mode == FUSED_UP) NEED_ALIGNED(d_ecoarse);
+  if (mode == FUSED_DOWN || mode == FUSED_DOWN_ZERO) NEED_ALIGNED(d_rcoarse);
+  CU(launch_fused_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
+                      (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
 int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega, double *d_v,
-                 const double *d_f, void *stream) {
+                 const double *d_f, int v0_is_zero, void *stream) {
   if (!h) return fail(MGCMT_ERR_ARG, "null hierarchy");
   if (!d_v || !d_f || d_v == d_f) return fail(MGCMT_ERR_ARG, "need distinct non-null v and f");
   NEED_ALIGNED(d_v, d_f);
   if (nu1 < 0 || nu2 < 0) return fail(MGCMT_ERR_ARG, "negative sweep count");
-  return vcycle_level(h, 0, shift, nu1, nu2, smoother, omega, d_v, d_f, (cudaStream_t)stream);
+  return vcycle_level(h, 0, shift, nu1, nu2, smoother, omega, d_v, d_f, v0_is_zero != 0, (cudaStream_t)stream);
 }
 
 int mgcmt_dot(long long n, const double *d_x, const double *d_y, double *d_out, void *stream) {

@@ -1,0 +1,430 @@
+// fused.cu -- one HBM pass per V-cycle leg: NU Jacobi sweeps fused with the transfer that follows /
+// precedes them (temporal blocking in registers).
+//
+//   down leg:  v_out = J^NU(v_in; f),   r_coarse = R (f - A_s v_out)        (MGCMTSolver.py:313-315)
+//   up leg:    v_out = J^NU(v_in + P e_coarse; f)                           (MGCMTSolver.py:323-326)
+//
+// Un-fused, a V(4,4) level costs 4 x 24 B + 18 B per unknown and leg; here a
+// leg reads v and f once and writes v once (+ the coarse vector): 26 B per unknown.
+//
+// How: every WARP owns a strip of 32*C columns (C per lane) and streams down a chunk of rows.  The NU
+// sweeps (+ the residual) form a software pipeline along the row direction: stage k lags stage k-1
+// by one row, and each stage keeps just three doubles per column -- two partial row sums and the
+// centre value -- because an arriving row is *scattered* into the three output rows it touches
+// (as upper neighbour of row n-1, centre of row n, lower neighbour of row n+1).  Horizontal
+// neighbours come from warp shuffles only; strips overlap by HALO columns and chunks by HALO rows,
+// and the overlap is recomputed (trapezoid blocking), so warps never synchronise with each other.
+// Input rows are prefetched with cp.async into a per-thread shared-memory ring (no barrier needed:
+// a thread only reads slots it filled itself); the f ring doubles as the queue that hands f to the
+// later stages.
+//
+// Arithmetic is the reference's weighted Jacobi v <- v + w D^-1 (f - A_s v) (MGCMTSolver.py:182-208)
+// with A_l = Ma (x) Kb + Ka (x) Mb - shift I; only the order of the row-sum additions differs from
+// stencil.cu (parity to the oracle is tested at 1e-12).
+#include <type_traits>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgcmt {
+
+namespace {
+
+constexpr int kVRing = 8;    // prefetch depth of the v ring (rows)
+constexpr int kFRing = 16;   // f ring: prefetch depth + NU + 2 rows of queue
+constexpr int kERing = 4;    // coarse-row ring (PROLONG)
+constexpr int kWarps = 4;    // warps per CTA (independent strips)
+
+__device__ __forceinline__ void cpa16(void *smem, const void *gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cpa8(void *smem, const void *gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// per-row coefficients staged in shared memory for the rows a chunk touches
+struct RowCoef {
+  double ka_lo, ka_di, ka_up, slow;  // slow: see the table fill in the kernel
+  double ma_lo, ma_di, ma_up, pad;
+};
+
+template <int C>
+struct Stage {
+  double a1[C], a2[C], xc[C];
+};
+
+}  // namespace
+
+template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C>
+__global__ void __launch_bounds__(kWarps * 32)
+fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v_in,
+                 const double *__restrict__ f, double *__restrict__ v_out,
+                 const double *__restrict__ e_coarse, double *__restrict__ r_coarse, int rows_per_chunk) {
+  constexpr int HALO = (NU + 3) & ~1;  // >= NU + 2, even (threads load 16-byte column pairs)
+  constexpr int WCOLS = 32 * C;
+  constexpr int USEFUL = WCOLS - 2 * HALO;
+  constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);  // pipeline stages after the input
+  constexpr int CE = C / 2;                        // coarse columns per thread
+  static_assert(C == 2 || C == 4, "C must be 2 or 4");
+  static_assert(USEFUL % 2 == 0, "strip width must be even");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: v ring [kVRing][128][C], f ring [kFRing][128][C], e ring [kERing][128][CE], row table
+  double *ring_v = reinterpret_cast<double *>(smem_raw);
+  double *ring_f = ring_v + kVRing * kWarps * 32 * C;
+  double *ring_e = ring_f + kFRing * kWarps * 32 * C;
+  RowCoef *rowtab = reinterpret_cast<RowCoef *>(ring_e + kERing * kWarps * 32 * (PROLONG ? CE : 0));
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(r0 + rows_per_chunk, L.nrows);
+  // first / last input row the useful outputs depend on; the loop starts on an even row at or before
+  // t_first (two rows earlier for PROLONG so both coarse rows of the first fine row are in hand)
+  const int t_first = r0 - NU - (RESTRICT ? 1 : 0);
+  const int t_last = r1 - 1 + NU + (RESTRICT ? 2 : 0);  // inclusive
+  const int t_begin = (t_first - (PROLONG ? 2 : 0)) & ~1;
+  const int tab0 = t_begin - NSTAGE - 1;                // first row held in rowtab
+  const int ntab = t_last + 3 - tab0;                   // ... up to row t_last + 2
+  const int nrc = L.nrows / 2, ncc = L.ncols / 2;
+
+  // reference row for the cached omega/diag: the middle of the chunk
+  const int gref = L.row0 + min(max((r0 + r1) / 2, 0), L.nrows - 1);
+  const double kad_ref = L.ka_di[gref];
+  const double mad_ref = FIVE ? 1.0 : L.ma_di[gref];
+
+  for (int i = tid; i < ntab; i += kWarps * 32) {
+    const int row = tab0 + i;
+    const int g = L.row0 + min(max(row, 0), L.nrows - 1);
+    RowCoef rc;
+    rc.ka_lo = L.ka_lo[g]; rc.ka_di = L.ka_di[g]; rc.ka_up = L.ka_up[g];
+    if (FIVE) { rc.ma_lo = 0.0; rc.ma_di = 1.0; rc.ma_up = 0.0; }
+    else { rc.ma_lo = L.ma_lo[g]; rc.ma_di = L.ma_di[g]; rc.ma_up = L.ma_up[g]; }
+    // slow = 1 if any row finalised while row `row` is the newest input (rows row-NSTAGE .. row-1) has a
+    // diagonal different from the reference row's, i.e. the step needs the division path
+    double slow = 0.0;
+    for (int d = 1; d <= NSTAGE; ++d) {
+      const int g2 = L.row0 + min(max(row - d, 0), L.nrows - 1);
+      const double mad2 = FIVE ? 1.0 : L.ma_di[g2];
+      if (L.ka_di[g2] != kad_ref || mad2 != mad_ref) slow = 1.0;
+    }
+    rc.slow = slow;
+    rc.pad = 0.0;
+    rowtab[i] = rc;
+  }
+  __syncthreads();
+
+  const int strip = blockIdx.x * kWarps + warp;
+  const int u0 = strip * USEFUL;  // first useful fine column of this strip
+  if (u0 >= L.ncols) return;      // surplus warp (no CTA-wide barrier after this point)
+  const int u1 = min(u0 + USEFUL, L.ncols);
+  const int c0 = u0 - HALO + C * lane;  // first column of this thread (even)
+
+  // rows for which column q carries a real unknown: [0, rlim[q])  (0 rows for columns outside the grid)
+  unsigned rlim[C];
+  bool colout[C];
+  double kbl[C], kbd[C], kbu[C], mbl[C], mbd[C], mbu[C], wref[C];
+#pragma unroll
+  for (int q = 0; q < C; ++q) {
+    const int j = c0 + q;
+    rlim[q] = (j >= 0 && j < L.ncols) ? (unsigned)L.nrows : 0u;
+    colout[q] = (j >= u0 && j < u1);
+    const int jc = min(max(j, 0), L.ncols - 1);
+    kbl[q] = L.kb_lo[jc]; kbd[q] = L.kb_di[jc]; kbu[q] = L.kb_up[jc];
+    if (FIVE) { mbl[q] = 0.0; mbd[q] = 1.0; mbu[q] = 0.0; }
+    else { mbl[q] = L.mb_lo[jc]; mbd[q] = L.mb_di[jc]; mbu[q] = L.mb_up[jc]; }
+    wref[q] = omega / ((mad_ref * kbd[q] + kad_ref * mbd[q]) - shift);
+  }
+  // 16-byte granules of this thread: both columns of a pair are inside or outside the grid together
+  // (c0 and ncols are even)
+  bool pairin[C / 2];
+#pragma unroll
+  for (int g = 0; g < C / 2; ++g) pairin[g] = rlim[2 * g] != 0u;
+
+  double *my_v = ring_v + (size_t)tid * C;  // slot stride = kWarps*32*C
+  double *my_f = ring_f + (size_t)tid * C;
+  double *my_e = ring_e + (size_t)tid * CE;
+  constexpr int SLOT = kWarps * 32 * C;
+  constexpr int ESLOT = kWarps * 32 * CE;
+
+  // ---- asynchronous row fetch -------------------------------------------------------------------
+  auto issue = [&](int t) {
+    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last;
+    if (!ZEROV) {
+      double *dst = my_v + (size_t)(t & (kVRing - 1)) * SLOT;
+#pragma unroll
+      for (int g = 0; g < C / 2; ++g) {
+        const bool ok = rowin && pairin[g];
+        cpa16(dst + 2 * g, v_in + (ok ? (size_t)t * L.ncols + c0 + 2 * g : 0), ok);
+      }
+    }
+    {
+      double *dst = my_f + (size_t)(t & (kFRing - 1)) * SLOT;
+#pragma unroll
+      for (int g = 0; g < C / 2; ++g) {
+        const bool ok = rowin && pairin[g];
+        cpa16(dst + 2 * g, f + (ok ? (size_t)t * L.ncols + c0 + 2 * g : 0), ok);
+      }
+    }
+    if (PROLONG && (t & 1) == 0) {
+      // coarse row I = t/2 is first needed by fine row t (even); coarse columns c0/2 .. c0/2+CE-1
+      const int I = t >> 1;
+      const bool rowc = (t >= 0) && I < nrc && t <= t_last;
+      double *dst = my_e + (size_t)(I & (kERing - 1)) * ESLOT;
+#pragma unroll
+      for (int g = 0; g < CE; ++g) {
+        const int J = (c0 >> 1) + g;
+        const bool ok = rowc && J >= 0 && J < ncc;
+        cpa8(dst + g, e_coarse + (ok ? (size_t)I * ncc + J : 0), ok);
+      }
+    }
+    cpa_commit();
+  };
+
+  Stage<C> st[NSTAGE > 0 ? NSTAGE : 1];
+#pragma unroll
+  for (int k = 0; k < NSTAGE; ++k)
+#pragma unroll
+    for (int q = 0; q < C; ++q) st[k].a1[q] = st[k].a2[q] = st[k].xc[q] = 0.0;
+
+  double eprev[C], ecur[C];  // column-interpolated coarse rows I-1 and I (PROLONG)
+#pragma unroll
+  for (int q = 0; q < C; ++q) eprev[q] = ecur[q] = 0.0;
+  double racc[CE];           // running full-weighting row sum (RESTRICT)
+#pragma unroll
+  for (int g = 0; g < CE; ++g) racc[g] = 0.0;
+
+  // one time step: input row t enters, every stage finalises one row.  ODD (row parity) and SLOW (some
+  // finalised row needs omega/diag recomputed) are compile-time so the common path is branch-free.
+  auto step = [&](int t, auto odd_tag, auto slow_tag) {
+    constexpr bool ODD = decltype(odd_tag)::value;
+    constexpr bool SLOW = decltype(slow_tag)::value;
+    cpa_wait<kVRing - 1>();  // row t has landed (the kVRing-1 younger groups may still be in flight)
+
+    // ---- stage 0: the input row t --------------------------------------------------------------
+    double x[C];
+    {
+      const double *src = my_v + (size_t)(t & (kVRing - 1)) * SLOT;
+#pragma unroll
+      for (int q = 0; q < C; ++q) x[q] = ZEROV ? 0.0 : src[q];
+    }
+    if (PROLONG) {
+      if (!ODD) {
+        // new coarse row I = t/2: interpolate along columns.  fine col c0+2g (even) = 1/2 (E[J-1] + E[J]),
+        // fine col c0+2g+1 = E[J], J = c0/2 + g.  Lane 0 has no left neighbour: its first column is the
+        // outermost halo column of the strip; the up leg has no residual stage, so HALO = NU + 2 leaves
+        // two columns of slack and that error never reaches a useful column.
+        const double *src = my_e + (size_t)((t >> 1) & (kERing - 1)) * ESLOT;
+        double e[CE];
+#pragma unroll
+        for (int g = 0; g < CE; ++g) e[g] = src[g];
+        const double eleft = __shfl_up_sync(0xffffffffu, e[CE - 1], 1);
+#pragma unroll
+        for (int q = 0; q < C; ++q) eprev[q] = ecur[q];
+#pragma unroll
+        for (int g = 0; g < CE; ++g) {
+          const double em = (g == 0) ? eleft : e[g - 1];
+          ecur[2 * g] = 0.5 * (em + e[g]);
+          ecur[2 * g + 1] = e[g];
+        }
+#pragma unroll
+        for (int q = 0; q < C; ++q) x[q] += 0.5 * (eprev[q] + ecur[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < C; ++q) x[q] += ecur[q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < C; ++q) x[q] = ((unsigned)t < rlim[q]) ? x[q] : 0.0;
+
+    // refill the ring slot that row t just vacated (f slots are vacated NU+2 rows later; the f ring is
+    // deep enough: kVRing + NU + 2 <= kFRing)
+    issue(t + kVRing);
+
+    // ---- stages 1..NSTAGE: row n of stage k-1 arrives, row n-1 of stage k is finalised -----------
+#pragma unroll
+    for (int k = 0; k < NSTAGE; ++k) {
+      const int n = t - k;       // arriving row (of stage k's input)
+      const int rho = n - 1;     // finalised row
+      const RowCoef *tb = rowtab + (rho - tab0);
+      const double cr_ka_up = tb[0].ka_up, cr_ma_up = FIVE ? 0.0 : tb[0].ma_up;
+      const double cn_ka_di = tb[1].ka_di, cn_ma_di = FIVE ? 1.0 : tb[1].ma_di;
+      const double cp_ka_lo = tb[2].ka_lo, cp_ma_lo = FIVE ? 0.0 : tb[2].ma_lo;
+      // horizontal part of the arriving row
+      const double xl = __shfl_up_sync(0xffffffffu, x[C - 1], 1);
+      const double xr = __shfl_down_sync(0xffffffffu, x[0], 1);
+      double T[C], S[C];
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const double xm = (q == 0) ? xl : x[q - 1];
+        const double xp = (q == C - 1) ? xr : x[q + 1];
+        T[q] = kbl[q] * xm + kbd[q] * x[q] + kbu[q] * xp;
+        S[q] = FIVE ? x[q] : (mbl[q] * xm + mbd[q] * x[q] + mbu[q] * xp);
+      }
+      constexpr bool kIsRes = RESTRICT;  // (only the last stage, tested below with the unrolled k)
+      const bool is_res = kIsRes && (k == NSTAGE - 1);
+      const double *fsrc = my_f + (size_t)(rho & (kFRing - 1)) * SLOT;
+      double w[C];
+#pragma unroll
+      for (int q = 0; q < C; ++q) w[q] = wref[q];
+      if (SLOW && !is_res) {
+        const double cr_ka_di = tb[0].ka_di, cr_ma_di = FIVE ? 1.0 : tb[0].ma_di;
+        if (cr_ka_di != kad_ref || cr_ma_di != mad_ref) {
+#pragma unroll
+          for (int q = 0; q < C; ++q) w[q] = omega / ((cr_ma_di * kbd[q] + cr_ka_di * mbd[q]) - shift);
+        }
+      }
+      double out[C];
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const double acc = st[k].a1[q] + (FIVE ? cr_ka_up * S[q] : (cr_ma_up * T[q] + cr_ka_up * S[q]));
+        const double ff = fsrc[q];
+        const double o = is_res ? (ff - acc) : (st[k].xc[q] + w[q] * (ff - acc));
+        out[q] = ((unsigned)rho < rlim[q]) ? o : 0.0;
+        // scatter the arriving row into the two rows still open
+        st[k].a1[q] = st[k].a2[q] + ((FIVE ? (T[q] + cn_ka_di * S[q]) : (cn_ma_di * T[q] + cn_ka_di * S[q])) - shift * x[q]);
+        st[k].a2[q] = FIVE ? cp_ka_lo * S[q] : (cp_ma_lo * T[q] + cp_ka_lo * S[q]);
+        st[k].xc[q] = x[q];
+      }
+      // the finalised row is the next stage's arriving row
+#pragma unroll
+      for (int q = 0; q < C; ++q) x[q] = out[q];
+
+      if (!is_res && k == NU - 1) {
+        // x = row rho of the NU-th sweep: the smoothed iterate
+        const bool rowok = (rho >= r0 && rho < r1);
+#pragma unroll
+        for (int g = 0; g < C / 2; ++g)
+          if (rowok && colout[2 * g])
+            st_stream2(v_out + (size_t)rho * L.ncols + c0 + 2 * g, make_double2(x[2 * g], x[2 * g + 1]));
+      }
+      if (is_res) {
+        // x = residual row rho (zero outside the grid): full weighting.  Columns first:
+        //   coarse J = c0/2 + g  <-  1/4 r[2J] + 1/2 r[2J+1] + 1/4 r[2J+2]
+        // rho = t - NU - 1 has the parity of t iff NU is odd
+        constexpr bool RHO_ODD = (ODD != ((NU + 1) % 2 != 0));
+        const double rnext = __shfl_down_sync(0xffffffffu, x[0], 1);
+        double crr[CE];
+#pragma unroll
+        for (int g = 0; g < CE; ++g) {
+          const double r2 = (g == CE - 1) ? rnext : x[2 * g + 2];
+          crr[g] = 0.25 * x[2 * g] + 0.5 * x[2 * g + 1] + 0.25 * r2;
+        }
+        if (!RHO_ODD) {
+          const int I = (rho >> 1) - 1;  // coarse row completed by this fine row (as its row 2I+2)
+          const bool rowok = (I >= (r0 >> 1) && I < (r1 >> 1));
+#pragma unroll
+          for (int g = 0; g < CE; ++g) {
+            if (rowok && colout[2 * g]) r_coarse[(size_t)I * ncc + (c0 >> 1) + g] = racc[g] + 0.25 * crr[g];
+            racc[g] = 0.25 * crr[g];
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < CE; ++g) racc[g] += 0.5 * crr[g];
+        }
+      }
+    }
+    if (NU == 0 && !RESTRICT) {
+      // pure prolongation-correction pass: write the corrected iterate
+      const bool rowok = (t >= r0 && t < r1);
+#pragma unroll
+      for (int g = 0; g < C / 2; ++g)
+        if (rowok && colout[2 * g])
+          st_stream2(v_out + (size_t)t * L.ncols + c0 + 2 * g, make_double2(x[2 * g], x[2 * g + 1]));
+    }
+  };
+
+#pragma unroll
+  for (int d = 0; d < kVRing; ++d) issue(t_begin + d);
+
+  using TrueT = std::integral_constant<bool, true>;
+  using FalseT = std::integral_constant<bool, false>;
+  for (int t = t_begin; t <= t_last; t += 2) {  // t_begin is even
+    const bool slow = (rowtab[t - tab0].slow != 0.0) || (rowtab[t + 1 - tab0].slow != 0.0);
+    if (!slow) {
+      step(t, FalseT{}, FalseT{});
+      step(t + 1, TrueT{}, FalseT{});
+    } else {
+      step(t, FalseT{}, TrueT{});
+      step(t + 1, TrueT{}, TrueT{});
+    }
+  }
+  cpa_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+static size_t fused_smem_bytes(bool prolong, int rows_per_chunk) {
+  size_t b = sizeof(double) * (size_t)(kVRing + kFRing) * kWarps * 32 * C;
+  if (prolong) b += sizeof(double) * (size_t)kERing * kWarps * 32 * (C / 2);
+  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 40);  // rows t_begin-NSTAGE-1 .. t_last+2
+  return b;
+}
+
+template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C>
+static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega, const double *v_in,
+                                  const double *f, double *v_out, const double *e_coarse, double *r_coarse,
+                                  cudaStream_t s) {
+  constexpr int USEFUL = 32 * C - 2 * ((NU + 3) & ~1);
+  const int strips = (L.ncols + USEFUL - 1) / USEFUL;
+  const int gx = (strips + kWarps - 1) / kWarps;
+  int rpc = 128;
+  while (rpc > 16 && (long long)gx * ((L.nrows + rpc - 1) / rpc) < 148LL * 2) rpc >>= 1;
+  if (rpc > L.nrows) rpc = L.nrows;  // nrows is a power of two >= 2 here (even chunks)
+  const size_t smem = fused_smem_bytes<C>(PROLONG, rpc);
+  auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(gx, (L.nrows + rpc - 1) / rpc);
+  kern<<<grid, kWarps * 32, smem, s>>>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, rpc);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <bool FIVE, int NU, int C>
+static cudaError_t dispatch_mode(const LevelDev &L, int mode, double shift, double omega, const double *v_in,
+                                 const double *f, double *v_out, const double *e_coarse, double *r_coarse,
+                                 cudaStream_t s) {
+  switch (mode) {
+    case FUSED_SMOOTH:
+      if (NU == 0) return cudaErrorInvalidValue;
+      return launch_fused_t<FIVE, NU, false, false, false, C>(L, shift, omega, v_in, f, v_out, nullptr, nullptr, s);
+    case FUSED_DOWN:
+      return launch_fused_t<FIVE, NU, false, true, false, C>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s);
+    case FUSED_DOWN_ZERO:
+      return launch_fused_t<FIVE, NU, false, true, true, C>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s);
+    case FUSED_UP:
+      return launch_fused_t<FIVE, NU, true, false, false, C>(L, shift, omega, v_in, f, v_out, e_coarse, nullptr, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
+                             const double *v_in, const double *f, double *v_out, const double *e_coarse,
+                             double *r_coarse, cudaStream_t s) {
+  if (L.nrows < 2) return cudaErrorInvalidValue;  // 2-D levels only
+#define NU_CASE(NUV)                                                                                         \
+  case NUV:                                                                                                  \
+    return L.five ? dispatch_mode<true, NUV, MGCMT_FUSED_C5>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s) \
+                  : dispatch_mode<false, NUV, MGCMT_FUSED_C9>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  switch (nu) {
+    NU_CASE(0) NU_CASE(1) NU_CASE(2) NU_CASE(3) NU_CASE(4)
+  }
+#undef NU_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace mgcmt

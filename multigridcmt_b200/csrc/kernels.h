@@ -31,6 +31,21 @@ cudaError_t launch_residual_restrict(const LevelDev &Lf, bool coarsen_rows, doub
 cudaError_t launch_prolong(const LevelDev &Lf, bool coarsen_rows, bool accumulate, const double *coarse,
                            double *fine, cudaStream_t s);
 
+// fused.cu: one pass = nu (0..4) Jacobi sweeps fused with the neighbouring transfer (2-D levels)
+enum { FUSED_SMOOTH = 0,     // v_out = J^nu(v_in)
+       FUSED_DOWN = 1,       // v_out = J^nu(v_in), r_coarse = R (f - A v_out)
+       FUSED_DOWN_ZERO = 2,  // same with v_in == 0 (not read)
+       FUSED_UP = 3 };       // v_out = J^nu(v_in + P e_coarse)
+#ifndef MGCMT_FUSED_C5
+#define MGCMT_FUSED_C5 4     // columns per lane, 5-point (finest) level
+#endif
+#ifndef MGCMT_FUSED_C9
+#define MGCMT_FUSED_C9 2     // columns per lane, 9-point (Galerkin) levels
+#endif
+cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
+                             const double *v_in, const double *f, double *v_out, const double *e_coarse,
+                             double *r_coarse, cudaStream_t s);
+
 // gs.cu
 cudaError_t launch_rbgs(const LevelDev &L, double shift, double omega, int nu, double *v, const double *f,
                         cudaStream_t s);

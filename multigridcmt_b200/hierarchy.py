@@ -114,11 +114,21 @@ class Hierarchy:
         _lib.check(_lib.load().mgcmt_coarse_solve(self.handle, float(shift), _ptr(f), _ptr(v), _stream_ptr(torch)))
         return v
 
-    def vcycle(self, shift, nu1, nu2, smoother, omega, v, f):
+    def vcycle(self, shift, nu1, nu2, smoother, omega, v, f, v0_is_zero=False):
         torch = _lib.require_cuda()
         _lib.check(_lib.load().mgcmt_vcycle(self.handle, float(shift), int(nu1), int(nu2), int(smoother),
-                                            float(omega), _ptr(v), _ptr(f), _stream_ptr(torch)))
+                                            float(omega), _ptr(v), _ptr(f), 1 if v0_is_zero else 0,
+                                            _stream_ptr(torch)))
         return v
+
+    def fused_leg(self, level, mode, nu, shift, omega, v_in, f, v_out, e_coarse=None, r_coarse=None):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_fused_leg(self.handle, level, int(mode), int(nu), float(shift), float(omega),
+                                               _ptr(v_in) if v_in is not None else None, _ptr(f), _ptr(v_out),
+                                               _ptr(e_coarse) if e_coarse is not None else None,
+                                               _ptr(r_coarse) if r_coarse is not None else None,
+                                               _stream_ptr(torch)))
+        return v_out
 
     def rayleigh(self, level, x, out2):
         torch = _lib.require_cuda()

@@ -144,6 +144,69 @@ def test_level_operators_match_oracle(T, prod, o, dim, N, shift):
             assert rel(h.prolong_correct(l, de, w).cpu().numpy(), v + P @ e) < RTOL
 
 
+# ---------------------------------------------------------------------------------------------------
+# fused legs (nu sweeps + transfer in one pass) against the single-operator kernels and the oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,shift", [(64, 4.38639582), (256, 1.7), (512, 0.0)])
+def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift):
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    from multigridcmt_b200.operators import recognise
+    sm = prod[0]
+    osolver = o[1]
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    h = get_hierarchy(recognise(H, "2d"), 8)
+    mats, Rs, Ps = oracle_levels(o, H, N, "2d", 3)
+    om = 2. / 3.
+    for l in range(2):                       # level 0: 5-point kernel; level 1: 9-point kernel
+        n, nc = h.level_size(l), h.level_size(l + 1)
+        A = mats[l] - sp.eye(n) * shift
+        v = rand(n, 40 + l); f = rand(n, 50 + l); e = rand(nc, 60 + l)
+        dv, df, de = dev(T, v), dev(T, f), dev(T, e)
+        for nu in (0, 1, 2, 3, 4):
+            want_v = osolver.wjacobi(v.copy(), f.copy(), A, nu=nu, omega=om)[:, 0] if nu else v
+            want_r = Rs[l] @ (f - A @ want_v)
+            out = T.full_like(dv, 7.0); rc = T.full((nc,), 7.0, dtype=T.float64, device="cuda")
+            if nu:   # mode 0: smooth only
+                h.fused_leg(l, 0, nu, shift, om, dv, df, out)
+                assert rel(out.cpu().numpy(), want_v) < RTOL, ("smooth", l, nu)
+            out.fill_(7.0)
+            h.fused_leg(l, 1, nu, shift, om, dv, df, out, None, rc)     # mode 1: down leg
+            if nu:
+                assert rel(out.cpu().numpy(), want_v) < RTOL, ("down v", l, nu)
+            assert rel(rc.cpu().numpy(), want_r) < RTOL, ("down r", l, nu)
+            # mode 2: zero start
+            zv = osolver.wjacobi(np.zeros(n), f.copy(), A, nu=nu, omega=om)[:, 0] if nu else np.zeros(n)
+            out.fill_(7.0); rc.fill_(7.0)
+            h.fused_leg(l, 2, nu, shift, om, None, df, out, None, rc)
+            if nu:
+                assert rel(out.cpu().numpy(), zv) < RTOL, ("down0 v", l, nu)
+            assert rel(rc.cpu().numpy(), Rs[l] @ (f - A @ zv)) < RTOL, ("down0 r", l, nu)
+            # mode 3: up leg
+            vc = v + Ps[l] @ e
+            want_u = osolver.wjacobi(vc.copy(), f.copy(), A, nu=nu, omega=om)[:, 0] if nu else vc
+            out.fill_(7.0)
+            h.fused_leg(l, 3, nu, shift, om, dv, df, out, de, None)
+            assert rel(out.cpu().numpy(), want_u) < RTOL, ("up", l, nu)
+
+
+def test_fused_and_unfused_vcycles_agree(T, prod):
+    from multigridcmt_b200 import _lib
+    sm, s, _ = prod
+    lib = _lib.load()
+    N = 512
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    v0 = rand(N * N, 1); f = rand(N * N, 2)
+    try:
+        outs = []
+        for fused in (1, 0):
+            lib.mgcmt_set_option(b"fused", fused)
+            outs.append(s.vcycle(v0.copy(), f.copy(), H, sm, nu1=6, nu2=5, shift=4.386, lowest_level=8, dimension="2d"))
+    finally:
+        lib.mgcmt_set_option(b"fused", 1)
+    assert rel(outs[0], outs[1]) < 1e-12
+
+
 @pytest.mark.parametrize("dim,N,low,shift", [("2d", 32, 8, 1.76659015), ("2d", 32, 8, 7.00620149), ("2d", 16, 2, 0.0),
                                              ("1d", 64, 16, 3.9), ("2d", 64, 32, 4.38639582)])
 def test_coarse_solve_matches_spsolve(T, prod, o, dim, N, low, shift):

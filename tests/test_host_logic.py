@@ -110,7 +110,7 @@ def test_bad_arguments_are_errors_not_crashes():
     assert rc == 1 and b"power of two" in lib.mgcmt_last_error()
     rc = lib.mgcmt_hier_create(ctypes.byref(handle), 4, 4, 1, None, p, p, p, p, p, 2, None)
     assert rc == 1
-    assert lib.mgcmt_vcycle(None, 0.0, 4, 4, 0, 0.66, None, None, None) == 1
+    assert lib.mgcmt_vcycle(None, 0.0, 4, 4, 0, 0.66, None, None, 0, None) == 1
     assert lib.mgcmt_dot(-1, None, None, None, None) == 1
 
 
