@@ -126,12 +126,16 @@ int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, 
  *   mode 1: d_vout = J^nu(d_vin),  d_rcoarse = R (f - A_s d_vout)      MGCMTSolver.py:313-315
  *   mode 2: as mode 1 with d_vin == 0 (d_vin is not read; the zero start of every coarse level, :316)
  *   mode 3: d_vout = J^nu(d_vin + P d_ecoarse)                         MGCMTSolver.py:323-326
- * For nu == 0, modes 1/2 leave d_vout untouched (the residual is taken of d_vin). */
+ * For nu == 0, modes 1/2 leave d_vout untouched (the residual is taken of d_vin).
+ * mode | 16 selects the shared-memory tile implementation (used for mid-size levels) instead of the
+ * register-streaming one; both compute the same thing. */
 int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, double omega,
                     const double *d_vin, const double *d_f, double *d_vout, const double *d_ecoarse,
                     double *d_rcoarse, void *stream);
 /* runtime switches, for tests and A/B timing: "fused" (1/0), "fused_min_cols" (smallest level width
- * that uses the fused legs) */
+ * that uses the fused legs), "tile_max_cols" (levels at most this wide use the tile legs),
+ * "tail_max_cols" (levels at most this wide are collapsed into the single-CTA tail kernel; 0 = off),
+ * "fused_c5" (2|4 columns per lane on the 5-point level) */
 int mgcmt_set_option(const char *name, int value);
 
 /* ---- reductions / vector post-processing (MGCMTProcessor.py, Rayleigh quotients in the drivers) --

@@ -30,6 +30,8 @@ struct Profile {
 // runtime switches (mgcmt_set_option): fused legs on/off, smallest level width that uses them
 int g_opt_fused = 1;
 int g_opt_fused_min_cols = 64;
+int g_opt_tile_max_cols = 1024;  // levels this narrow (or narrower) use the shared-memory tile legs
+int g_opt_tail_max_cols = 64;    // levels this narrow are collapsed into the single-CTA tail kernel
 
 void prof_mark(cudaStream_t s) {
   if (!g_prof.on) return;
@@ -203,10 +205,36 @@ int get_inverse(mgcmt_hier *h, double shift, cudaStream_t s, double **out) {
   return MGCMT_OK;
 }
 
+bool use_tile(const mgcmt_hier *h, int l) {
+  const Level &L = h->lev[l];
+  return L.dev.ncols <= g_opt_tile_max_cols && L.dev.nrows >= 16 && L.dev.ncols >= 16;
+}
+cudaError_t launch_leg(const mgcmt_hier *h, int l, int mode, int nu, double shift, double omega, const double *vin,
+                       const double *f, double *vout, const double *e, double *rc, cudaStream_t s) {
+  const Level &L = h->lev[l];
+  if (use_tile(h, l)) return launch_tile_leg(L.dev, mode, nu, shift, omega, vin, f, vout, e, rc, s);
+  return launch_fused_leg(L.dev, mode, nu, shift, omega, vin, f, vout, e, rc, s);
+}
+
+// can levels l .. coarsest run inside the single-CTA tail kernel?
+bool use_tail(const mgcmt_hier *h, int l, int smoother, int nu1, int nu2, bool v_zero) {
+  if (!g_opt_fused || smoother != MGCMT_SMOOTH_WJACOBI || !h->coarsen_rows || !v_zero) return false;
+  if (nu1 != 4 || nu2 != 4) return false;
+  const int nl = h->nlev - l;
+  if (nl < 2 || nl > kTailMaxLevels) return false;
+  const Level &L = h->lev[l];
+  if (L.dev.ncols > g_opt_tail_max_cols || L.dev.nrows != L.dev.ncols || L.dev.row0 != 0) return false;
+  if (h->lev[h->nlev - 1].n > 256) return false;  // the dense inverse is read by one CTA
+  size_t words = 0, mx = 0;
+  for (int k = l; k < h->nlev; ++k) { words += 2 * ((h->lev[k].n + 1) & ~(size_t)1); mx = mx > h->lev[k].n ? mx : h->lev[k].n; }
+  words += (mx + 1) & ~(size_t)1;
+  return words * sizeof(double) <= 200 * 1024;
+}
+
 bool use_fused(const mgcmt_hier *h, int l, int smoother) {
   const Level &L = h->lev[l];
   return g_opt_fused && smoother == MGCMT_SMOOTH_WJACOBI && h->coarsen_rows && L.dev.nrows >= 16 &&
-         L.dev.ncols >= g_opt_fused_min_cols && L.dev.row0 == 0;
+         L.dev.ncols >= 16 && (L.dev.ncols >= g_opt_fused_min_cols || use_tile(h, l)) && L.dev.row0 == 0;
 }
 
 // down leg with the fused kernels: nu1 sweeps (in passes of <= 4) + residual + restriction into C.f.
@@ -219,7 +247,7 @@ int fused_down(mgcmt_hier *h, int l, double shift, double omega, int nu1, double
   int left = nu1;
   while (left > 4) {
     if (l == 0) prof_mark(s);
-    CU(launch_fused_leg(L.dev, FUSED_SMOOTH, 4, shift, omega, a, f, b, nullptr, nullptr, s));
+    CU(launch_leg(h, l, FUSED_SMOOTH, 4, shift, omega, a, f, b, nullptr, nullptr, s));
     if (l == 0) prof_mark(s);
     double *t = a; a = b; b = t;
     left -= 4;
@@ -227,8 +255,8 @@ int fused_down(mgcmt_hier *h, int l, double shift, double omega, int nu1, double
   }
   if (v_zero && left == 0) CU(cudaMemsetAsync(a, 0, sizeof(double) * L.n, s));
   if (l == 0) prof_mark(s);
-  CU(launch_fused_leg(L.dev, (v_zero && left > 0) ? FUSED_DOWN_ZERO : FUSED_DOWN, left, shift, omega, a, f, b,
-                      nullptr, C.f, s));
+  CU(launch_leg(h, l, (v_zero && left > 0) ? FUSED_DOWN_ZERO : FUSED_DOWN, left, shift, omega, a, f, b, nullptr,
+                C.f, s));
   if (l == 0) prof_mark(s);
   if (left > 0) { double *t = a; a = b; b = t; }
   *cur = a;
@@ -243,14 +271,14 @@ int fused_up(mgcmt_hier *h, int l, double shift, double omega, int nu2, double *
   int left = nu2;
   const int first = left > 4 ? 4 : left;
   if (l == 0) prof_mark(s);
-  CU(launch_fused_leg(L.dev, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
+  CU(launch_leg(h, l, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
   if (l == 0) prof_mark(s);
   { double *t = a; a = b; b = t; }
   left -= first;
   while (left > 0) {
     const int nu = left > 4 ? 4 : left;
     if (l == 0) prof_mark(s);
-    CU(launch_fused_leg(L.dev, FUSED_SMOOTH, nu, shift, omega, a, f, b, nullptr, nullptr, s));
+    CU(launch_leg(h, l, FUSED_SMOOTH, nu, shift, omega, a, f, b, nullptr, nullptr, s));
     if (l == 0) prof_mark(s);
     double *t = a; a = b; b = t;
     left -= nu;
@@ -271,6 +299,15 @@ int vcycle_level(mgcmt_hier *h, int l, double shift, int nu1, int nu2, int smoot
   }
   Level &C = h->lev[l + 1];
   int rc;
+  if (use_tail(h, l, smoother, nu1, nu2, v_zero)) {
+    double *inv = nullptr;
+    rc = get_inverse(h, shift, s, &inv);
+    if (rc) return rc;
+    LevelDev devs[kTailMaxLevels];
+    for (int k = l; k < h->nlev; ++k) devs[k - l] = h->lev[k].dev;
+    CU(launch_tail(devs, h->nlev - l, inv, shift, omega, f, v, s));
+    return MGCMT_OK;
+  }
   if (use_fused(h, l, smoother)) {
     double *cur = nullptr;
     rc = fused_down(h, l, shift, omega, nu1, v, f, v_zero, &cur, s);
@@ -533,6 +570,13 @@ int mgcmt_set_option(const char *name, int value) {
   if (!name) return fail(MGCMT_ERR_ARG, "null option name");
   if (!strcmp(name, "fused")) { g_opt_fused = value; return MGCMT_OK; }
   if (!strcmp(name, "fused_min_cols")) { g_opt_fused_min_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "tile_max_cols")) { g_opt_tile_max_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "tail_max_cols")) { g_opt_tail_max_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "fused_c5")) {
+    if (value != 2 && value != 4) return fail(MGCMT_ERR_ARG, "fused_c5 must be 2 or 4");
+    mgcmt::g_fused_c5 = value;
+    return MGCMT_OK;
+  }
   return fail(MGCMT_ERR_ARG, std::string("unknown option ") + name);
 }
 
@@ -542,14 +586,20 @@ int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, 
   if (rc) return rc;
   if (level + 1 >= h->nlev && mode != FUSED_SMOOTH) return fail(MGCMT_ERR_ARG, "no coarser level");
   if (!h->coarsen_rows || h->lev[level].dev.nrows < 2) return fail(MGCMT_ERR_ARG, "fused legs are 2-D only");
+  const bool force_tile = (mode & 16) != 0;  // bit 4: use the shared-memory tile implementation
+  mode &= 15;
   if (nu < 0 || nu > 4 || mode < 0 || mode > 3) return fail(MGCMT_ERR_ARG, "bad fused leg mode / nu");
   if (d_vin == d_vout) return fail(MGCMT_ERR_ARG, "fused legs are out of place");
   NEED_ALIGNED(d_f, d_vout);
   if (mode != FUSED_DOWN_ZERO) NEED_ALIGNED(d_vin);
   if (mode == FUSED_UP) NEED_ALIGNED(d_ecoarse);
   if (mode == FUSED_DOWN || mode == FUSED_DOWN_ZERO) NEED_ALIGNED(d_rcoarse);
-  CU(launch_fused_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
-                      (cudaStream_t)stream));
+  if (force_tile)
+    CU(launch_tile_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
+                       (cudaStream_t)stream));
+  else
+    CU(launch_fused_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
+                        (cudaStream_t)stream));
   return MGCMT_OK;
 }
 

@@ -105,17 +105,21 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   for (int i = tid; i < ntab; i += kWarps * 32) {
     const int row = tab0 + i;
     const int g = L.row0 + min(max(row, 0), L.nrows - 1);
+    const bool rin = (row >= 0 && row < L.nrows);
     RowCoef rc;
-    rc.ka_lo = L.ka_lo[g]; rc.ka_di = L.ka_di[g]; rc.ka_up = L.ka_up[g];
-    if (FIVE) { rc.ma_lo = 0.0; rc.ma_di = 1.0; rc.ma_up = 0.0; }
-    else { rc.ma_lo = L.ma_lo[g]; rc.ma_di = L.ma_di[g]; rc.ma_up = L.ma_up[g]; }
+    // Rows outside the grid get an all-zero operator row: with zero-filled inputs every stage then
+    // reproduces the Dirichlet zeros there by itself (x + w (0 - 0) = 0), so the hot loop needs no masks.
+    rc.ka_lo = rin ? L.ka_lo[g] : 0.0; rc.ka_di = rin ? L.ka_di[g] : 0.0; rc.ka_up = rin ? L.ka_up[g] : 0.0;
+    if (FIVE) { rc.ma_lo = 0.0; rc.ma_di = rin ? 1.0 : 0.0; rc.ma_up = 0.0; }
+    else { rc.ma_lo = rin ? L.ma_lo[g] : 0.0; rc.ma_di = rin ? L.ma_di[g] : 0.0; rc.ma_up = rin ? L.ma_up[g] : 0.0; }
     // slow = 1 if any row finalised while row `row` is the newest input (rows row-NSTAGE .. row-1) has a
     // diagonal different from the reference row's, i.e. the step needs the division path
     double slow = 0.0;
     for (int d = 1; d <= NSTAGE; ++d) {
-      const int g2 = L.row0 + min(max(row - d, 0), L.nrows - 1);
-      const double mad2 = FIVE ? 1.0 : L.ma_di[g2];
-      if (L.ka_di[g2] != kad_ref || mad2 != mad_ref) slow = 1.0;
+      const int r2 = row - d;
+      if (r2 < 0 || r2 >= L.nrows) continue;
+      const double mad2 = FIVE ? 1.0 : L.ma_di[L.row0 + r2];
+      if (L.ka_di[L.row0 + r2] != kad_ref || mad2 != mad_ref) slow = 1.0;
     }
     rc.slow = slow;
     rc.pad = 0.0;
@@ -139,10 +143,12 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     rlim[q] = (j >= 0 && j < L.ncols) ? (unsigned)L.nrows : 0u;
     colout[q] = (j >= u0 && j < u1);
     const int jc = min(max(j, 0), L.ncols - 1);
-    kbl[q] = L.kb_lo[jc]; kbd[q] = L.kb_di[jc]; kbu[q] = L.kb_up[jc];
+    const bool cin = (j >= 0 && j < L.ncols);
+    // columns outside the grid: zero operator column and zero relaxation weight (see the row table)
+    kbl[q] = cin ? L.kb_lo[jc] : 0.0; kbd[q] = cin ? L.kb_di[jc] : 0.0; kbu[q] = cin ? L.kb_up[jc] : 0.0;
     if (FIVE) { mbl[q] = 0.0; mbd[q] = 1.0; mbu[q] = 0.0; }
-    else { mbl[q] = L.mb_lo[jc]; mbd[q] = L.mb_di[jc]; mbu[q] = L.mb_up[jc]; }
-    wref[q] = omega / ((mad_ref * kbd[q] + kad_ref * mbd[q]) - shift);
+    else { mbl[q] = cin ? L.mb_lo[jc] : 0.0; mbd[q] = cin ? L.mb_di[jc] : 0.0; mbu[q] = cin ? L.mb_up[jc] : 0.0; }
+    wref[q] = cin ? omega / ((mad_ref * L.kb_di[jc] + kad_ref * (FIVE ? 1.0 : L.mb_di[jc])) - shift) : 0.0;
   }
   // 16-byte granules of this thread: both columns of a pair are inside or outside the grid together
   // (c0 and ncols are even)
@@ -150,41 +156,44 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
 #pragma unroll
   for (int g = 0; g < C / 2; ++g) pairin[g] = rlim[2 * g] != 0u;
 
-  double *my_v = ring_v + (size_t)tid * C;  // slot stride = kWarps*32*C
-  double *my_f = ring_f + (size_t)tid * C;
-  double *my_e = ring_e + (size_t)tid * CE;
-  constexpr int SLOT = kWarps * 32 * C;
-  constexpr int ESLOT = kWarps * 32 * CE;
+  // ring layout [slot][granule g][thread] of 16-byte granules: a warp's accesses to one granule are 512
+  // contiguous bytes, i.e. bank-conflict free for both the cp.async writes and the LDS.128 reads
+  constexpr int NT = kWarps * 32;
+  constexpr int SLOT = NT * C;          // doubles per ring slot
+  constexpr int ESLOT = NT * CE;
+  double2 *my_v = reinterpret_cast<double2 *>(ring_v) + tid;  // granule g of slot s: my_v[(s*(C/2) + g) * NT]
+  double2 *my_f = reinterpret_cast<double2 *>(ring_f) + tid;
+  double *my_e = ring_e + tid;                                 // coarse value g of slot s: my_e[(s*CE + g) * NT]
 
   // ---- asynchronous row fetch -------------------------------------------------------------------
   auto issue = [&](int t) {
     const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last;
     if (!ZEROV) {
-      double *dst = my_v + (size_t)(t & (kVRing - 1)) * SLOT;
+      double2 *dst = my_v + (t & (kVRing - 1)) * (C / 2) * NT;
 #pragma unroll
       for (int g = 0; g < C / 2; ++g) {
         const bool ok = rowin && pairin[g];
-        cpa16(dst + 2 * g, v_in + (ok ? (size_t)t * L.ncols + c0 + 2 * g : 0), ok);
+        cpa16(dst + g * NT, v_in + (ok ? (size_t)t * L.ncols + c0 + 2 * g : 0), ok);
       }
     }
     {
-      double *dst = my_f + (size_t)(t & (kFRing - 1)) * SLOT;
+      double2 *dst = my_f + (t & (kFRing - 1)) * (C / 2) * NT;
 #pragma unroll
       for (int g = 0; g < C / 2; ++g) {
         const bool ok = rowin && pairin[g];
-        cpa16(dst + 2 * g, f + (ok ? (size_t)t * L.ncols + c0 + 2 * g : 0), ok);
+        cpa16(dst + g * NT, f + (ok ? (size_t)t * L.ncols + c0 + 2 * g : 0), ok);
       }
     }
     if (PROLONG && (t & 1) == 0) {
       // coarse row I = t/2 is first needed by fine row t (even); coarse columns c0/2 .. c0/2+CE-1
       const int I = t >> 1;
       const bool rowc = (t >= 0) && I < nrc && t <= t_last;
-      double *dst = my_e + (size_t)(I & (kERing - 1)) * ESLOT;
+      double *dst = my_e + (I & (kERing - 1)) * ESLOT;
 #pragma unroll
       for (int g = 0; g < CE; ++g) {
         const int J = (c0 >> 1) + g;
         const bool ok = rowc && J >= 0 && J < ncc;
-        cpa8(dst + g, e_coarse + (ok ? (size_t)I * ncc + J : 0), ok);
+        cpa8(dst + g * NT, e_coarse + (ok ? (size_t)I * ncc + J : 0), ok);
       }
     }
     cpa_commit();
@@ -213,9 +222,13 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     // ---- stage 0: the input row t --------------------------------------------------------------
     double x[C];
     {
-      const double *src = my_v + (size_t)(t & (kVRing - 1)) * SLOT;
+      const double2 *src = my_v + (t & (kVRing - 1)) * (C / 2) * NT;
 #pragma unroll
-      for (int q = 0; q < C; ++q) x[q] = ZEROV ? 0.0 : src[q];
+      for (int g = 0; g < C / 2; ++g) {
+        const double2 xx = ZEROV ? make_double2(0.0, 0.0) : src[g * NT];
+        x[2 * g] = xx.x;
+        x[2 * g + 1] = xx.y;
+      }
     }
     if (PROLONG) {
       if (!ODD) {
@@ -223,10 +236,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
         // fine col c0+2g+1 = E[J], J = c0/2 + g.  Lane 0 has no left neighbour: its first column is the
         // outermost halo column of the strip; the up leg has no residual stage, so HALO = NU + 2 leaves
         // two columns of slack and that error never reaches a useful column.
-        const double *src = my_e + (size_t)((t >> 1) & (kERing - 1)) * ESLOT;
+        const double *src = my_e + ((t >> 1) & (kERing - 1)) * ESLOT;
         double e[CE];
 #pragma unroll
-        for (int g = 0; g < CE; ++g) e[g] = src[g];
+        for (int g = 0; g < CE; ++g) e[g] = src[g * NT];
         const double eleft = __shfl_up_sync(0xffffffffu, e[CE - 1], 1);
 #pragma unroll
         for (int q = 0; q < C; ++q) eprev[q] = ecur[q];
@@ -243,8 +256,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
         for (int q = 0; q < C; ++q) x[q] += ecur[q];
       }
     }
+    if (PROLONG) {  // the interpolated correction is the only input that is not already zero outside the grid
 #pragma unroll
-    for (int q = 0; q < C; ++q) x[q] = ((unsigned)t < rlim[q]) ? x[q] : 0.0;
+      for (int q = 0; q < C; ++q) x[q] = ((unsigned)t < rlim[q]) ? x[q] : 0.0;
+    }
 
     // refill the ring slot that row t just vacated (f slots are vacated NU+2 rows later; the f ring is
     // deep enough: kVRing + NU + 2 <= kFRing)
@@ -272,24 +287,32 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       }
       constexpr bool kIsRes = RESTRICT;  // (only the last stage, tested below with the unrolled k)
       const bool is_res = kIsRes && (k == NSTAGE - 1);
-      const double *fsrc = my_f + (size_t)(rho & (kFRing - 1)) * SLOT;
+      const double2 *fsrc = my_f + (rho & (kFRing - 1)) * (C / 2) * NT;
+      double ffv[C];
+#pragma unroll
+      for (int g = 0; g < C / 2; ++g) {
+        const double2 f2 = fsrc[g * NT];
+        ffv[2 * g] = f2.x;
+        ffv[2 * g + 1] = f2.y;
+      }
       double w[C];
 #pragma unroll
       for (int q = 0; q < C; ++q) w[q] = wref[q];
       if (SLOW && !is_res) {
-        const double cr_ka_di = tb[0].ka_di, cr_ma_di = FIVE ? 1.0 : tb[0].ma_di;
-        if (cr_ka_di != kad_ref || cr_ma_di != mad_ref) {
+        const double cr_ka_di = tb[0].ka_di, cr_ma_di = tb[0].ma_di;  // ma_di == 0 marks a row outside the grid
+        if (cr_ma_di != 0.0 && (cr_ka_di != kad_ref || cr_ma_di != mad_ref)) {
 #pragma unroll
-          for (int q = 0; q < C; ++q) w[q] = omega / ((cr_ma_di * kbd[q] + cr_ka_di * mbd[q]) - shift);
+          for (int q = 0; q < C; ++q)
+            w[q] = (rlim[q] != 0u) ? omega / ((cr_ma_di * kbd[q] + cr_ka_di * mbd[q]) - shift) : 0.0;
         }
       }
       double out[C];
 #pragma unroll
       for (int q = 0; q < C; ++q) {
         const double acc = st[k].a1[q] + (FIVE ? cr_ka_up * S[q] : (cr_ma_up * T[q] + cr_ka_up * S[q]));
-        const double ff = fsrc[q];
+        const double ff = ffv[q];
         const double o = is_res ? (ff - acc) : (st[k].xc[q] + w[q] * (ff - acc));
-        out[q] = ((unsigned)rho < rlim[q]) ? o : 0.0;
+        out[q] = o;
         // scatter the arriving row into the two rows still open
         st[k].a1[q] = st[k].a2[q] + ((FIVE ? (T[q] + cn_ka_di * S[q]) : (cn_ma_di * T[q] + cn_ka_di * S[q])) - shift * x[q]);
         st[k].a2[q] = FIVE ? cp_ka_lo * S[q] : (cp_ma_lo * T[q] + cp_ka_lo * S[q]);
@@ -412,13 +435,17 @@ static cudaError_t dispatch_mode(const LevelDev &L, int mode, double shift, doub
   return cudaErrorInvalidValue;
 }
 
+int g_fused_c5 = MGCMT_FUSED_C5;  // columns per lane on the 5-point level (2 or 4), switchable for A/B timing
+
 cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,
                              double *r_coarse, cudaStream_t s) {
   if (L.nrows < 2) return cudaErrorInvalidValue;  // 2-D levels only
 #define NU_CASE(NUV)                                                                                         \
   case NUV:                                                                                                  \
-    return L.five ? dispatch_mode<true, NUV, MGCMT_FUSED_C5>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s) \
+    if (L.five && g_fused_c5 == 4)                                                                           \
+      return dispatch_mode<true, NUV, 4>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);      \
+    return L.five ? dispatch_mode<true, NUV, 2>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s) \
                   : dispatch_mode<false, NUV, MGCMT_FUSED_C9>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
   switch (nu) {
     NU_CASE(0) NU_CASE(1) NU_CASE(2) NU_CASE(3) NU_CASE(4)

@@ -42,9 +42,19 @@ enum { FUSED_SMOOTH = 0,     // v_out = J^nu(v_in)
 #ifndef MGCMT_FUSED_C9
 #define MGCMT_FUSED_C9 2     // columns per lane, 9-point (Galerkin) levels
 #endif
+extern int g_fused_c5;
 cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,
                              double *r_coarse, cudaStream_t s);
+
+// tile.cu: shared-memory tile version of the fused legs (mid-size levels; same modes, nu 0..4 at run
+// time), and the single-CTA kernel that runs all levels first..coarsest of a V-cycle in one launch
+cudaError_t launch_tile_leg(const LevelDev &L, int mode, int nu, double shift, double omega, const double *v_in,
+                            const double *f, double *v_out, const double *e_coarse, double *r_coarse,
+                            cudaStream_t s);
+constexpr int kTailMaxLevels = 8;
+cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, double shift, double omega,
+                        const double *f_first, double *v_first, cudaStream_t s);
 
 // gs.cu
 cudaError_t launch_rbgs(const LevelDev &L, double shift, double omega, int nu, double *v, const double *f,

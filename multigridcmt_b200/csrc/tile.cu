@@ -1,0 +1,441 @@
+// tile.cu -- shared-memory kernels for the levels that are too small to feed the streaming kernels.
+//
+//  * tile_leg_kernel: one V-cycle leg (nu Jacobi sweeps fused with restriction of the residual, or with
+//    prolongation + correction) on a T x T tile per CTA, overlapped tiling: the CTA stages the tile plus
+//    a 6-point halo of v and f in shared memory, sweeps there (a barrier per sweep) and writes only
+//    its own T x T (and (T/2)^2 coarse) points.  Used for mid-size levels, where a whole leg is a few
+//    microseconds of work and what matters is having thousands of threads in flight, not HBM traffic.
+//  * tail_kernel: the whole bottom of the V-cycle -- every level from `first` down to the coarsest,
+//    including the exact coarsest solve, and back up -- in ONE launch by ONE CTA, all level vectors
+//    resident in shared memory (north_star: "coarse levels ... collapsed into a single persistent-CTA
+//    kernel").  Un-collapsed, these levels cost ~11 launches each at launch latency.
+//
+// Arithmetic: identical operators to stencil.cu / transfer.cu / coarse.cu (weighted Jacobi
+// MGCMTSolver.py:182-208, residual + full weighting :315, interpolation + correction :323-324, exact
+// coarsest solve :305-308 through the cached dense inverse).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgcmt {
+
+namespace {
+
+constexpr int kTileHalo = 6;  // >= nu + 2 for nu <= 4, even
+
+struct RowC {
+  double ka_lo, ka_di, ka_up, inside;  // inside: 1.0 for rows of the grid, else 0 (operator row zeroed)
+  double ma_lo, ma_di, ma_up, pad;
+};
+
+// (A_s x)(r,c) from a shared-memory array with pitch P; coefficient rows rc (this row), column factors in
+// registers.  FIVE: Ma = Mb = I.
+template <bool FIVE>
+__device__ __forceinline__ double apply_point(const double *__restrict__ a, int P, int r, int c, const RowC &rc,
+                                              double kbl, double kbd, double kbu, double mbl, double mbd,
+                                              double mbu, double shift) {
+  const double *p = a + r * P + c;
+  if (FIVE) {
+    const double t = kbl * p[-1] + kbd * p[0] + kbu * p[1];
+    return rc.ka_lo * p[-P] + (t + rc.ka_di * p[0]) + rc.ka_up * p[P] - shift * p[0];
+  }
+  const double tm = kbl * p[-P - 1] + kbd * p[-P] + kbu * p[-P + 1];
+  const double t0 = kbl * p[-1] + kbd * p[0] + kbu * p[1];
+  const double tp = kbl * p[P - 1] + kbd * p[P] + kbu * p[P + 1];
+  const double sm = mbl * p[-P - 1] + mbd * p[-P] + mbu * p[-P + 1];
+  const double s0 = mbl * p[-1] + mbd * p[0] + mbu * p[1];
+  const double sp = mbl * p[P - 1] + mbd * p[P] + mbu * p[P + 1];
+  return (rc.ma_lo * tm + rc.ka_lo * sm) + (rc.ma_di * t0 + rc.ka_di * s0) + (rc.ma_up * tp + rc.ka_up * sp) -
+         shift * p[0];
+}
+
+}  // namespace
+
+// mode: FUSED_SMOOTH / FUSED_DOWN / FUSED_DOWN_ZERO / FUSED_UP (kernels.h)
+template <bool FIVE, int T>
+__global__ void __launch_bounds__((T + 2 * kTileHalo) * (T == 32 ? 5 : 9))
+tile_leg_kernel(LevelDev L, int mode, int nu, double shift, double omega, const double *__restrict__ v_in,
+                const double *__restrict__ f, double *__restrict__ v_out, const double *__restrict__ e_coarse,
+                double *__restrict__ r_coarse) {
+  constexpr int H = kTileHalo;
+  constexpr int E = T + 2 * H;   // extended tile edge
+  constexpr int P = E + 1;       // pitch
+  constexpr int RPP = (T == 32 ? 5 : 9);  // tile rows handled per pass (threads = E * RPP)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *A = reinterpret_cast<double *>(smem_raw);
+  double *B = A + E * P;
+  double *F = B + E * P;
+  RowC *rows = reinterpret_cast<RowC *>(F + E * P);
+
+  const int tid = threadIdx.x;
+  const int c = tid % E;        // this thread's tile column (fixed)
+  const int rbase = tid / E;    // first tile row
+  const int i0 = blockIdx.y * T - H, j0 = blockIdx.x * T - H;  // grid coords of tile (0,0)
+  const int gj = j0 + c;
+  const bool cin = (gj >= 0 && gj < L.ncols);
+  const int gjc = min(max(gj, 0), L.ncols - 1);
+  const int ncc = L.ncols / 2, nrc = L.nrows / 2;
+
+  // row table (zero operator rows outside the grid: Dirichlet zeros reproduce themselves)
+  for (int r = tid; r < E; r += blockDim.x) {
+    const int gi = i0 + r;
+    const bool rin = (gi >= 0 && gi < L.nrows);
+    const int g = L.row0 + min(max(gi, 0), L.nrows - 1);
+    RowC rc;
+    rc.ka_lo = rin ? L.ka_lo[g] : 0.0; rc.ka_di = rin ? L.ka_di[g] : 0.0; rc.ka_up = rin ? L.ka_up[g] : 0.0;
+    if (FIVE) { rc.ma_lo = 0.0; rc.ma_di = rin ? 1.0 : 0.0; rc.ma_up = 0.0; }
+    else { rc.ma_lo = rin ? L.ma_lo[g] : 0.0; rc.ma_di = rin ? L.ma_di[g] : 0.0; rc.ma_up = rin ? L.ma_up[g] : 0.0; }
+    rc.inside = rin ? 1.0 : 0.0;
+    rc.pad = 0.0;
+    rows[r] = rc;
+  }
+  // column factors of this thread (zero outside the grid)
+  const double kbl = cin ? L.kb_lo[gjc] : 0.0, kbd = cin ? L.kb_di[gjc] : 0.0, kbu = cin ? L.kb_up[gjc] : 0.0;
+  const double mbl = (!FIVE && cin) ? L.mb_lo[gjc] : 0.0, mbd = FIVE ? 1.0 : (cin ? L.mb_di[gjc] : 0.0),
+               mbu = (!FIVE && cin) ? L.mb_up[gjc] : 0.0;
+  const double kbd_g = L.kb_di[gjc], mbd_g = FIVE ? 1.0 : L.mb_di[gjc];
+  // omega / diag for the tile's reference row (its middle); other rows (first / last grid rows of a
+  // Galerkin level) take the division
+  const int gref = L.row0 + min(max(i0 + E / 2, 0), L.nrows - 1);
+  const double kad_ref = L.ka_di[gref], mad_ref = FIVE ? 1.0 : L.ma_di[gref];
+  const double wref = cin ? omega / ((mad_ref * kbd_g + kad_ref * mbd_g) - shift) : 0.0;
+
+  // ---- stage the tile: A = v (+ P e), F = f ---------------------------------------------------------
+  for (int r = rbase; r < E; r += RPP) {
+    const int gi = i0 + r;
+    const bool in = cin && gi >= 0 && gi < L.nrows;
+    double x = 0.0, ff = 0.0;
+    if (in) {
+      ff = f[(size_t)gi * L.ncols + gj];
+      if (mode != FUSED_DOWN_ZERO) x = v_in[(size_t)gi * L.ncols + gj];
+      if (mode == FUSED_UP) {
+        // (P e)(gi,gj): odd index -> injection of coarse (i-1)/2; even -> mean of coarse i/2-1 and i/2
+        const int I = gi >> 1, J = gj >> 1;
+        auto E_ = [&](int ii, int jj) -> double {
+          return (ii >= 0 && ii < nrc && jj >= 0 && jj < ncc) ? e_coarse[(size_t)ii * ncc + jj] : 0.0;
+        };
+        double pe;
+        if (gi & 1) {
+          pe = (gj & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
+        } else {
+          const double top = (gj & 1) ? E_(I - 1, J) : 0.5 * (E_(I - 1, J - 1) + E_(I - 1, J));
+          const double bot = (gj & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
+          pe = 0.5 * (top + bot);
+        }
+        x += pe;
+      }
+    }
+    A[r * P + c] = x;
+    F[r * P + c] = ff;
+  }
+  __syncthreads();
+
+  // ---- nu weighted-Jacobi sweeps, ping-pong A <-> B.  Border ring of the extended tile is never
+  // updated: it is halo whose staleness moves inwards one point per sweep (H >= nu + 2 covers it).
+  const bool cint = (c >= 1 && c <= E - 2);
+  for (int s = 0; s < nu; ++s) {
+    for (int r = rbase; r < E; r += RPP) {
+      double o = A[r * P + c];
+      if (cint && r >= 1 && r <= E - 2) {
+        const RowC rc = rows[r];
+        const double av = apply_point<FIVE>(A, P, r, c, rc, kbl, kbd, kbu, mbl, mbd, mbu, shift);
+        double w = wref;
+        if (rc.ka_di != kad_ref || rc.ma_di != mad_ref)
+          w = (cin && rc.inside != 0.0) ? omega / ((rc.ma_di * kbd_g + rc.ka_di * mbd_g) - shift) : 0.0;
+        o = o + w * (F[r * P + c] - av);
+      }
+      B[r * P + c] = o;
+    }
+    __syncthreads();
+    double *t = A; A = B; B = t;
+  }
+
+  // ---- write the tile's own points ------------------------------------------------------------------
+  if (!((mode == FUSED_DOWN || mode == FUSED_DOWN_ZERO) && nu == 0)) {
+    if (c >= H && c < H + T && cin) {
+      for (int r = rbase; r < E; r += RPP) {
+        const int gi = i0 + r;
+        if (r >= H && r < H + T && gi < L.nrows) v_out[(size_t)gi * L.ncols + gj] = A[r * P + c];
+      }
+    }
+  }
+  if (mode != FUSED_DOWN && mode != FUSED_DOWN_ZERO) return;
+
+  // ---- residual into B, then full weighting ---------------------------------------------------------
+  for (int r = rbase; r < E; r += RPP) {
+    double res = 0.0;
+    if (cint && r >= 1 && r <= E - 2) {
+      const RowC rc = rows[r];
+      if (cin && rc.inside != 0.0)
+        res = F[r * P + c] - apply_point<FIVE>(A, P, r, c, rc, kbl, kbd, kbu, mbl, mbd, mbu, shift);
+    }
+    B[r * P + c] = res;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (T / 2) * (T / 2); idx += blockDim.x) {
+    const int ci = idx / (T / 2), cj = idx - ci * (T / 2);
+    const int I = (blockIdx.y * T) / 2 + ci, J = (blockIdx.x * T) / 2 + cj;
+    if (I < nrc && J < ncc) {
+      const double *p = B + (H + 2 * ci) * P + (H + 2 * cj);
+      const double a0 = 0.25 * p[0] + 0.5 * p[1] + 0.25 * p[2];
+      const double a1 = 0.25 * p[P] + 0.5 * p[P + 1] + 0.25 * p[P + 2];
+      const double a2 = 0.25 * p[2 * P] + 0.5 * p[2 * P + 1] + 0.25 * p[2 * P + 2];
+      r_coarse[(size_t)I * ncc + J] = 0.25 * a0 + 0.5 * a1 + 0.25 * a2;
+    }
+  }
+}
+
+template <bool FIVE, int T>
+static cudaError_t launch_tile_t(const LevelDev &L, int mode, int nu, double shift, double omega,
+                                 const double *v_in, const double *f, double *v_out, const double *e_coarse,
+                                 double *r_coarse, cudaStream_t s) {
+  constexpr int E = T + 2 * kTileHalo;
+  constexpr int threads = E * (T == 32 ? 5 : 9);
+  const size_t smem = sizeof(double) * 3 * E * (E + 1) + sizeof(RowC) * E;
+  auto kern = tile_leg_kernel<FIVE, T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((L.ncols + T - 1) / T, (L.nrows + T - 1) / T);
+  kern<<<grid, threads, smem, s>>>(L, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tile_leg(const LevelDev &L, int mode, int nu, double shift, double omega, const double *v_in,
+                            const double *f, double *v_out, const double *e_coarse, double *r_coarse,
+                            cudaStream_t s) {
+  if (nu < 0 || nu > 4 || L.nrows < 2) return cudaErrorInvalidValue;
+  const bool small = (long long)L.nrows * L.ncols <= 256LL * 256;  // 16x16 tiles keep >= 64 CTAs busy
+  if (L.five)
+    return small ? launch_tile_t<true, 16>(L, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s)
+                 : launch_tile_t<true, 32>(L, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  return small ? launch_tile_t<false, 16>(L, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s)
+               : launch_tile_t<false, 32>(L, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+}
+
+// =====================================================================================================
+// tail kernel: levels first .. last (last = coarsest) of one hierarchy in one CTA
+// =====================================================================================================
+struct TailLevel {
+  LevelDev dev;
+  int voff, foff;  // offsets (doubles) of this level's v and f inside the shared-memory arena
+};
+struct TailArgs {
+  int nlev;                 // number of levels handled (>= 2: at least one smoothing level + the coarsest)
+  TailLevel lev[kTailMaxLevels];
+  int tmpoff;               // scratch of the largest level
+  const double *inv;        // dense inverse of the coarsest shifted operator (n_c x n_c, row-major)
+  double shift, omega;
+};
+
+namespace {
+
+// one weighted-Jacobi sweep src -> dst on a whole level held in shared memory (pitch = ncols).
+// zero_src: src is identically zero (first sweep after the zero initial guess): v = w f.
+template <bool FIVE>
+__device__ void tail_sweep(const LevelDev &L, double shift, double omega, const double *src, const double *f,
+                           double *dst, bool zero_src) {
+  const int n = L.nrows * L.ncols, nc = L.ncols;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int i = idx / nc, j = idx - i * nc;
+    const double kal = L.ka_lo[i], kad = L.ka_di[i], kau = L.ka_up[i];
+    const double kbl = L.kb_lo[j], kbd = L.kb_di[j], kbu = L.kb_up[j];
+    double mad = 1.0, mbd = 1.0;
+    double av = 0.0, x = 0.0;
+    if (!FIVE) { mad = L.ma_di[i]; mbd = L.mb_di[j]; }
+    if (!zero_src) {
+      auto at = [&](int ii, int jj) -> double {
+        return (ii >= 0 && ii < L.nrows && jj >= 0 && jj < nc) ? src[ii * nc + jj] : 0.0;
+      };
+      x = src[idx];
+      if (FIVE) {
+        const double t = kbl * at(i, j - 1) + kbd * x + kbu * at(i, j + 1);
+        av = kal * at(i - 1, j) + (t + kad * x) + kau * at(i + 1, j) - shift * x;
+      } else {
+        const double mal = L.ma_lo[i], mau = L.ma_up[i];
+        const double mbl = L.mb_lo[j], mbu = L.mb_up[j];
+        const double xm0 = at(i - 1, j - 1), xm1 = at(i - 1, j), xm2 = at(i - 1, j + 1);
+        const double x00 = at(i, j - 1), x02 = at(i, j + 1);
+        const double xp0 = at(i + 1, j - 1), xp1 = at(i + 1, j), xp2 = at(i + 1, j + 1);
+        const double tm = kbl * xm0 + kbd * xm1 + kbu * xm2, sm = mbl * xm0 + mbd * xm1 + mbu * xm2;
+        const double t0 = kbl * x00 + kbd * x + kbu * x02, s0 = mbl * x00 + mbd * x + mbu * x02;
+        const double tp = kbl * xp0 + kbd * xp1 + kbu * xp2, sp = mbl * xp0 + mbd * xp1 + mbu * xp2;
+        av = (mal * tm + kal * sm) + (mad * t0 + kad * s0) + (mau * tp + kau * sp) - shift * x;
+      }
+    }
+    const double d = (mad * kbd + kad * mbd) - shift;
+    dst[idx] = x + (omega / d) * (f[idx] - av);
+  }
+}
+
+template <bool FIVE>
+__device__ void tail_residual(const LevelDev &L, double shift, const double *v, const double *f, double *r) {
+  const int n = L.nrows * L.ncols, nc = L.ncols;
+  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+    const int i = idx / nc, j = idx - i * nc;
+    auto at = [&](int ii, int jj) -> double {
+      return (ii >= 0 && ii < L.nrows && jj >= 0 && jj < nc) ? v[ii * nc + jj] : 0.0;
+    };
+    const double kal = L.ka_lo[i], kad = L.ka_di[i], kau = L.ka_up[i];
+    const double kbl = L.kb_lo[j], kbd = L.kb_di[j], kbu = L.kb_up[j];
+    const double x = v[idx];
+    double av;
+    if (FIVE) {
+      const double t = kbl * at(i, j - 1) + kbd * x + kbu * at(i, j + 1);
+      av = kal * at(i - 1, j) + (t + kad * x) + kau * at(i + 1, j) - shift * x;
+    } else {
+      const double mal = L.ma_lo[i], mad = L.ma_di[i], mau = L.ma_up[i];
+      const double mbl = L.mb_lo[j], mbd = L.mb_di[j], mbu = L.mb_up[j];
+      const double xm0 = at(i - 1, j - 1), xm1 = at(i - 1, j), xm2 = at(i - 1, j + 1);
+      const double x00 = at(i, j - 1), x02 = at(i, j + 1);
+      const double xp0 = at(i + 1, j - 1), xp1 = at(i + 1, j), xp2 = at(i + 1, j + 1);
+      const double tm = kbl * xm0 + kbd * xm1 + kbu * xm2, sm = mbl * xm0 + mbd * xm1 + mbu * xm2;
+      const double t0 = kbl * x00 + kbd * x + kbu * x02, s0 = mbl * x00 + mbd * x + mbu * x02;
+      const double tp = kbl * xp0 + kbd * xp1 + kbu * xp2, sp = mbl * xp0 + mbd * xp1 + mbu * xp2;
+      av = (mal * tm + kal * sm) + (mad * t0 + kad * s0) + (mau * tp + kau * sp) - shift * x;
+    }
+    r[idx] = f[idx] - av;
+  }
+}
+
+__device__ void tail_restrict(const LevelDev &Lf, const double *r, double *fc) {
+  const int nrc = Lf.nrows / 2, ncc = Lf.ncols / 2, nc = Lf.ncols;
+  for (int idx = threadIdx.x; idx < nrc * ncc; idx += blockDim.x) {
+    const int I = idx / ncc, J = idx - I * ncc;
+    auto at = [&](int ii, int jj) -> double { return (ii < Lf.nrows && jj < nc) ? r[ii * nc + jj] : 0.0; };
+    const double a0 = 0.25 * at(2 * I, 2 * J) + 0.5 * at(2 * I, 2 * J + 1) + 0.25 * at(2 * I, 2 * J + 2);
+    const double a1 = 0.25 * at(2 * I + 1, 2 * J) + 0.5 * at(2 * I + 1, 2 * J + 1) + 0.25 * at(2 * I + 1, 2 * J + 2);
+    const double a2 = 0.25 * at(2 * I + 2, 2 * J) + 0.5 * at(2 * I + 2, 2 * J + 1) + 0.25 * at(2 * I + 2, 2 * J + 2);
+    fc[idx] = 0.25 * a0 + 0.5 * a1 + 0.25 * a2;
+  }
+}
+
+// v += P e
+__device__ void tail_prolong_add(const LevelDev &Lf, const double *e, double *v) {
+  const int nrc = Lf.nrows / 2, ncc = Lf.ncols / 2, nc = Lf.ncols;
+  for (int idx = threadIdx.x; idx < Lf.nrows * nc; idx += blockDim.x) {
+    const int i = idx / nc, j = idx - i * nc;
+    const int I = i >> 1, J = j >> 1;
+    auto E_ = [&](int ii, int jj) -> double { return (ii >= 0 && ii < nrc && jj >= 0 && jj < ncc) ? e[ii * ncc + jj] : 0.0; };
+    double pe;
+    if (i & 1) {
+      pe = (j & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
+    } else {
+      const double top = (j & 1) ? E_(I - 1, J) : 0.5 * (E_(I - 1, J - 1) + E_(I - 1, J));
+      const double bot = (j & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
+      pe = 0.5 * (top + bot);
+    }
+    v[idx] += pe;
+  }
+}
+
+template <bool FIVE>
+__device__ void tail_smooth4(const LevelDev &L, double shift, double omega, double *v, const double *f, double *tmp,
+                             bool v_zero) {
+  // 4 sweeps v -> tmp -> v -> tmp -> v
+  tail_sweep<FIVE>(L, shift, omega, v, f, tmp, v_zero);
+  __syncthreads();
+  tail_sweep<FIVE>(L, shift, omega, tmp, f, v, false);
+  __syncthreads();
+  tail_sweep<FIVE>(L, shift, omega, v, f, tmp, false);
+  __syncthreads();
+  tail_sweep<FIVE>(L, shift, omega, tmp, f, v, false);
+  __syncthreads();
+}
+
+}  // namespace
+
+// f_first (global) -> v_first (global): the V-cycle restricted to levels first..last with a zero start
+__global__ void __launch_bounds__(1024) tail_kernel(TailArgs a, const double *__restrict__ f_first,
+                                                    double *__restrict__ v_first) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *arena = reinterpret_cast<double *>(smem_raw);
+  double *tmp = arena + a.tmpoff;
+  const int nl = a.nlev;
+  {
+    const int n0 = a.lev[0].dev.nrows * a.lev[0].dev.ncols;
+    double *f0 = arena + a.lev[0].foff;
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) f0[i] = f_first[i];
+  }
+  __syncthreads();
+  // down
+  for (int l = 0; l < nl - 1; ++l) {
+    const LevelDev &L = a.lev[l].dev;
+    double *v = arena + a.lev[l].voff, *f = arena + a.lev[l].foff;
+    if (L.five) tail_smooth4<true>(L, a.shift, a.omega, v, f, tmp, true);
+    else tail_smooth4<false>(L, a.shift, a.omega, v, f, tmp, true);
+    if (L.five) tail_residual<true>(L, a.shift, v, f, tmp);
+    else tail_residual<false>(L, a.shift, v, f, tmp);
+    __syncthreads();
+    tail_restrict(L, tmp, arena + a.lev[l + 1].foff);
+    __syncthreads();
+  }
+  // coarsest: v = inv f (one warp per row, same summation order as gemv_kernel in coarse.cu)
+  {
+    const LevelDev &L = a.lev[nl - 1].dev;
+    const int n = L.nrows * L.ncols;
+    const double *f = arena + a.lev[nl - 1].foff;
+    double *v = arena + a.lev[nl - 1].voff;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = warp; r < n; r += nw) {
+      const double *row = a.inv + (size_t)r * n;
+      double acc = 0.0;
+      for (int c = lane; c < n; c += 32) acc += row[c] * f[c];
+      acc = warp_sum(acc);
+      if (lane == 0) v[r] = acc;
+    }
+  }
+  __syncthreads();
+  // up
+  for (int l = nl - 2; l >= 0; --l) {
+    const LevelDev &L = a.lev[l].dev;
+    double *v = arena + a.lev[l].voff, *f = arena + a.lev[l].foff;
+    tail_prolong_add(L, arena + a.lev[l + 1].voff, v);
+    __syncthreads();
+    if (L.five) tail_smooth4<true>(L, a.shift, a.omega, v, f, tmp, false);
+    else tail_smooth4<false>(L, a.shift, a.omega, v, f, tmp, false);
+  }
+  {
+    const int n0 = a.lev[0].dev.nrows * a.lev[0].dev.ncols;
+    const double *v0 = arena + a.lev[0].voff;
+    for (int i = threadIdx.x; i < n0; i += blockDim.x) v_first[i] = v0[i];
+  }
+}
+
+cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, double shift, double omega,
+                        const double *f_first, double *v_first, cudaStream_t s) {
+  if (nlev < 2 || nlev > kTailMaxLevels) return cudaErrorInvalidValue;
+  TailArgs a;
+  a.nlev = nlev;
+  a.inv = inv;
+  a.shift = shift;
+  a.omega = omega;
+  int off = 0, maxn = 0;
+  for (int l = 0; l < nlev; ++l) {
+    const int n = levels[l].nrows * levels[l].ncols;
+    a.lev[l].dev = levels[l];
+    a.lev[l].voff = off; off += (n + 1) & ~1;
+    a.lev[l].foff = off; off += (n + 1) & ~1;
+    if (n > maxn) maxn = n;
+  }
+  a.tmpoff = off;
+  off += (maxn + 1) & ~1;
+  const size_t smem = sizeof(double) * (size_t)off;
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int n0 = levels[0].nrows * levels[0].ncols;
+  int threads = n0 >= 1024 ? 1024 : (n0 < 64 ? 64 : ((n0 + 31) / 32) * 32);
+  tail_kernel<<<1, threads, smem, s>>>(a, f_first, v_first);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace mgcmt

@@ -147,8 +147,9 @@ def test_level_operators_match_oracle(T, prod, o, dim, N, shift):
 # ---------------------------------------------------------------------------------------------------
 # fused legs (nu sweeps + transfer in one pass) against the single-operator kernels and the oracle
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", [0, 16])   # 0: register-streaming kernel, 16: shared-memory tile kernel
 @pytest.mark.parametrize("N,shift", [(64, 4.38639582), (256, 1.7), (512, 0.0)])
-def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift):
+def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift, impl):
     from multigridcmt_b200 import _lib
     from multigridcmt_b200.hierarchy import get_hierarchy
     from multigridcmt_b200.operators import recognise
@@ -168,17 +169,17 @@ def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift):
             want_r = Rs[l] @ (f - A @ want_v)
             out = T.full_like(dv, 7.0); rc = T.full((nc,), 7.0, dtype=T.float64, device="cuda")
             if nu:   # mode 0: smooth only
-                h.fused_leg(l, 0, nu, shift, om, dv, df, out)
+                h.fused_leg(l, 0 | impl, nu, shift, om, dv, df, out)
                 assert rel(out.cpu().numpy(), want_v) < RTOL, ("smooth", l, nu)
             out.fill_(7.0)
-            h.fused_leg(l, 1, nu, shift, om, dv, df, out, None, rc)     # mode 1: down leg
+            h.fused_leg(l, 1 | impl, nu, shift, om, dv, df, out, None, rc)     # mode 1: down leg
             if nu:
                 assert rel(out.cpu().numpy(), want_v) < RTOL, ("down v", l, nu)
             assert rel(rc.cpu().numpy(), want_r) < RTOL, ("down r", l, nu)
             # mode 2: zero start
             zv = osolver.wjacobi(np.zeros(n), f.copy(), A, nu=nu, omega=om)[:, 0] if nu else np.zeros(n)
             out.fill_(7.0); rc.fill_(7.0)
-            h.fused_leg(l, 2, nu, shift, om, None, df, out, None, rc)
+            h.fused_leg(l, 2 | impl, nu, shift, om, None, df, out, None, rc)
             if nu:
                 assert rel(out.cpu().numpy(), zv) < RTOL, ("down0 v", l, nu)
             assert rel(rc.cpu().numpy(), Rs[l] @ (f - A @ zv)) < RTOL, ("down0 r", l, nu)
@@ -186,25 +187,35 @@ def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift):
             vc = v + Ps[l] @ e
             want_u = osolver.wjacobi(vc.copy(), f.copy(), A, nu=nu, omega=om)[:, 0] if nu else vc
             out.fill_(7.0)
-            h.fused_leg(l, 3, nu, shift, om, dv, df, out, de, None)
+            h.fused_leg(l, 3 | impl, nu, shift, om, dv, df, out, de, None)
             assert rel(out.cpu().numpy(), want_u) < RTOL, ("up", l, nu)
 
 
-def test_fused_and_unfused_vcycles_agree(T, prod):
+def test_all_vcycle_paths_agree(T, prod):
+    """streaming legs / tile legs / single-CTA tail / one-kernel-per-operator: same V-cycle."""
     from multigridcmt_b200 import _lib
     sm, s, _ = prod
     lib = _lib.load()
     N = 512
     H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
     v0 = rand(N * N, 1); f = rand(N * N, 2)
+    configs = [dict(fused=0), dict(fused=1, tile_max_cols=0, tail_max_cols=0), dict(fused=1, tile_max_cols=1024, tail_max_cols=0),
+               dict(fused=1, tile_max_cols=1024, tail_max_cols=64), dict(fused=1, tile_max_cols=0, tail_max_cols=32)]
     try:
         outs = []
-        for fused in (1, 0):
-            lib.mgcmt_set_option(b"fused", fused)
-            outs.append(s.vcycle(v0.copy(), f.copy(), H, sm, nu1=6, nu2=5, shift=4.386, lowest_level=8, dimension="2d"))
+        for cfg in configs:
+            for k, v in cfg.items():
+                _lib.check(lib.mgcmt_set_option(k.encode(), v))
+            outs.append((s.vcycle(v0.copy(), f.copy(), H, sm, nu1=6, nu2=5, shift=4.386, lowest_level=8, dimension="2d"),
+                         s.vcycle(np.zeros(N * N), f.copy(), H, sm, shift=1.7, lowest_level=8, dimension="2d"),
+                         s.vcycle(np.zeros(64 * 64), f[:4096].copy(), (-1. / np.pi ** 2) * sm.laplacian(64, "2d"), sm,
+                                  shift=1.7, lowest_level=4, dimension="2d")))
     finally:
-        lib.mgcmt_set_option(b"fused", 1)
-    assert rel(outs[0], outs[1]) < 1e-12
+        for k, v in dict(fused=1, tile_max_cols=1024, tail_max_cols=64).items():
+            lib.mgcmt_set_option(k.encode(), v)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert rel(b, a) < 1e-12
 
 
 @pytest.mark.parametrize("dim,N,low,shift", [("2d", 32, 8, 1.76659015), ("2d", 32, 8, 7.00620149), ("2d", 16, 2, 0.0),

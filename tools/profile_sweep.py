@@ -11,12 +11,18 @@ from multigridcmt_b200.hierarchy import get_hierarchy
 
 what = sys.argv[1] if len(sys.argv) > 1 else "jacobi"
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+for kv in sys.argv[3:]:   # option=value pairs for mgcmt_set_option
+    k, v = kv.split("=")
+    _lib.check(_lib.load().mgcmt_set_option(k.encode(), int(v)))
 sm = MGCMTStencilMaker()
 H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
 h = get_hierarchy(H, 8)
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 v = torch.rand(N * N, dtype=torch.float64, device="cuda", generator=g)
 f = torch.rand(N * N, dtype=torch.float64, device="cuda", generator=g)
+out = torch.empty_like(v); rc = torch.rand(N * N // 4, dtype=torch.float64, device="cuda", generator=g)
+v1 = torch.rand(N * N // 4, dtype=torch.float64, device="cuda", generator=g); f1 = v1 * 0.5; out1 = torch.empty_like(v1)
+rc1 = torch.empty(N * N // 16, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 reps = 5
@@ -25,6 +31,12 @@ for it in range(2):
     for _ in range(reps):
         if what == "jacobi":
             h.smooth(0, _lib.SMOOTH_WJACOBI, 1.7, 2.0 / 3.0, 4, v, f)
+        elif what == "down":
+            h.fused_leg(0, 1, 4, 1.7, 2.0 / 3.0, v, f, out, None, rc)
+        elif what == "up":
+            h.fused_leg(0, 3, 4, 1.7, 2.0 / 3.0, v, f, out, rc, None)
+        elif what == "down1":
+            h.fused_leg(1, 1, 4, 1.7, 2.0 / 3.0, v1, f1, out1, None, rc1)
         else:
             h.vcycle(1.7, 4, 4, _lib.SMOOTH_WJACOBI, 2.0 / 3.0, v, f)
     e1.record()
