@@ -30,7 +30,7 @@ struct Profile {
 // runtime switches (mgcmt_set_option): fused legs on/off, smallest level width that uses them
 int g_opt_fused = 1;
 int g_opt_fused_min_cols = 64;
-int g_opt_tile_max_cols = 1024;  // levels this narrow (or narrower) use the shared-memory tile legs
+int g_opt_tile_max_cols = 256;   // levels this narrow (or narrower) use the shared-memory tile legs
 int g_opt_tail_max_cols = 64;    // levels this narrow are collapsed into the single-CTA tail kernel
 
 void prof_mark(cudaStream_t s) {

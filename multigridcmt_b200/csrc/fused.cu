@@ -30,8 +30,15 @@ namespace mgcmt {
 
 namespace {
 
-constexpr int kVRing = 8;    // prefetch depth of the v ring (rows)
-constexpr int kFRing = 16;   // f ring: prefetch depth + NU + 2 rows of queue
+#ifndef MGCMT_VRING
+#define MGCMT_VRING 4
+#endif
+#ifndef MGCMT_MIN_CTAS
+#define MGCMT_MIN_CTAS 2
+#endif
+constexpr int kVRing = MGCMT_VRING;  // prefetch depth of the v ring (rows, power of two)
+constexpr int kFRing = kVRing + 8;   // f ring: prefetch depth + up to NU + 2 rows of queue (not a power of
+                                     // two: slots are tracked incrementally)
 constexpr int kERing = 4;    // coarse-row ring (PROLONG)
 constexpr int kWarps = 4;    // warps per CTA (independent strips)
 
@@ -65,7 +72,7 @@ struct Stage {
 }  // namespace
 
 template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, (C == 4 ? MGCMT_MIN_CTAS : 1))
 fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v_in,
                  const double *__restrict__ f, double *__restrict__ v_out,
                  const double *__restrict__ e_coarse, double *__restrict__ r_coarse, int rows_per_chunk) {
@@ -166,7 +173,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   double *my_e = ring_e + tid;                                 // coarse value g of slot s: my_e[(s*CE + g) * NT]
 
   // ---- asynchronous row fetch -------------------------------------------------------------------
-  auto issue = [&](int t) {
+  auto issue = [&](int t, int fslot) {
     const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last;
     if (!ZEROV) {
       double2 *dst = my_v + (t & (kVRing - 1)) * (C / 2) * NT;
@@ -177,7 +184,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       }
     }
     {
-      double2 *dst = my_f + (t & (kFRing - 1)) * (C / 2) * NT;
+      double2 *dst = my_f + fslot * (C / 2) * NT;
 #pragma unroll
       for (int g = 0; g < C / 2; ++g) {
         const bool ok = rowin && pairin[g];
@@ -214,6 +221,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
 
   // one time step: input row t enters, every stage finalises one row.  ODD (row parity) and SLOW (some
   // finalised row needs omega/diag recomputed) are compile-time so the common path is branch-free.
+  int fs = 0;  // f-ring slot of the current input row t: (t - t_begin) mod kFRing
   auto step = [&](int t, auto odd_tag, auto slow_tag) {
     constexpr bool ODD = decltype(odd_tag)::value;
     constexpr bool SLOW = decltype(slow_tag)::value;
@@ -263,7 +271,11 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
 
     // refill the ring slot that row t just vacated (f slots are vacated NU+2 rows later; the f ring is
     // deep enough: kVRing + NU + 2 <= kFRing)
-    issue(t + kVRing);
+    {
+      int fnew = fs + kVRing;
+      fnew -= (fnew >= kFRing) ? kFRing : 0;
+      issue(t + kVRing, fnew);
+    }
 
     // ---- stages 1..NSTAGE: row n of stage k-1 arrives, row n-1 of stage k is finalised -----------
 #pragma unroll
@@ -287,7 +299,9 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       }
       constexpr bool kIsRes = RESTRICT;  // (only the last stage, tested below with the unrolled k)
       const bool is_res = kIsRes && (k == NSTAGE - 1);
-      const double2 *fsrc = my_f + (rho & (kFRing - 1)) * (C / 2) * NT;
+      int frho = fs - (k + 1);  // slot of row rho = t - k - 1 (slots of rows before t_begin hold garbage that
+      frho += (frho < 0) ? kFRing : 0;  // only ever reaches rows outside every valid region)
+      const double2 *fsrc = my_f + frho * (C / 2) * NT;
       double ffv[C];
 #pragma unroll
       for (int g = 0; g < C / 2; ++g) {
@@ -364,10 +378,11 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
         if (rowok && colout[2 * g])
           st_stream2(v_out + (size_t)t * L.ncols + c0 + 2 * g, make_double2(x[2 * g], x[2 * g + 1]));
     }
+    fs = (fs + 1 == kFRing) ? 0 : fs + 1;
   };
 
 #pragma unroll
-  for (int d = 0; d < kVRing; ++d) issue(t_begin + d);
+  for (int d = 0; d < kVRing; ++d) issue(t_begin + d, d);
 
   using TrueT = std::integral_constant<bool, true>;
   using FalseT = std::integral_constant<bool, false>;
@@ -389,7 +404,7 @@ template <int C>
 static size_t fused_smem_bytes(bool prolong, int rows_per_chunk) {
   size_t b = sizeof(double) * (size_t)(kVRing + kFRing) * kWarps * 32 * C;
   if (prolong) b += sizeof(double) * (size_t)kERing * kWarps * 32 * (C / 2);
-  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 40);  // rows t_begin-NSTAGE-1 .. t_last+2
+  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 24);  // rows t_begin-NSTAGE-1 .. t_last+2 (<= rpc + 22)
   return b;
 }
 
@@ -401,7 +416,7 @@ static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega,
   const int strips = (L.ncols + USEFUL - 1) / USEFUL;
   const int gx = (strips + kWarps - 1) / kWarps;
   int rpc = 128;
-  while (rpc > 16 && (long long)gx * ((L.nrows + rpc - 1) / rpc) < 148LL * 2) rpc >>= 1;
+  while (rpc > 16 && (long long)gx * ((L.nrows + rpc - 1) / rpc) < 264) rpc >>= 1;  // ~90 % of 148 SMs x 2 CTAs
   if (rpc > L.nrows) rpc = L.nrows;  // nrows is a power of two >= 2 here (even chunks)
   const size_t smem = fused_smem_bytes<C>(PROLONG, rpc);
   auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C>;
