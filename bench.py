@@ -271,7 +271,8 @@ def run_ours(args):
         for c in range(k):
             # w0 = 0 as in the reference's drivers (2DPotGS.py:94): flagged, so the zero vector is not read
             _lib.check(lib.mgcmt_vcycle(h.handle, shifts[c], 4, 4, smoother_code, omega, _ptr(W[c]), _ptr(V[c]), 1, stream))
-            _lib.check(lib.mgcmt_normalize(n, _ptr(W[c]), stream))
+            # Rayleigh quotient w^T H w / w^T w (one fused pass); the normalisation w/||w|| of 2DPotGS.py:96 is
+            # what the first step of the Gram-Schmidt below does for every column anyway
             _lib.check(lib.mgcmt_rayleigh(h.handle, 0, _ptr(W[c]), _ptr(rq[c]), stream))
         _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(W), 1, stream))
         V.copy_(W)

@@ -31,7 +31,7 @@ struct Profile {
 int g_opt_fused = 1;
 int g_opt_fused_min_cols = 64;
 int g_opt_tile_max_cols = 256;   // levels this narrow (or narrower) use the shared-memory tile legs
-int g_opt_tail_max_cols = 64;    // levels this narrow are collapsed into the single-CTA tail kernel
+int g_opt_tail_max_cols = 32;    // levels this narrow are collapsed into the single-CTA tail kernel
 
 void prof_mark(cudaStream_t s) {
   if (!g_prof.on) return;
@@ -225,10 +225,9 @@ bool use_tail(const mgcmt_hier *h, int l, int smoother, int nu1, int nu2, bool v
   const Level &L = h->lev[l];
   if (L.dev.ncols > g_opt_tail_max_cols || L.dev.nrows != L.dev.ncols || L.dev.row0 != 0) return false;
   if (h->lev[h->nlev - 1].n > 256) return false;  // the dense inverse is read by one CTA
-  size_t words = 0, mx = 0;
-  for (int k = l; k < h->nlev; ++k) { words += 2 * ((h->lev[k].n + 1) & ~(size_t)1); mx = mx > h->lev[k].n ? mx : h->lev[k].n; }
-  words += (mx + 1) & ~(size_t)1;
-  return words * sizeof(double) <= 200 * 1024;
+  LevelDev devs[kTailMaxLevels];
+  for (int k = l; k < h->nlev; ++k) devs[k - l] = h->lev[k].dev;
+  return tail_smem_bytes(devs, nl) <= kTailMaxSmem;
 }
 
 bool use_fused(const mgcmt_hier *h, int l, int smoother) {
@@ -631,9 +630,17 @@ int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2
   if (rc) return rc;
   Level &L = h->lev[level];
   cudaStream_t s = (cudaStream_t)stream;
-  CU(launch_apply(L.dev, 0.0, d_x, L.tmp, nullptr, nullptr, s));
-  CU(launch_dot((long long)L.n, L.tmp, d_x, sc->partials, d_out2, s));
-  CU(launch_dot((long long)L.n, d_x, d_x, sc->partials, d_out2 + 1, s));
+  // one pass: the operator-apply kernel keeps x^T(Ax) and x^T x partial sums per CTA (L.tmp as scratch),
+  // then one ordered finish
+  const int nb = march_grid_blocks(L.dev);
+  if ((size_t)2 * nb > L.n) {  // tiny level: scratch too small for the partials, use the plain route
+    CU(launch_apply(L.dev, 0.0, d_x, L.tmp, nullptr, nullptr, s));
+    CU(launch_dot((long long)L.n, L.tmp, d_x, sc->partials, d_out2, s));
+    CU(launch_dot((long long)L.n, d_x, d_x, sc->partials, d_out2 + 1, s));
+    return MGCMT_OK;
+  }
+  CU(launch_rayleigh_partials(L.dev, d_x, L.tmp, nullptr, nullptr, s));
+  CU(launch_finish(2, nb, L.tmp, d_out2, s));
   return MGCMT_OK;
 }
 
@@ -662,6 +669,17 @@ int mgcmt_gramschmidt(long long n, int k, double *d_V, int modified, void *strea
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   double *scal = sc->scal;  // [0] sumsq / <q,q>, [1..16] dots, [32..] <u_i,u_i> (classical)
+  if (modified && (n % 2 == 0) && al16(d_V) && k <= 8) {
+    // MGCMTProcessor.py:44-50, two fused passes per column (reduce.cu): 29 instead of 42 vector passes at k = 4
+    CU(launch_dot(n, d_V, d_V, sc->partials, scal, s));  // ||w_0||^2
+    for (int i = 0; i < k; ++i) {
+      double *qi = d_V + (size_t)i * n;
+      const int m = k - 1 - i;
+      CU(launch_mgs_scale_dots(n, m, qi, scal, qi + n, n, sc->partials, scal + 1, s));  // scal[1] = <q,q>, scal[2..] dots
+      if (m > 0) CU(launch_mgs_update(n, m, qi, scal + 1, qi + n, n, sc->partials, scal, s));  // scal[0] = ||w_{i+1}||^2
+    }
+    return MGCMT_OK;
+  }
   if (modified) {
     // MGCMTProcessor.py:44-50
     for (int i = 0; i < k; ++i) {

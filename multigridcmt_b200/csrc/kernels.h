@@ -6,7 +6,7 @@
 
 namespace mgcmt {
 
-enum { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_APPLY = 2 };
+enum { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_APPLY = 2, OP_RAYLEIGH = 3 };
 
 // number of kernels this library has launched since it was loaded (reported by bench.py as gpu_launches)
 extern long long g_launch_count;
@@ -20,6 +20,10 @@ cudaError_t launch_residual(const LevelDev &L, double shift, const double *v, co
                             const double *halo_top, const double *halo_bot, cudaStream_t s);
 cudaError_t launch_apply(const LevelDev &L, double shift, const double *x, double *y, const double *halo_top,
                          const double *halo_bot, cudaStream_t s);
+
+cudaError_t launch_rayleigh_partials(const LevelDev &L, const double *x, double *partials, const double *halo_top,
+                                     const double *halo_bot, cudaStream_t s);
+int march_grid_blocks(const LevelDev &L);
 
 // transfer.cu
 cudaError_t launch_galerkin_tridiag(int n_fine, const double *lo, const double *di, const double *up,
@@ -53,6 +57,8 @@ cudaError_t launch_tile_leg(const LevelDev &L, int mode, int nu, double shift, d
                             const double *f, double *v_out, const double *e_coarse, double *r_coarse,
                             cudaStream_t s);
 constexpr int kTailMaxLevels = 8;
+constexpr size_t kTailMaxSmem = 216 * 1024;
+size_t tail_smem_bytes(const LevelDev *levels, int nlev);
 cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, double shift, double omega,
                         const double *f_first, double *v_first, cudaStream_t s);
 
@@ -75,6 +81,13 @@ cudaError_t launch_dot(long long n, const double *x, const double *y, double *pa
 // out[m] = <x0 + m*stride, y>, m < M <= 16; partials: M * kReduceBlocks doubles of scratch
 cudaError_t launch_multidot(long long n, int M, const double *x0, long long stride, const double *y,
                             double *partials, double *out, cudaStream_t s);
+// out[m] = ordered sum of partials[m*B .. m*B+B)
+cudaError_t launch_finish(int M, int B, const double *partials, double *out, cudaStream_t s);
+// fused modified Gram-Schmidt passes (MGCMTProcessor.py:44-50), see reduce.cu
+cudaError_t launch_mgs_scale_dots(long long n, int m, double *wi, const double *sumsq, const double *wj0,
+                                  long long stride, double *partials, double *out, cudaStream_t s);
+cudaError_t launch_mgs_update(long long n, int m, const double *qi, const double *dots, double *wj0, long long stride,
+                              double *partials, double *out_sumsq, cudaStream_t s);
 cudaError_t launch_scale_by_inv_norm(long long n, double *x, const double *sumsq, cudaStream_t s);
 cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *denom, double sign,
                             const double *x, double *y, cudaStream_t s);

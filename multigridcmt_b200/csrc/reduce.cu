@@ -104,6 +104,123 @@ cudaError_t launch_multidot(long long n, int M, const double *x0, long long stri
   return cudaGetLastError();
 }
 
+cudaError_t launch_finish(int M, int B, const double *partials, double *out, cudaStream_t s) {
+  finish_kernel<<<M, 256, 0, s>>>(B, partials, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---- fused modified Gram-Schmidt (MGCMTProcessor.py:44-50) -----------------------------------------
+// pass 1 of column i:  q = w_i / sqrt(*sumsq) (written in place);  partial sums of <q,q> (slot 0) and of
+//                      <w_j, q> for the m later columns j (slots 1..m)
+template <int M>
+__global__ void __launch_bounds__(kRedThreads)
+mgs_scale_dots_kernel(long long n, double *__restrict__ wi, const double *__restrict__ sumsq,
+                      const double *__restrict__ wj0, long long stride, double *__restrict__ partials) {
+  const double nrm = sqrt(*sumsq);
+  double acc[M + 1];
+#pragma unroll
+  for (int m = 0; m <= M; ++m) acc[m] = 0.0;
+  const long long n2 = n >> 1;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += step) {
+    double2 q = reinterpret_cast<const double2 *>(wi)[i];
+    q.x = q.x / nrm;
+    q.y = q.y / nrm;
+    reinterpret_cast<double2 *>(wi)[i] = q;
+    acc[0] += q.x * q.x;
+    acc[0] += q.y * q.y;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const double2 w = reinterpret_cast<const double2 *>(wj0 + m * stride)[i];
+      acc[m + 1] += w.x * q.x;
+      acc[m + 1] += w.y * q.y;
+    }
+  }
+  __shared__ double sm[M + 1][kRedThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int m = 0; m <= M; ++m) {
+    const double s = warp_sum(acc[m]);
+    if (lane == 0) sm[m][w] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x <= M) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedThreads / 32; ++k) s += sm[threadIdx.x][k];
+    partials[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// pass 2 of column i:  w_j -= (dots[1+j] / dots[0]) q  for the m later columns;  partial sums of the new
+//                      ||w_{i+1}||^2 (the next column to be normalised)
+template <int M>
+__global__ void __launch_bounds__(kRedThreads)
+mgs_update_kernel(long long n, const double *__restrict__ qi, const double *__restrict__ dots,
+                  double *__restrict__ wj0, long long stride, double *__restrict__ partials) {
+  double c[M];
+  const double qq = dots[0];
+#pragma unroll
+  for (int m = 0; m < M; ++m) c[m] = dots[1 + m] / qq;
+  double acc = 0.0;
+  const long long n2 = n >> 1;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += step) {
+    const double2 q = reinterpret_cast<const double2 *>(qi)[i];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      double2 w = reinterpret_cast<double2 *>(wj0 + m * stride)[i];
+      w.x -= c[m] * q.x;
+      w.y -= c[m] * q.y;
+      reinterpret_cast<double2 *>(wj0 + m * stride)[i] = w;
+      if (m == 0) {
+        acc += w.x * w.x;
+        acc += w.y * w.y;
+      }
+    }
+  }
+  __shared__ double sm[kRedThreads / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const double s = warp_sum(acc);
+  if (lane == 0) sm[w] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedThreads / 32; ++k) t += sm[k];
+    partials[blockIdx.x] = t;
+  }
+}
+
+// both need n even and 16-byte aligned columns (checked by the caller, which otherwise uses the un-fused path)
+cudaError_t launch_mgs_scale_dots(long long n, int m, double *wi, const double *sumsq, const double *wj0,
+                                  long long stride, double *partials, double *out, cudaStream_t s) {
+  const int B = blocks_for(n);
+  switch (m) {
+#define CASE(MM) case MM: mgs_scale_dots_kernel<MM><<<B, kRedThreads, 0, s>>>(n, wi, sumsq, wj0, stride, partials); break;
+    CASE(0) CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+#undef CASE
+    default: return cudaErrorInvalidValue;
+  }
+  finish_kernel<<<m + 1, 256, 0, s>>>(B, partials, out);
+  count_launch(2);
+  return cudaGetLastError();
+}
+cudaError_t launch_mgs_update(long long n, int m, const double *qi, const double *dots, double *wj0, long long stride,
+                              double *partials, double *out_sumsq, cudaStream_t s) {
+  const int B = blocks_for(n);
+  switch (m) {
+#define CASE(MM) case MM: mgs_update_kernel<MM><<<B, kRedThreads, 0, s>>>(n, qi, dots, wj0, stride, partials); break;
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7)
+#undef CASE
+    default: return cudaErrorInvalidValue;
+  }
+  finish_kernel<<<1, 256, 0, s>>>(B, partials, out_sumsq);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_dot(long long n, const double *x, const double *y, double *partials, double *out,
                        cudaStream_t s) {
   return launch_multidot(n, 1, x, 0, y, partials, out, s);

@@ -77,7 +77,7 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
     cp_async16(&ring_v[slot][tid], s + jc, ok);
     if (lane == 0) cp_async8(&ring_e[slot][warp][0], s + (jc > 0 ? jc - 1 : 0), ok && jc > 0);
     if (lane == 31) cp_async8(&ring_e[slot][warp][1], s + (jc + 2 < L.ncols ? jc + 2 : 0), ok && jc + 2 < L.ncols);
-    if (OP != OP_APPLY) {
+    if (OP != OP_APPLY && OP != OP_RAYLEIGH) {
       const bool okf = active && i >= i_begin && i < i_end;
       cp_async16(&ring_f[slot][tid], f + (okf ? (size_t)i * L.ncols + jc : 0), okf);
     }
@@ -130,6 +130,7 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
 
   double last_kad = 0, last_mad = 0, winv0 = 0, winv1 = 0;
   bool have_w = false;
+  double rq_num = 0.0, rq_den = 0.0;
 
   for (int i = i_begin; i < i_end; ++i) {
     // slot of row i-1 is free now: refill it with row i-1+kPF, then wait for row i+1
@@ -137,7 +138,7 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
     cp_async_wait<kPF - 2>();
     n = horiz(fetch(i + 1));
     double2 ff = make_double2(0.0, 0.0);
-    if (OP != OP_APPLY) ff = ring_f[(i + 1) & (kPF - 1)][tid];
+    if (OP != OP_APPLY && OP != OP_RAYLEIGH) ff = ring_f[(i + 1) & (kPF - 1)][tid];
     const int gi = L.row0 + i;
     const double kal = L.ka_lo[gi], kad = L.ka_di[gi], kau = L.ka_up[gi];
     double av0, av1, mad = 1.0;
@@ -151,7 +152,13 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
       av1 = (mal * p.t1 + kal * p.s1) + (mad * c.t1 + kad * c.s1) + (mau * n.t1 + kau * n.s1) - shift * c.x1;
     }
     double2 o;
-    if (OP == OP_JACOBI) {
+    if (OP == OP_RAYLEIGH) {
+      rq_num += c.x0 * av0;
+      rq_num += c.x1 * av1;
+      rq_den += c.x0 * c.x0;
+      rq_den += c.x1 * c.x1;
+      o.x = o.y = 0.0;
+    } else if (OP == OP_JACOBI) {
       if (!have_w || kad != last_kad || mad != last_mad) {  // block-uniform: first and last rows only
         const double d0 = FIVE ? (kad + kbd0) - shift : (mad * kbd0 + kad * mbd0) - shift;
         const double d1 = FIVE ? (kad + kbd1) - shift : (mad * kbd1 + kad * mbd1) - shift;
@@ -168,11 +175,26 @@ stencil_march_kernel(LevelDev L, double shift, double omega, const double *__res
       o.x = av0;
       o.y = av1;
     }
-    if (active) st_stream2(out + (size_t)i * L.ncols + j0, o);
+    if (OP != OP_RAYLEIGH && active) st_stream2(out + (size_t)i * L.ncols + j0, o);
     p = c;
     c = n;
   }
   cp_async_wait<0>();
+  if (OP == OP_RAYLEIGH) {
+    // block partials of x^T A x and x^T x: out[b] and out[nblocks + b], summed in order by finish_kernel
+    __shared__ double red[2][TPB / 32];
+    const double a = warp_sum(rq_num), b = warp_sum(rq_den);
+    if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+    __syncthreads();
+    if (tid == 0) {
+      double sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int w = 0; w < TPB / 32; ++w) { sa += red[0][w]; sb += red[1][w]; }
+      const int nb = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+      out[bid] = sa;
+      out[nb + bid] = sb;
+    }
+  }
 }
 
 // launch geometry: CTAs of 32/64/128 threads (2 columns per thread); rows per CTA chosen so the grid
@@ -216,6 +238,19 @@ cudaError_t launch_residual(const LevelDev &L, double shift, const double *v, co
 cudaError_t launch_apply(const LevelDev &L, double shift, const double *x, double *y, const double *halo_top,
                          const double *halo_bot, cudaStream_t s) {
   return launch_march<OP_APPLY>(L, shift, 0.0, x, nullptr, y, halo_top, halo_bot, s);
+}
+// partials: 2 * (number of CTAs) doubles (see march_grid_blocks); block b writes x^T A x and x^T x partials
+cudaError_t launch_rayleigh_partials(const LevelDev &L, const double *x, double *partials, const double *halo_top,
+                                     const double *halo_bot, cudaStream_t s) {
+  return launch_march<OP_RAYLEIGH>(L, 0.0, 0.0, x, nullptr, partials, halo_top, halo_bot, s);
+}
+int march_grid_blocks(const LevelDev &L) {
+  const int TPB = L.ncols >= 1024 ? 128 : (L.ncols >= 256 ? 64 : 32);
+  const int col_blocks = (L.ncols / 2 + TPB - 1) / TPB;
+  int rpc = 32;
+  while (rpc > 2 && (long long)col_blocks * ((L.nrows + rpc - 1) / rpc) < 148LL * 4) rpc >>= 1;
+  if (rpc > L.nrows) rpc = L.nrows;
+  return col_blocks * ((L.nrows + rpc - 1) / rpc);
 }
 
 }  // namespace mgcmt

@@ -217,133 +217,63 @@ cudaError_t launch_tile_leg(const LevelDev &L, int mode, int nu, double shift, d
 }
 
 // =====================================================================================================
-// tail kernel: levels first .. last (last = coarsest) of one hierarchy in one CTA
+// tail kernel: levels first .. last (last = coarsest) of one hierarchy in one CTA.
+// Shared-memory arena per level: V and TMP with a one-point zero halo (pitch n+2: no bounds checks, and
+// the Dirichlet zeros / the truncated last restriction row come for free), F, W = omega/diag (the
+// divisions are done once per launch, not once per sweep), and the 12 tridiagonal factor arrays.
 // =====================================================================================================
 struct TailLevel {
   LevelDev dev;
-  int voff, foff;  // offsets (doubles) of this level's v and f inside the shared-memory arena
+  int voff, toff, foff, woff, coff;  // offsets (doubles) into the arena: V, TMP (haloed), F, W, coefficients
 };
 struct TailArgs {
   int nlev;                 // number of levels handled (>= 2: at least one smoothing level + the coarsest)
   TailLevel lev[kTailMaxLevels];
-  int tmpoff;               // scratch of the largest level
+  int arena_doubles;
   const double *inv;        // dense inverse of the coarsest shifted operator (n_c x n_c, row-major)
   double shift, omega;
 };
 
 namespace {
 
-// one weighted-Jacobi sweep src -> dst on a whole level held in shared memory (pitch = ncols).
-// zero_src: src is identically zero (first sweep after the zero initial guess): v = w f.
-template <bool FIVE>
-__device__ void tail_sweep(const LevelDev &L, double shift, double omega, const double *src, const double *f,
-                           double *dst, bool zero_src) {
-  const int n = L.nrows * L.ncols, nc = L.ncols;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const int i = idx / nc, j = idx - i * nc;
-    const double kal = L.ka_lo[i], kad = L.ka_di[i], kau = L.ka_up[i];
-    const double kbl = L.kb_lo[j], kbd = L.kb_di[j], kbu = L.kb_up[j];
-    double mad = 1.0, mbd = 1.0;
-    double av = 0.0, x = 0.0;
-    if (!FIVE) { mad = L.ma_di[i]; mbd = L.mb_di[j]; }
-    if (!zero_src) {
-      auto at = [&](int ii, int jj) -> double {
-        return (ii >= 0 && ii < L.nrows && jj >= 0 && jj < nc) ? src[ii * nc + jj] : 0.0;
-      };
-      x = src[idx];
-      if (FIVE) {
-        const double t = kbl * at(i, j - 1) + kbd * x + kbu * at(i, j + 1);
-        av = kal * at(i - 1, j) + (t + kad * x) + kau * at(i + 1, j) - shift * x;
-      } else {
-        const double mal = L.ma_lo[i], mau = L.ma_up[i];
-        const double mbl = L.mb_lo[j], mbu = L.mb_up[j];
-        const double xm0 = at(i - 1, j - 1), xm1 = at(i - 1, j), xm2 = at(i - 1, j + 1);
-        const double x00 = at(i, j - 1), x02 = at(i, j + 1);
-        const double xp0 = at(i + 1, j - 1), xp1 = at(i + 1, j), xp2 = at(i + 1, j + 1);
-        const double tm = kbl * xm0 + kbd * xm1 + kbu * xm2, sm = mbl * xm0 + mbd * xm1 + mbu * xm2;
-        const double t0 = kbl * x00 + kbd * x + kbu * x02, s0 = mbl * x00 + mbd * x + mbu * x02;
-        const double tp = kbl * xp0 + kbd * xp1 + kbu * xp2, sp = mbl * xp0 + mbd * xp1 + mbu * xp2;
-        av = (mal * tm + kal * sm) + (mad * t0 + kad * s0) + (mau * tp + kau * sp) - shift * x;
-      }
-    }
-    const double d = (mad * kbd + kad * mbd) - shift;
-    dst[idx] = x + (omega / d) * (f[idx] - av);
-  }
+// coefficient block of a level: [ka_lo ka_di ka_up ma_lo ma_di ma_up] x nrows, then the same for columns
+struct TailCoef {
+  const double *ka_lo, *ka_di, *ka_up, *ma_lo, *ma_di, *ma_up, *kb_lo, *kb_di, *kb_up, *mb_lo, *mb_di, *mb_up;
+};
+__device__ __forceinline__ TailCoef tail_coef(double *base, int nr, int nc) {
+  TailCoef c;
+  c.ka_lo = base; c.ka_di = base + nr; c.ka_up = base + 2 * nr;
+  c.ma_lo = base + 3 * nr; c.ma_di = base + 4 * nr; c.ma_up = base + 5 * nr;
+  double *b = base + 6 * nr;
+  c.kb_lo = b; c.kb_di = b + nc; c.kb_up = b + 2 * nc;
+  c.mb_lo = b + 3 * nc; c.mb_di = b + 4 * nc; c.mb_up = b + 5 * nc;
+  return c;
 }
 
-template <bool FIVE>
-__device__ void tail_residual(const LevelDev &L, double shift, const double *v, const double *f, double *r) {
-  const int n = L.nrows * L.ncols, nc = L.ncols;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    const int i = idx / nc, j = idx - i * nc;
-    auto at = [&](int ii, int jj) -> double {
-      return (ii >= 0 && ii < L.nrows && jj >= 0 && jj < nc) ? v[ii * nc + jj] : 0.0;
-    };
-    const double kal = L.ka_lo[i], kad = L.ka_di[i], kau = L.ka_up[i];
-    const double kbl = L.kb_lo[j], kbd = L.kb_di[j], kbu = L.kb_up[j];
-    const double x = v[idx];
-    double av;
-    if (FIVE) {
-      const double t = kbl * at(i, j - 1) + kbd * x + kbu * at(i, j + 1);
-      av = kal * at(i - 1, j) + (t + kad * x) + kau * at(i + 1, j) - shift * x;
-    } else {
-      const double mal = L.ma_lo[i], mad = L.ma_di[i], mau = L.ma_up[i];
-      const double mbl = L.mb_lo[j], mbd = L.mb_di[j], mbu = L.mb_up[j];
-      const double xm0 = at(i - 1, j - 1), xm1 = at(i - 1, j), xm2 = at(i - 1, j + 1);
-      const double x00 = at(i, j - 1), x02 = at(i, j + 1);
-      const double xp0 = at(i + 1, j - 1), xp1 = at(i + 1, j), xp2 = at(i + 1, j + 1);
-      const double tm = kbl * xm0 + kbd * xm1 + kbu * xm2, sm = mbl * xm0 + mbd * xm1 + mbu * xm2;
-      const double t0 = kbl * x00 + kbd * x + kbu * x02, s0 = mbl * x00 + mbd * x + mbu * x02;
-      const double tp = kbl * xp0 + kbd * xp1 + kbu * xp2, sp = mbl * xp0 + mbd * xp1 + mbu * xp2;
-      av = (mal * tm + kal * sm) + (mad * t0 + kad * s0) + (mau * tp + kau * sp) - shift * x;
-    }
-    r[idx] = f[idx] - av;
-  }
+// (A_s x)(i,j) on a haloed array (pitch P = nc + 2), general 9-point separable form (Ma = Mb = I on a
+// 5-point level: the extra terms are exact zeros)
+__device__ __forceinline__ double tail_apply(const double *x, int P, int i, int j, const TailCoef &c, double shift) {
+  const double *p = x + (i + 1) * P + (j + 1);
+  const double kbl = c.kb_lo[j], kbd = c.kb_di[j], kbu = c.kb_up[j];
+  const double mbl = c.mb_lo[j], mbd = c.mb_di[j], mbu = c.mb_up[j];
+  const double tm = kbl * p[-P - 1] + kbd * p[-P] + kbu * p[-P + 1], sm = mbl * p[-P - 1] + mbd * p[-P] + mbu * p[-P + 1];
+  const double t0 = kbl * p[-1] + kbd * p[0] + kbu * p[1], s0 = mbl * p[-1] + mbd * p[0] + mbu * p[1];
+  const double tp = kbl * p[P - 1] + kbd * p[P] + kbu * p[P + 1], sp = mbl * p[P - 1] + mbd * p[P] + mbu * p[P + 1];
+  return (c.ma_lo[i] * tm + c.ka_lo[i] * sm) + (c.ma_di[i] * t0 + c.ka_di[i] * s0) + (c.ma_up[i] * tp + c.ka_up[i] * sp) -
+         shift * p[0];
 }
 
-__device__ void tail_restrict(const LevelDev &Lf, const double *r, double *fc) {
-  const int nrc = Lf.nrows / 2, ncc = Lf.ncols / 2, nc = Lf.ncols;
-  for (int idx = threadIdx.x; idx < nrc * ncc; idx += blockDim.x) {
-    const int I = idx / ncc, J = idx - I * ncc;
-    auto at = [&](int ii, int jj) -> double { return (ii < Lf.nrows && jj < nc) ? r[ii * nc + jj] : 0.0; };
-    const double a0 = 0.25 * at(2 * I, 2 * J) + 0.5 * at(2 * I, 2 * J + 1) + 0.25 * at(2 * I, 2 * J + 2);
-    const double a1 = 0.25 * at(2 * I + 1, 2 * J) + 0.5 * at(2 * I + 1, 2 * J + 1) + 0.25 * at(2 * I + 1, 2 * J + 2);
-    const double a2 = 0.25 * at(2 * I + 2, 2 * J) + 0.5 * at(2 * I + 2, 2 * J + 1) + 0.25 * at(2 * I + 2, 2 * J + 2);
-    fc[idx] = 0.25 * a0 + 0.5 * a1 + 0.25 * a2;
+// dst = src + W (F - A_s src)  (one weighted-Jacobi sweep), or dst = F - A_s src when residual
+template <bool RESIDUAL>
+__device__ __forceinline__ void tail_pass(int nr, int nc, int lgc, const TailCoef &c, double shift, const double *src,
+                                          const double *F, const double *W, double *dst) {
+  const int P = nc + 2;
+  for (int idx = threadIdx.x; idx < nr * nc; idx += blockDim.x) {
+    const int i = idx >> lgc, j = idx & (nc - 1);
+    const double av = tail_apply(src, P, i, j, c, shift);
+    const double r = F[idx] - av;
+    dst[(i + 1) * P + (j + 1)] = RESIDUAL ? r : (src[(i + 1) * P + (j + 1)] + W[idx] * r);
   }
-}
-
-// v += P e
-__device__ void tail_prolong_add(const LevelDev &Lf, const double *e, double *v) {
-  const int nrc = Lf.nrows / 2, ncc = Lf.ncols / 2, nc = Lf.ncols;
-  for (int idx = threadIdx.x; idx < Lf.nrows * nc; idx += blockDim.x) {
-    const int i = idx / nc, j = idx - i * nc;
-    const int I = i >> 1, J = j >> 1;
-    auto E_ = [&](int ii, int jj) -> double { return (ii >= 0 && ii < nrc && jj >= 0 && jj < ncc) ? e[ii * ncc + jj] : 0.0; };
-    double pe;
-    if (i & 1) {
-      pe = (j & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
-    } else {
-      const double top = (j & 1) ? E_(I - 1, J) : 0.5 * (E_(I - 1, J - 1) + E_(I - 1, J));
-      const double bot = (j & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
-      pe = 0.5 * (top + bot);
-    }
-    v[idx] += pe;
-  }
-}
-
-template <bool FIVE>
-__device__ void tail_smooth4(const LevelDev &L, double shift, double omega, double *v, const double *f, double *tmp,
-                             bool v_zero) {
-  // 4 sweeps v -> tmp -> v -> tmp -> v
-  tail_sweep<FIVE>(L, shift, omega, v, f, tmp, v_zero);
-  __syncthreads();
-  tail_sweep<FIVE>(L, shift, omega, tmp, f, v, false);
-  __syncthreads();
-  tail_sweep<FIVE>(L, shift, omega, v, f, tmp, false);
-  __syncthreads();
-  tail_sweep<FIVE>(L, shift, omega, tmp, f, v, false);
-  __syncthreads();
 }
 
 }  // namespace
@@ -353,57 +283,146 @@ __global__ void __launch_bounds__(1024) tail_kernel(TailArgs a, const double *__
                                                     double *__restrict__ v_first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *arena = reinterpret_cast<double *>(smem_raw);
-  double *tmp = arena + a.tmpoff;
   const int nl = a.nlev;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // ---- setup: zero everything (halos, zero initial guesses), stage coefficients, F of the first level
+  for (int i = tid; i < a.arena_doubles; i += nt) arena[i] = 0.0;
+  __syncthreads();
+  for (int l = 0; l < nl; ++l) {
+    const LevelDev &L = a.lev[l].dev;
+    double *cb = arena + a.lev[l].coff;
+    const int nr = L.nrows, nc = L.ncols;
+    for (int i = tid; i < nr; i += nt) {
+      cb[i] = L.ka_lo[L.row0 + i]; cb[nr + i] = L.ka_di[L.row0 + i]; cb[2 * nr + i] = L.ka_up[L.row0 + i];
+      cb[3 * nr + i] = L.five ? 0.0 : L.ma_lo[L.row0 + i];
+      cb[4 * nr + i] = L.five ? 1.0 : L.ma_di[L.row0 + i];
+      cb[5 * nr + i] = L.five ? 0.0 : L.ma_up[L.row0 + i];
+    }
+    double *cc = cb + 6 * nr;
+    for (int j = tid; j < nc; j += nt) {
+      cc[j] = L.kb_lo[j]; cc[nc + j] = L.kb_di[j]; cc[2 * nc + j] = L.kb_up[j];
+      cc[3 * nc + j] = L.five ? 0.0 : L.mb_lo[j];
+      cc[4 * nc + j] = L.five ? 1.0 : L.mb_di[j];
+      cc[5 * nc + j] = L.five ? 0.0 : L.mb_up[j];
+    }
+  }
   {
     const int n0 = a.lev[0].dev.nrows * a.lev[0].dev.ncols;
     double *f0 = arena + a.lev[0].foff;
-    for (int i = threadIdx.x; i < n0; i += blockDim.x) f0[i] = f_first[i];
+    for (int i = tid; i < n0; i += nt) f0[i] = f_first[i];
   }
   __syncthreads();
-  // down
-  for (int l = 0; l < nl - 1; ++l) {
+  for (int l = 0; l < nl - 1; ++l) {  // W = omega / diag, once
     const LevelDev &L = a.lev[l].dev;
-    double *v = arena + a.lev[l].voff, *f = arena + a.lev[l].foff;
-    if (L.five) tail_smooth4<true>(L, a.shift, a.omega, v, f, tmp, true);
-    else tail_smooth4<false>(L, a.shift, a.omega, v, f, tmp, true);
-    if (L.five) tail_residual<true>(L, a.shift, v, f, tmp);
-    else tail_residual<false>(L, a.shift, v, f, tmp);
-    __syncthreads();
-    tail_restrict(L, tmp, arena + a.lev[l + 1].foff);
-    __syncthreads();
-  }
-  // coarsest: v = inv f (one warp per row, same summation order as gemv_kernel in coarse.cu)
-  {
-    const LevelDev &L = a.lev[nl - 1].dev;
-    const int n = L.nrows * L.ncols;
-    const double *f = arena + a.lev[nl - 1].foff;
-    double *v = arena + a.lev[nl - 1].voff;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int r = warp; r < n; r += nw) {
-      const double *row = a.inv + (size_t)r * n;
-      double acc = 0.0;
-      for (int c = lane; c < n; c += 32) acc += row[c] * f[c];
-      acc = warp_sum(acc);
-      if (lane == 0) v[r] = acc;
+    const int nr = L.nrows, nc = L.ncols, lgc = 31 - __clz(nc);
+    const TailCoef c = tail_coef(arena + a.lev[l].coff, nr, nc);
+    double *W = arena + a.lev[l].woff;
+    for (int idx = tid; idx < nr * nc; idx += nt) {
+      const int i = idx >> lgc, j = idx & (nc - 1);
+      W[idx] = a.omega / ((c.ma_di[i] * c.kb_di[j] + c.ka_di[i] * c.mb_di[j]) - a.shift);
     }
   }
   __syncthreads();
-  // up
+
+  // ---- down: 4 sweeps (V -> T -> V -> T -> V), residual into T, full weighting into the next F --------
+  for (int l = 0; l < nl - 1; ++l) {
+    const LevelDev &L = a.lev[l].dev;
+    const int nr = L.nrows, nc = L.ncols, lgc = 31 - __clz(nc), P = nc + 2;
+    const TailCoef c = tail_coef(arena + a.lev[l].coff, nr, nc);
+    double *V = arena + a.lev[l].voff, *T = arena + a.lev[l].toff;
+    const double *F = arena + a.lev[l].foff, *W = arena + a.lev[l].woff;
+    for (int s = 0; s < 2; ++s) {
+      tail_pass<false>(nr, nc, lgc, c, a.shift, V, F, W, T);
+      __syncthreads();
+      tail_pass<false>(nr, nc, lgc, c, a.shift, T, F, W, V);
+      __syncthreads();
+    }
+    tail_pass<true>(nr, nc, lgc, c, a.shift, V, F, W, T);
+    __syncthreads();
+    const int nrc = nr >> 1, ncc = nc >> 1, lgcc = lgc - 1;
+    double *Fc = arena + a.lev[l + 1].foff;
+    for (int idx = tid; idx < nrc * ncc; idx += nt) {
+      const int I = idx >> lgcc, J = idx & (ncc - 1);
+      const double *p = T + (2 * I + 1) * P + (2 * J + 1);  // haloed: fine (2I, 2J); row/col n are the zero halo
+      const double a0 = 0.25 * p[0] + 0.5 * p[1] + 0.25 * p[2];
+      const double a1 = 0.25 * p[P] + 0.5 * p[P + 1] + 0.25 * p[P + 2];
+      const double a2 = 0.25 * p[2 * P] + 0.5 * p[2 * P + 1] + 0.25 * p[2 * P + 2];
+      Fc[idx] = 0.25 * a0 + 0.5 * a1 + 0.25 * a2;
+    }
+    __syncthreads();
+  }
+  // ---- coarsest: v = inv f (one warp per row, same summation order as gemv_kernel in coarse.cu) --------
+  {
+    const LevelDev &L = a.lev[nl - 1].dev;
+    const int n = L.nrows * L.ncols, nc = L.ncols, P = nc + 2, lgc = 31 - __clz(nc);
+    const double *F = arena + a.lev[nl - 1].foff;
+    double *V = arena + a.lev[nl - 1].voff;
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int r = warp; r < n; r += nw) {
+      const double *row = a.inv + (size_t)r * n;
+      double acc = 0.0;
+      for (int cidx = lane; cidx < n; cidx += 32) acc += row[cidx] * F[cidx];
+      acc = warp_sum(acc);
+      if (lane == 0) V[((r >> lgc) + 1) * P + (r & (nc - 1)) + 1] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- up: v += P e, then 4 sweeps ------------------------------------------------------------------------
   for (int l = nl - 2; l >= 0; --l) {
     const LevelDev &L = a.lev[l].dev;
-    double *v = arena + a.lev[l].voff, *f = arena + a.lev[l].foff;
-    tail_prolong_add(L, arena + a.lev[l + 1].voff, v);
+    const int nr = L.nrows, nc = L.ncols, lgc = 31 - __clz(nc), P = nc + 2, Pc = (nc >> 1) + 2;
+    const TailCoef c = tail_coef(arena + a.lev[l].coff, nr, nc);
+    double *V = arena + a.lev[l].voff, *T = arena + a.lev[l].toff;
+    const double *F = arena + a.lev[l].foff, *W = arena + a.lev[l].woff;
+    const double *E = arena + a.lev[l + 1].voff;
+    for (int idx = tid; idx < nr * nc; idx += nt) {
+      const int i = idx >> lgc, j = idx & (nc - 1);
+      const int I = i >> 1, J = j >> 1;
+      const double *e = E + (I + 1) * Pc + (J + 1);  // e[-1], e[-Pc]: coarse neighbours (zero halo at the edges)
+      double pe;
+      if (i & 1) {
+        pe = (j & 1) ? e[0] : 0.5 * (e[-1] + e[0]);
+      } else {
+        const double top = (j & 1) ? e[-Pc] : 0.5 * (e[-Pc - 1] + e[-Pc]);
+        const double bot = (j & 1) ? e[0] : 0.5 * (e[-1] + e[0]);
+        pe = 0.5 * (top + bot);
+      }
+      V[(i + 1) * P + (j + 1)] += pe;
+    }
     __syncthreads();
-    if (L.five) tail_smooth4<true>(L, a.shift, a.omega, v, f, tmp, false);
-    else tail_smooth4<false>(L, a.shift, a.omega, v, f, tmp, false);
+    for (int s = 0; s < 2; ++s) {
+      tail_pass<false>(nr, nc, lgc, c, a.shift, V, F, W, T);
+      __syncthreads();
+      tail_pass<false>(nr, nc, lgc, c, a.shift, T, F, W, V);
+      __syncthreads();
+    }
   }
   {
-    const int n0 = a.lev[0].dev.nrows * a.lev[0].dev.ncols;
-    const double *v0 = arena + a.lev[0].voff;
-    for (int i = threadIdx.x; i < n0; i += blockDim.x) v_first[i] = v0[i];
+    const LevelDev &L = a.lev[0].dev;
+    const int nc = L.ncols, lgc = 31 - __clz(nc), P = nc + 2;
+    const double *V = arena + a.lev[0].voff;
+    for (int idx = tid; idx < L.nrows * nc; idx += nt) v_first[idx] = V[((idx >> lgc) + 1) * P + (idx & (nc - 1)) + 1];
   }
 }
+
+static size_t tail_layout(const LevelDev *levels, int nlev, TailArgs *a) {
+  int off = 0;
+  auto take = [&](int n) { const int o = off; off += (n + 1) & ~1; return o; };
+  for (int l = 0; l < nlev; ++l) {
+    const int nr = levels[l].nrows, nc = levels[l].ncols;
+    const int hal = (nr + 2) * (nc + 2);
+    const int vo = take(hal), to = (l + 1 < nlev) ? take(hal) : 0, fo = take(nr * nc);
+    const int wo = (l + 1 < nlev) ? take(nr * nc) : 0, co = take(6 * nr + 6 * nc);
+    if (a) {
+      a->lev[l].dev = levels[l];
+      a->lev[l].voff = vo; a->lev[l].toff = to; a->lev[l].foff = fo; a->lev[l].woff = wo; a->lev[l].coff = co;
+    }
+  }
+  if (a) a->arena_doubles = off;
+  return sizeof(double) * (size_t)off;
+}
+
+size_t tail_smem_bytes(const LevelDev *levels, int nlev) { return tail_layout(levels, nlev, nullptr); }
 
 cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, double shift, double omega,
                         const double *f_first, double *v_first, cudaStream_t s) {
@@ -413,21 +432,11 @@ cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, dou
   a.inv = inv;
   a.shift = shift;
   a.omega = omega;
-  int off = 0, maxn = 0;
-  for (int l = 0; l < nlev; ++l) {
-    const int n = levels[l].nrows * levels[l].ncols;
-    a.lev[l].dev = levels[l];
-    a.lev[l].voff = off; off += (n + 1) & ~1;
-    a.lev[l].foff = off; off += (n + 1) & ~1;
-    if (n > maxn) maxn = n;
-  }
-  a.tmpoff = off;
-  off += (maxn + 1) & ~1;
-  const size_t smem = sizeof(double) * (size_t)off;
-  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  const size_t smem = tail_layout(levels, nlev, &a);
+  if (smem > kTailMaxSmem) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailMaxSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

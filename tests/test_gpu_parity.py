@@ -211,7 +211,7 @@ def test_all_vcycle_paths_agree(T, prod):
                          s.vcycle(np.zeros(64 * 64), f[:4096].copy(), (-1. / np.pi ** 2) * sm.laplacian(64, "2d"), sm,
                                   shift=1.7, lowest_level=4, dimension="2d")))
     finally:
-        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=64).items():
+        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=32).items():
             lib.mgcmt_set_option(k.encode(), v)
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
