@@ -89,6 +89,9 @@ int mgcmt_hier_level_coefs(const mgcmt_hier_t *h, int level, double *h_rowcoef6,
 /* ---- single-level operators (all on `stream`, device pointers, level sizes) --------------------- */
 /* y = (A_l - shift I) x            -- the `shifted_matrix * v` of MGCMTSolver.py:315 */
 int mgcmt_apply(mgcmt_hier_t *h, int level, double shift, const double *d_x, double *d_y, void *stream);
+/* y = M_l x with M_l = Ma_l (x) Mb_l, the Galerkin-coarsened mass matrix R..R I P..P of the RQ multigrid
+ * (`M_coarse = R*M*P`, MGCMTSolver.py:79,111); the identity on the finest level */
+int mgcmt_apply_mass(mgcmt_hier_t *h, int level, const double *d_x, double *d_y, void *stream);
 /* r = f - (A_l - shift I) v        -- MGCMTSolver.py:315 (inner bracket) */
 int mgcmt_residual(mgcmt_hier_t *h, int level, double shift, const double *d_v, const double *d_f,
                    double *d_r, void *stream);
@@ -148,6 +151,9 @@ int mgcmt_normalize(long long n, double *d_x, void *stream);
 /* y = alpha*x + y with alpha read from device memory, scaled by `sign` */
 int mgcmt_axpy_dev(long long n, const double *d_alpha, double sign, const double *d_x, double *d_y,
                    void *stream);
+/* out = a*x + b*y with host scalars (the vector updates of rqmin, MGCMTSolver.py:34-36,51,54) */
+int mgcmt_axpby(long long n, double a, const double *d_x, double b, const double *d_y, double *d_out,
+                void *stream);
 /* Gram-Schmidt of k vectors of length n stored one after another (vector-major: d_V + c*n is
  * column c).  modified != 0: MGS exactly as MGCMTProcessor.gramschmidt (MGCMTProcessor.py:44-50);
  * modified == 0: classical GS followed by normalisation (MGCMTProcessor.py:35-42). In place. */

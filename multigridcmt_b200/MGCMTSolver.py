@@ -254,6 +254,159 @@ class MGCMTSolver:
         return np.ascontiguousarray(V.cpu().numpy().T)
 
     # ------------------------------------------------------------------------------------------
+    # Rayleigh-quotient minimisation family (MGCMTSolver.py:17-122).  1-D only, as in the reference (D6).
+    # Vector work (operator / mass applies, dots, updates, transfers) runs on the device through the C ABI;
+    # the 2x2 generalised eigenproblem of each CG step is solved on the host with the same
+    # scipy.linalg.eig call the reference makes (MGCMTSolver.py:48).
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _is_identity(M, n):
+        import scipy.sparse as sp
+        if M is None:
+            return True
+        if sp.issparse(M):
+            return M.shape == (n, n) and (M - sp.eye(n)).count_nonzero() == 0
+        M = np.asarray(M)
+        return M.shape == (n, n) and np.array_equal(M, np.eye(n))
+
+    def _rq_hierarchy(self, A, M, n, lowest):
+        if not self._is_identity(M, n):
+            raise NotImplementedError("the device RQ path needs M = identity on the finest level (as in RQMin.py:17); "
+                                      "coarse mass matrices R*M*P are built from it")
+        op = recognise(A, "1d")
+        return get_hierarchy(op, lowest)
+
+    def _rqmin_level(self, h, level, x, nu):
+        """rqmin (MGCMTSolver.py:17-57) for the level operators A_l, M_l of hierarchy h; x: device vector."""
+        torch = _lib.require_cuda()
+        from scipy.linalg import eig
+        lib = _lib.load()
+        n = x.numel()
+        stream = _stream_ptr(torch)
+        scal = torch.zeros(16, dtype=torch.float64, device="cuda")
+
+        def A_(v):
+            return h.apply(level, 0.0, v, torch.empty_like(v))
+
+        def M_(v):
+            return h.apply_mass(level, v, torch.empty_like(v))
+
+        def dots(pairs):
+            for i, (a, b) in enumerate(pairs):
+                _lib.check(lib.mgcmt_dot(n, _ptr(a), _ptr(b), _ptr(scal[i:i + 1]), stream))
+            return scal[:len(pairs)].cpu().tolist()
+
+        def axpby(a, u, b, v):
+            out = torch.empty_like(u)
+            _lib.check(lib.mgcmt_axpby(n, float(a), _ptr(u), float(b), _ptr(v), _ptr(out), stream))
+            return out
+
+        Ax, Mx = A_(x), M_(x)
+        xax, xmx = dots([(x, Ax), (x, Mx)])
+        rho = xax / xmx
+        g = axpby(2.0, Ax, -2.0 * rho, Mx)
+        gold = x
+        p = x
+        for it in range(nu):
+            if it == 0:
+                p = axpby(-1.0, g, 0.0, g)
+            else:
+                gmg, omo = dots([(g, M_(g)), (gold, M_(gold))])
+                p = axpby(-1.0, g, gmg / omo, p)
+            Ap, Mp = A_(p), M_(p)
+            d = dots([(x, Ax), (x, Ap), (p, Ax), (p, Ap), (x, Mx), (x, Mp), (p, Mx), (p, Mp)])
+            R = np.array([[d[0], d[1]], [d[2], d[3]]])
+            RM = np.array([[d[4], d[5]], [d[6], d[7]]])
+            w, vecs = eig(R, b=RM)
+            rx = np.array(vecs[:, np.argmin(w)])
+            delta = rx[1] / rx[0]
+            delta = float(np.real(delta))
+            x = axpby(1.0, x, delta, p)
+            Ax, Mx = A_(x), M_(x)
+            xax, xmx = dots([(x, Ax), (x, Mx)])
+            rho = xax / xmx
+            gold = g
+            g = axpby(2.0, Ax, -2.0 * rho, Mx)
+        return x, rho
+
+    def rqmin(self, A, v0, M=None, nu=4):
+        # MGCMTSolver.py:17-57 (M=None is unusable in the reference, quirk Q9; here it means the identity)
+        shape = np.shape(v0) if not is_device_tensor(v0) else None
+        x = to_device(v0)
+        if is_device_tensor(v0):
+            x = x.clone()
+        n = x.numel()
+        h = self._rq_hierarchy(A, M, n, min(n, 4096))
+        x, rho = self._rqmin_level(h, 0, x, nu)
+        if shape is None:
+            return x, rho
+        return to_host(x).reshape(shape), rho
+
+    def _rqmg_level(self, h, level, k, nu1, nu2, nmin):
+        torch = _lib.require_cuda()
+        n = k.numel()
+        k, rho = self._rqmin_level(h, level, k, nu1)
+        if n > nmin and level + 1 < h.num_levels:
+            kc = torch.empty(h.level_size(level + 1), dtype=torch.float64, device="cuda")
+            h.restrict(level, k, kc)                      # k_coarse = R k: the restricted ITERATE (MGCMTSolver.py:113)
+            c, rho = self._rqmg_level(h, level + 1, kc, nu1, nu2, nmin)
+            h.prolong_correct(level, c, k)                # k = k + P c (:116-118)
+            k, rho = self._rqmin_level(h, level, k, nu2)
+        return k, rho
+
+    def vcycle_rqmg(self, x, A, M, nu1=4, nu2=4, nmin=2):
+        # MGCMTSolver.py:99-122
+        shape = np.shape(x) if not is_device_tensor(x) else None
+        k = to_device(x)
+        if is_device_tensor(x):
+            k = k.clone()
+        n = k.numel()
+        if n < 2 or n & (n - 1):
+            print("New gridsize isn't a power of 2 !")
+            return None
+        low = max(2, int(nmin))
+        while low & (low - 1):
+            low += 1
+        h = self._rq_hierarchy(A, M, n, min(low, n))
+        k, rho = self._rqmg_level(h, 0, k, nu1, nu2, nmin)
+        if shape is None:
+            return k, rho
+        return to_host(k).reshape(shape), rho
+
+    def vcycle_rqmg2(self, x_matrix, A, M, nu1=4, nu2=4, nmin=2, level=0):
+        # MGCMTSolver.py:59-94 (block variant; Gram-Schmidt x4 on the finest level only)
+        torch = _lib.require_cuda()
+        dev_in = is_device_tensor(x_matrix)
+        xm = x_matrix if dev_in else np.asarray(x_matrix, dtype=np.float64)
+        n, nv = xm.shape
+        low = max(2, int(nmin))
+        h = self._rq_hierarchy(A, M, n, min(low, n))
+        K = (xm.t().contiguous().clone() if dev_in
+             else torch.from_numpy(np.ascontiguousarray(xm.T)).cuda())
+        lib = _lib.load()
+
+        def rec(lv, K):
+            nl = K.shape[1]
+            for i in range(nv):
+                xi, _ = self._rqmin_level(h, lv, K[i].clone(), nu1)
+                K[i].copy_(xi)
+            if lv == 0:
+                for _ in range(4):
+                    _lib.check(lib.mgcmt_gramschmidt(nl, nv, _ptr(K), 1, _stream_ptr(torch)))
+            if nl > nmin and lv + 1 < h.num_levels:
+                Kc = torch.empty(nv, h.level_size(lv + 1), dtype=torch.float64, device="cuda")
+                for i in range(nv):
+                    h.restrict(lv, K[i], Kc[i])
+                Cc = rec(lv + 1, Kc)
+                for i in range(nv):
+                    h.prolong_correct(lv, Cc[i], K[i])
+                    xi, _ = self._rqmin_level(h, lv, K[i].clone(), nu2)
+                    K[i].copy_(xi)
+            return K
+        K = rec(0, K)
+        return K.t() if dev_in else np.ascontiguousarray(K.cpu().numpy().T)
+
+    # ------------------------------------------------------------------------------------------
     # Rayleigh quotient helper (the `v^T H v` the drivers compute inline, e.g. 2DPotGS.py:103)
     # ------------------------------------------------------------------------------------------
     def rayleigh_quotient(self, A, v, dimension="1d"):

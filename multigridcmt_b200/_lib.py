@@ -39,6 +39,8 @@ SIGNATURES = {
     "mgcmt_hier_level_shape": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I)]),
     "mgcmt_hier_level_coefs": (_I, [_P, _I, _P, _P]),
     "mgcmt_apply": (_I, [_P, _I, _D, _P, _P, _P]),
+    "mgcmt_apply_mass": (_I, [_P, _I, _P, _P, _P]),
+    "mgcmt_axpby": (_I, [_LL, _D, _P, _D, _P, _P, _P]),
     "mgcmt_residual": (_I, [_P, _I, _D, _P, _P, _P, _P]),
     "mgcmt_smooth": (_I, [_P, _I, _I, _D, _D, _I, _P, _P, _P, _P]),
     "mgcmt_restrict": (_I, [_P, _I, _P, _P, _P]),

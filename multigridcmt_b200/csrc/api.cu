@@ -88,6 +88,7 @@ struct Level {
   LevelDev dev;
   double *coef = nullptr;  // 6*nrows_glob + 6*ncols doubles
   double *v = nullptr, *f = nullptr, *tmp = nullptr;
+  double *zrow = nullptr;  // 3*nrows_glob zeros: the "Ka = 0" factor used by the mass-matrix apply
   size_t n = 0;
 };
 
@@ -407,6 +408,8 @@ int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows
     CUB(cudaMalloc(&L.coef, sizeof(double) * (6 * (size_t)nr + 6 * (size_t)nc)));
     set_coef_ptrs(L);
     CUB(cudaMalloc(&L.tmp, sizeof(double) * L.n));
+    CUB(cudaMalloc(&L.zrow, sizeof(double) * 3 * (size_t)nr));
+    CUB(cudaMemsetAsync(L.zrow, 0, sizeof(double) * 3 * (size_t)nr, s));
     if (l > 0) {
       CUB(cudaMalloc(&L.v, sizeof(double) * L.n));
       CUB(cudaMalloc(&L.f, sizeof(double) * L.n));
@@ -463,6 +466,7 @@ int mgcmt_hier_destroy(mgcmt_hier_t *h) {
     cudaFree(L.v);
     cudaFree(L.f);
     cudaFree(L.tmp);
+    cudaFree(L.zrow);
   }
   for (auto &e : h->invs) cudaFree(e.inv);
   cudaFree(h->status);
@@ -496,6 +500,26 @@ int mgcmt_apply(mgcmt_hier_t *h, int level, double shift, const double *d_x, dou
   if (rc) return rc;
   NEED_ALIGNED(d_x, d_y);
   CU(launch_apply(h->lev[level].dev, shift, d_x, d_y, nullptr, nullptr, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_apply_mass(mgcmt_hier_t *h, int level, const double *d_x, double *d_y, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  NEED_ALIGNED(d_x, d_y);
+  // M_l = Ma (x) Mb is the operator with Kb := Mb and Ka := 0
+  const Level &L = h->lev[level];
+  LevelDev m = L.dev;
+  m.kb_lo = L.dev.mb_lo; m.kb_di = L.dev.mb_di; m.kb_up = L.dev.mb_up;
+  m.ka_lo = L.zrow; m.ka_di = L.zrow + L.dev.nrows_glob; m.ka_up = L.zrow + 2 * (size_t)L.dev.nrows_glob;
+  if (L.dev.nrows_glob > 1 && h->coarsen_rows) m.five = 0;  // 2-D: needs the Ma factor (identity on the finest level)
+  CU(launch_apply(m, 0.0, d_x, d_y, nullptr, nullptr, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_axpby(long long n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream) {
+  if (n < 0 || !d_x || !d_y || !d_out) return fail(MGCMT_ERR_ARG, "bad axpby arguments");
+  CU(launch_axpby(n, a, d_x, b, d_y, d_out, (cudaStream_t)stream));
   return MGCMT_OK;
 }
 

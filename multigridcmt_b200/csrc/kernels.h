@@ -91,6 +91,7 @@ cudaError_t launch_mgs_update(long long n, int m, const double *qi, const double
 cudaError_t launch_scale_by_inv_norm(long long n, double *x, const double *sumsq, cudaStream_t s);
 cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *denom, double sign,
                             const double *x, double *y, cudaStream_t s);
+cudaError_t launch_axpby(long long n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s);
 cudaError_t launch_scale_to(long long n, const double *x, const double *sumsq, double *y, cudaStream_t s);
 
 }  // namespace mgcmt

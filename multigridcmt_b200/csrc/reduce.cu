@@ -262,4 +262,19 @@ cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *deno
   return cudaGetLastError();
 }
 
+// out = a x + b y   (host scalars)
+__global__ void axpby_kernel(long long n, double a, const double *__restrict__ x, double b, const double *__restrict__ y,
+                             double *__restrict__ out) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += step) out[i] = a * x[i] + b * y[i];
+}
+cudaError_t launch_axpby(long long n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s) {
+  long long blk = (n + 255) / 256;
+  if (blk > 148 * 16) blk = 148 * 16;
+  if (blk < 1) blk = 1;
+  axpby_kernel<<<(int)blk, 256, 0, s>>>(n, a, x, b, y, out);
+  count_launch();
+  return cudaGetLastError();
+}
+
 }  // namespace mgcmt

@@ -76,6 +76,11 @@ class Hierarchy:
         _lib.check(_lib.load().mgcmt_apply(self.handle, level, float(shift), _ptr(x), _ptr(y), _stream_ptr(torch)))
         return y
 
+    def apply_mass(self, level, x, y):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_apply_mass(self.handle, level, _ptr(x), _ptr(y), _stream_ptr(torch)))
+        return y
+
     def residual(self, level, shift, v, f, r):
         torch = _lib.require_cuda()
         _lib.check(_lib.load().mgcmt_residual(self.handle, level, float(shift), _ptr(v), _ptr(f), _ptr(r),

@@ -387,6 +387,36 @@ def test_gramschmidt_large_and_deterministic(T, prod, o):
     assert np.max(np.abs(oc - np.eye(k))) < 1e-13
 
 
+def test_rq_family_matches_reference_golden(prod, golden, o):
+    """rqmin / vcycle_rqmg (MGCMTSolver.py:17-122) against the real reference's outputs."""
+    sm, s, _ = prod
+    n = 32
+    H = sp.csr_matrix((-1. / np.pi ** 2) * sm.laplacian(n))
+    M = sp.eye(n, format="csr")
+    x, rho = s.rqmin(H, golden["rq_x0"].copy(), M, nu=4)
+    assert x.shape == (n,)
+    assert rel(x, golden["rq_rqmin_x"]) < 1e-9 and abs(rho - float(golden["rq_rqmin_rho"])) < 1e-10
+    x, rho = s.vcycle_rqmg(golden["rq_x0"].copy(), H, M)
+    assert rel(x, golden["rq_rqmg_x"]) < 1e-8 and abs(rho - float(golden["rq_rqmg_rho"])) < 1e-9
+    # two RQMG cycles from a random start approach the lowest eigenvalue (RQMin.py:28-35 pattern), n = 256
+    n = 256
+    H = sp.csr_matrix((-1. / np.pi ** 2) * sm.laplacian(n))
+    M = sp.eye(n, format="csr")
+    x = np.random.RandomState(0).random_sample(n)
+    ox, orho = x.copy(), None
+    for _ in range(2):
+        x, rho = s.vcycle_rqmg(x, H, M)
+        ox, orho = o[1].vcycle_rqmg(ox, H, M)
+    assert abs(rho - orho) < 1e-8 * abs(orho)
+    assert abs(rho - orc.well_eigenvalue_1d(n, 1)) < 0.1   # RQMG converges slowly from a random start (report p.51)
+    # block variant runs and returns orthonormal-ish columns of the right shape
+    Xb = np.random.RandomState(1).random_sample((64, 2))
+    H64 = sp.csr_matrix((-1. / np.pi ** 2) * sm.laplacian(64))
+    out = s.vcycle_rqmg2(Xb, H64, sp.eye(64, format="csr"))
+    want = o[1].vcycle_rqmg2(Xb.copy(), H64, sp.eye(64, format="csr"))
+    assert out.shape == (64, 2) and rel(out[:, 0], want[:, 0]) < 1e-6
+
+
 def test_rayleigh_quotient(prod):
     sm, s, _ = prod
     N = 128
