@@ -78,6 +78,25 @@ int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows
                       const double *h_row_lo, const double *h_row_di, const double *h_row_up,
                       const double *h_col_lo, const double *h_col_di, const double *h_col_up,
                       int lowest_level, void *stream);
+/* As mgcmt_hier_create, but levels finer than first_work_level get no work vectors (only their operators):
+ * the replicated coarse part of a slab-decomposed solver, driven through mgcmt_vcycle_from. */
+int mgcmt_hier_create2(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows,
+                       const double *h_row_lo, const double *h_row_di, const double *h_row_up,
+                       const double *h_col_lo, const double *h_col_di, const double *h_col_up,
+                       int lowest_level, int first_work_level, void *stream);
+/* Row-slab piece of an nrows_glob x ncols grid for multi-GPU runs: levels 0..nlevels-1
+ * hold the rows [row_begin >> l, (row_begin + nrows_own) >> l) of level l plus `halo` (even, >= 6) rows above
+ * and below, as one dense (own + 2 halo) x ncols array; halo rows outside the global grid stay zero.  The
+ * operator factors are the full global ones.  Valid calls on such a handle: the single-level operators,
+ * mgcmt_fused_leg (streaming implementation; restriction from the last slab level writes into / prolongation
+ * reads from a FULL coarse array, i.e. the replicated coarse grid) and mgcmt_slab_rayleigh.  Keeping the
+ * halo rows current between legs (NCCL send/recv, multigridcmt_b200/slab.py) is the caller's job. */
+int mgcmt_hier_create_slab(mgcmt_hier_t **out, int nrows_glob, int ncols, int row_begin, int nrows_own,
+                           int nlevels, int halo, const double *h_row_lo, const double *h_row_di,
+                           const double *h_row_up, const double *h_col_lo, const double *h_col_di,
+                           const double *h_col_up, void *stream);
+/* the hierarchy's own v / f / scratch vectors of a level (NULL where not allocated) */
+int mgcmt_hier_level_buffers(mgcmt_hier_t *h, int level, double **d_v, double **d_f, double **d_tmp);
 int mgcmt_hier_destroy(mgcmt_hier_t *h);
 int mgcmt_hier_num_levels(const mgcmt_hier_t *h);
 /* grid size of a level (level 0 = finest) */
@@ -122,6 +141,14 @@ int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double 
  * start from w0 = 0, e.g. 2DPotGS.py:94); d_v is then not read. */
 int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega,
                  double *d_v, const double *d_f, int v0_is_zero, void *stream);
+
+/* The V-cycle restricted to levels level..coarsest with a zero initial guess and 4/4 sweeps -- what every
+ * coarse level of MGCMTSolver.vcycle runs (MGCMTSolver.py:316-320).  d_v, d_f: vectors of that level. */
+int mgcmt_vcycle_from(mgcmt_hier_t *h, int level, double shift, int smoother, double omega, double *d_v,
+                      const double *d_f, void *stream);
+/* slab piece: d_out2[0] = x^T A x, d_out2[1] = x^T x summed over the OWNED rows of this rank only (the caller
+ * all-reduces); d_x is the slab array including its halo rows */
+int mgcmt_slab_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream);
 
 /* One fused pass over a 2-D level (what mgcmt_vcycle is made of when the smoother is weighted Jacobi):
  * nu (0..4) Jacobi sweeps fused with the neighbouring grid transfer, out of place (d_vin != d_vout).

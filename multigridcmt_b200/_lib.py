@@ -34,6 +34,11 @@ SIGNATURES = {
     "mgcmt_profile_enable": (_I, [_I]),
     "mgcmt_profile_read": (_I, [C.POINTER(_D), C.POINTER(_LL)]),
     "mgcmt_hier_create": (_I, [C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "mgcmt_hier_create2": (_I, [C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "mgcmt_hier_create_slab": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "mgcmt_hier_level_buffers": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "mgcmt_vcycle_from": (_I, [_P, _I, _D, _I, _D, _P, _P, _P]),
+    "mgcmt_slab_rayleigh": (_I, [_P, _I, _P, _P, _P]),
     "mgcmt_hier_destroy": (_I, [_P]),
     "mgcmt_hier_num_levels": (_I, [_P]),
     "mgcmt_hier_level_shape": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I)]),

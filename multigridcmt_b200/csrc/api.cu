@@ -103,6 +103,9 @@ struct InvEntry {
 struct mgcmt_hier {
   int nlev = 0;
   bool coarsen_rows = true;
+  bool slab = false;   // row-slab piece of a decomposed grid: only single-level operators are valid
+  int halo = 0;        // halo rows above and below the owned rows of every slab level
+  int first_work = 0;  // levels below this one have no work vectors (replicated coarse part of a slab solver)
   std::vector<Level> lev;
   std::vector<InvEntry> invs;
   uint64_t clock = 0;
@@ -358,32 +361,19 @@ int mgcmt_profile_read(double *ms_total, long long *intervals) {
 }
 const char *mgcmt_last_error(void) { return g_err.c_str(); }
 
-int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows, const double *h_row_lo,
-                      const double *h_row_di, const double *h_row_up, const double *h_col_lo,
-                      const double *h_col_di, const double *h_col_up, int lowest_level, void *stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!out) return fail(MGCMT_ERR_ARG, "out is null");
-  *out = nullptr;
-  if (!h_row_lo || !h_row_di || !h_row_up || !h_col_lo || !h_col_di || !h_col_up)
-    return fail(MGCMT_ERR_ARG, "null coefficient array");
-  if (!is_pow2(ncols) || ncols < 2) return fail(MGCMT_ERR_ARG, "ncols must be a power of two >= 2");
-  if (!is_pow2(nrows)) return fail(MGCMT_ERR_ARG, "nrows must be a power of two (1 for 1-D)");
-  if (!coarsen_rows && nrows != 1) return fail(MGCMT_ERR_ARG, "coarsen_rows = 0 needs nrows == 1");
-  if (!is_pow2(lowest_level) || lowest_level < 2 || lowest_level > ncols)
-    return fail(MGCMT_ERR_ARG, "lowest_level must be a power of two in [2, ncols]");
-  int nlev = 1;
-  for (int c = ncols; c > lowest_level; c >>= 1) ++nlev;
-  if (coarsen_rows && (nrows >> (nlev - 1)) < 1)
-    return fail(MGCMT_ERR_ARG, "nrows too small for the requested number of levels");
-  {
-    const long long nc_rows = coarsen_rows ? (nrows >> (nlev - 1)) : nrows;
-    const long long ncoarse = nc_rows * lowest_level;
-    if (ncoarse > 4096) return fail(MGCMT_ERR_ARG, "coarsest level larger than 4096 unknowns is not supported");
-  }
-
+// Shared builder.  Plain hierarchy: row_begin = 0, nrows_own = nrows_glob, halo = 0, nlev from lowest_level.
+// Slab piece: levels 0..nlev-1 hold rows [row_begin >> l, (row_begin + nrows_own) >> l) plus `halo` rows on both
+// sides; coefficient arrays are always the full global ones (O(N)).
+static int build_hier(mgcmt_hier_t **out, int nrows_glob, int ncols, int coarsen_rows, const double *h_row_lo,
+                      const double *h_row_di, const double *h_row_up, const double *h_col_lo, const double *h_col_di,
+                      const double *h_col_up, int nlev, bool slab, int row_begin, int nrows_own, int halo,
+                      int coarse_full_after, int first_work, cudaStream_t s) {
   mgcmt_hier *h = new mgcmt_hier();
   h->nlev = nlev;
   h->coarsen_rows = coarsen_rows != 0;
+  h->slab = slab;
+  h->halo = halo;
+  h->first_work = first_work;
   h->lev.resize(nlev);
   auto bail = [&](int code, const std::string &msg) {
     mgcmt_hier_destroy(h);
@@ -396,23 +386,41 @@ int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows
   } while (0)
 
   CUB(cudaMalloc(&h->status, sizeof(int)));
-  int nr = nrows, nc = ncols;
+  int nr = nrows_glob, nc = ncols;
   for (int l = 0; l < nlev; ++l) {
     Level &L = h->lev[l];
-    L.dev.nrows = nr;
+    const int own = slab ? (nrows_own >> l) : nr;
+    const int begin = slab ? (row_begin >> l) : 0;
+    L.dev.nrows = slab ? own + 2 * halo : nr;
     L.dev.ncols = nc;
-    L.dev.row0 = 0;
+    L.dev.row0 = slab ? begin - halo : 0;
     L.dev.nrows_glob = nr;
     L.dev.five = (l == 0 || !coarsen_rows) ? 1 : 0;
-    L.n = (size_t)nr * nc;
+    L.dev.crow_shift = 0;
+    L.dev.nrows_coarse = 0;
+    if (slab) {
+      if (l + 1 < nlev) {  // coarse level is a slab piece too
+        L.dev.crow_shift = halo / 2;
+        L.dev.nrows_coarse = (own >> 1) + 2 * halo;
+      } else if (coarse_full_after) {  // coarse level is the full (replicated) grid
+        L.dev.crow_shift = (begin - halo) / 2;  // exact: begin and halo are even
+        L.dev.nrows_coarse = nr >> 1;
+      }
+    }
+    L.n = (size_t)L.dev.nrows * nc;
     CUB(cudaMalloc(&L.coef, sizeof(double) * (6 * (size_t)nr + 6 * (size_t)nc)));
     set_coef_ptrs(L);
-    CUB(cudaMalloc(&L.tmp, sizeof(double) * L.n));
     CUB(cudaMalloc(&L.zrow, sizeof(double) * 3 * (size_t)nr));
     CUB(cudaMemsetAsync(L.zrow, 0, sizeof(double) * 3 * (size_t)nr, s));
-    if (l > 0) {
-      CUB(cudaMalloc(&L.v, sizeof(double) * L.n));
-      CUB(cudaMalloc(&L.f, sizeof(double) * L.n));
+    if (l >= first_work) {
+      CUB(cudaMalloc(&L.tmp, sizeof(double) * L.n));
+      CUB(cudaMemsetAsync(L.tmp, 0, sizeof(double) * L.n, s));
+      if (l > 0 && !slab) {  // slab pieces: the caller owns the level vectors (multigridcmt_b200/slab.py)
+        CUB(cudaMalloc(&L.v, sizeof(double) * L.n));
+        CUB(cudaMalloc(&L.f, sizeof(double) * L.n));
+        CUB(cudaMemsetAsync(L.v, 0, sizeof(double) * L.n, s));
+        CUB(cudaMemsetAsync(L.f, 0, sizeof(double) * L.n, s));
+      }
     }
     if (l == 0) {
       std::vector<double> host(6 * (size_t)nr + 6 * (size_t)nc, 0.0);
@@ -459,6 +467,62 @@ int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows
   return MGCMT_OK;
 }
 
+static int check_create_args(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows, const double *a,
+                             const double *b, const double *c, const double *d, const double *e, const double *f) {
+  if (!out) return fail(MGCMT_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!a || !b || !c || !d || !e || !f) return fail(MGCMT_ERR_ARG, "null coefficient array");
+  if (!is_pow2(ncols) || ncols < 2) return fail(MGCMT_ERR_ARG, "ncols must be a power of two >= 2");
+  if (!is_pow2(nrows)) return fail(MGCMT_ERR_ARG, "nrows must be a power of two (1 for 1-D)");
+  if (!coarsen_rows && nrows != 1) return fail(MGCMT_ERR_ARG, "coarsen_rows = 0 needs nrows == 1");
+  return MGCMT_OK;
+}
+
+int mgcmt_hier_create2(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows, const double *h_row_lo,
+                       const double *h_row_di, const double *h_row_up, const double *h_col_lo,
+                       const double *h_col_di, const double *h_col_up, int lowest_level, int first_work_level,
+                       void *stream) {
+  int rc = check_create_args(out, nrows, ncols, coarsen_rows, h_row_lo, h_row_di, h_row_up, h_col_lo, h_col_di, h_col_up);
+  if (rc) return rc;
+  if (!is_pow2(lowest_level) || lowest_level < 2 || lowest_level > ncols)
+    return fail(MGCMT_ERR_ARG, "lowest_level must be a power of two in [2, ncols]");
+  int nlev = 1;
+  for (int c = ncols; c > lowest_level; c >>= 1) ++nlev;
+  if (coarsen_rows && (nrows >> (nlev - 1)) < 1)
+    return fail(MGCMT_ERR_ARG, "nrows too small for the requested number of levels");
+  if (first_work_level < 0 || first_work_level >= nlev) return fail(MGCMT_ERR_ARG, "bad first_work_level");
+  {
+    const long long nc_rows = coarsen_rows ? (nrows >> (nlev - 1)) : nrows;
+    const long long ncoarse = nc_rows * lowest_level;
+    if (ncoarse > 4096) return fail(MGCMT_ERR_ARG, "coarsest level larger than 4096 unknowns is not supported");
+  }
+  return build_hier(out, nrows, ncols, coarsen_rows, h_row_lo, h_row_di, h_row_up, h_col_lo, h_col_di, h_col_up, nlev,
+                    false, 0, nrows, 0, 0, first_work_level, (cudaStream_t)stream);
+}
+
+int mgcmt_hier_create(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_rows, const double *h_row_lo,
+                      const double *h_row_di, const double *h_row_up, const double *h_col_lo,
+                      const double *h_col_di, const double *h_col_up, int lowest_level, void *stream) {
+  return mgcmt_hier_create2(out, nrows, ncols, coarsen_rows, h_row_lo, h_row_di, h_row_up, h_col_lo, h_col_di,
+                            h_col_up, lowest_level, 0, stream);
+}
+
+int mgcmt_hier_create_slab(mgcmt_hier_t **out, int nrows_glob, int ncols, int row_begin, int nrows_own, int nlevels,
+                           int halo, const double *h_row_lo, const double *h_row_di, const double *h_row_up,
+                           const double *h_col_lo, const double *h_col_di, const double *h_col_up, void *stream) {
+  int rc = check_create_args(out, nrows_glob, ncols, 1, h_row_lo, h_row_di, h_row_up, h_col_lo, h_col_di, h_col_up);
+  if (rc) return rc;
+  if (nlevels < 1 || nlevels > 16) return fail(MGCMT_ERR_ARG, "bad number of slab levels");
+  if (halo < 6 || (halo & 1)) return fail(MGCMT_ERR_ARG, "halo must be even and >= 6 (NU + 2 rows for NU = 4)");
+  const int align = 1 << nlevels;  // slab cuts must stay on even rows on every distributed level
+  if (row_begin < 0 || nrows_own <= 0 || row_begin + nrows_own > nrows_glob || (row_begin % align) || (nrows_own % align))
+    return fail(MGCMT_ERR_ARG, "slab rows must be multiples of 2^nlevels inside the grid");
+  if ((nrows_own >> (nlevels - 1)) < halo) return fail(MGCMT_ERR_ARG, "coarsest slab level owns fewer rows than the halo");
+  if ((ncols >> (nlevels - 1)) < 64) return fail(MGCMT_ERR_ARG, "slab levels must be at least 64 columns wide");
+  return build_hier(out, nrows_glob, ncols, 1, h_row_lo, h_row_di, h_row_up, h_col_lo, h_col_di, h_col_up, nlevels, true,
+                    row_begin, nrows_own, halo, 1, 0, (cudaStream_t)stream);
+}
+
 int mgcmt_hier_destroy(mgcmt_hier_t *h) {
   if (!h) return MGCMT_OK;
   for (auto &L : h->lev) {
@@ -475,6 +539,15 @@ int mgcmt_hier_destroy(mgcmt_hier_t *h) {
 }
 
 int mgcmt_hier_num_levels(const mgcmt_hier_t *h) { return h ? h->nlev : 0; }
+
+int mgcmt_hier_level_buffers(mgcmt_hier_t *h, int level, double **d_v, double **d_f, double **d_tmp) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (d_v) *d_v = h->lev[level].v;
+  if (d_f) *d_f = h->lev[level].f;
+  if (d_tmp) *d_tmp = h->lev[level].tmp;
+  return MGCMT_OK;
+}
 
 int mgcmt_hier_level_shape(const mgcmt_hier_t *h, int level, int *nrows, int *ncols) {
   int rc = check_level(h, level);
@@ -538,6 +611,8 @@ int mgcmt_smooth(mgcmt_hier_t *h, int level, int smoother, double shift, double 
   if (rc) return rc;
   NEED_ALIGNED(d_v, d_f);
   if (d_tmp && !al16(d_tmp)) return fail(MGCMT_ERR_ARG, "d_tmp must be 16-byte aligned");
+  if (!d_tmp && !h->lev[level].tmp) return fail(MGCMT_ERR_STATE, "level has no scratch vector in this hierarchy");
+  if (h->slab) return fail(MGCMT_ERR_STATE, "slab pieces are driven leg by leg (mgcmt_fused_leg)");
   return smooth_impl(h, level, smoother, shift, omega, nu, d_v, d_f, d_tmp, (cudaStream_t)stream);
 }
 
@@ -607,7 +682,8 @@ int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, 
                     const double *d_f, double *d_vout, const double *d_ecoarse, double *d_rcoarse, void *stream) {
   int rc = check_level(h, level);
   if (rc) return rc;
-  if (level + 1 >= h->nlev && mode != FUSED_SMOOTH) return fail(MGCMT_ERR_ARG, "no coarser level");
+  if (level + 1 >= h->nlev && mode != FUSED_SMOOTH && !h->slab) return fail(MGCMT_ERR_ARG, "no coarser level");
+  if (h->slab && (mode & 16)) return fail(MGCMT_ERR_ARG, "slab levels use the streaming legs");
   if (!h->coarsen_rows || h->lev[level].dev.nrows < 2) return fail(MGCMT_ERR_ARG, "fused legs are 2-D only");
   const bool force_tile = (mode & 16) != 0;  // bit 4: use the shared-memory tile implementation
   mode &= 15;
@@ -632,7 +708,43 @@ int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, 
   if (!d_v || !d_f || d_v == d_f) return fail(MGCMT_ERR_ARG, "need distinct non-null v and f");
   NEED_ALIGNED(d_v, d_f);
   if (nu1 < 0 || nu2 < 0) return fail(MGCMT_ERR_ARG, "negative sweep count");
+  if (h->slab || h->first_work > 0) return fail(MGCMT_ERR_STATE, "this hierarchy has no full finest level (slab piece / coarse part)");
   return vcycle_level(h, 0, shift, nu1, nu2, smoother, omega, d_v, d_f, v0_is_zero != 0, (cudaStream_t)stream);
+}
+
+int mgcmt_vcycle_from(mgcmt_hier_t *h, int level, double shift, int smoother, double omega, double *d_v,
+                      const double *d_f, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (h->slab || level < h->first_work) return fail(MGCMT_ERR_STATE, "level has no work vectors in this hierarchy");
+  if (!d_v || !d_f || d_v == d_f) return fail(MGCMT_ERR_ARG, "need distinct non-null v and f");
+  NEED_ALIGNED(d_v, d_f);
+  // the V-cycle restricted to levels level..coarsest, zero initial guess, 4/4 sweeps: what MGCMTSolver.vcycle
+  // does at every coarse level (MGCMTSolver.py:316-320)
+  return vcycle_level(h, level, shift, 4, 4, smoother, omega, d_v, d_f, true, (cudaStream_t)stream);
+}
+
+int mgcmt_slab_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (!h->slab) return fail(MGCMT_ERR_STATE, "not a slab hierarchy");
+  if (!d_out2) return fail(MGCMT_ERR_ARG, "null output");
+  NEED_ALIGNED(d_x);
+  Level &L = h->lev[level];
+  cudaStream_t s = (cudaStream_t)stream;
+  // view of the owned rows with the neighbouring halo rows as Dirichlet / halo inputs
+  LevelDev own = L.dev;
+  const int H = h->halo, nown = L.dev.nrows - 2 * H, begin = L.dev.row0 + H;
+  own.nrows = nown;
+  own.row0 = begin;
+  const double *x0 = d_x + (size_t)H * L.dev.ncols;
+  const double *top = begin > 0 ? d_x + (size_t)(H - 1) * L.dev.ncols : nullptr;
+  const double *bot = (begin + nown < L.dev.nrows_glob) ? d_x + (size_t)(H + nown) * L.dev.ncols : nullptr;
+  const int nb = march_grid_blocks(own);
+  if ((size_t)2 * nb > L.n) return fail(MGCMT_ERR_STATE, "scratch too small");
+  CU(launch_rayleigh_partials(own, x0, L.tmp, top, bot, s));
+  CU(launch_finish(2, nb, L.tmp, d_out2, s));
+  return MGCMT_OK;
 }
 
 int mgcmt_dot(long long n, const double *d_x, const double *d_y, double *d_out, void *stream) {
@@ -654,6 +766,7 @@ int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2
   if (rc) return rc;
   Level &L = h->lev[level];
   cudaStream_t s = (cudaStream_t)stream;
+  if (!L.tmp || h->slab) return fail(MGCMT_ERR_STATE, "level has no scratch vector in this hierarchy");
   // one pass: the operator-apply kernel keeps x^T(Ax) and x^T x partial sums per CTA (L.tmp as scratch),
   // then one ordered finish
   const int nb = march_grid_blocks(L.dev);

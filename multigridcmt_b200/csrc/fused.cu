@@ -102,17 +102,21 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   const int t_begin = (t_first - (PROLONG ? 2 : 0)) & ~1;
   const int tab0 = t_begin - NSTAGE - 1;                // first row held in rowtab
   const int ntab = t_last + 3 - tab0;                   // ... up to row t_last + 2
-  const int nrc = L.nrows / 2, ncc = L.ncols / 2;
+  const int nrc = L.nrows_coarse ? L.nrows_coarse : L.nrows / 2, ncc = L.ncols / 2;
+  const int cs = L.crow_shift;
 
-  // reference row for the cached omega/diag: the middle of the chunk
-  const int gref = L.row0 + min(max((r0 + r1) / 2, 0), L.nrows - 1);
+  // reference row for the cached omega/diag: the middle of the chunk (global row index)
+  const int gref = min(max(L.row0 + (r0 + r1) / 2, 0), L.nrows_glob - 1);
   const double kad_ref = L.ka_di[gref];
   const double mad_ref = FIVE ? 1.0 : L.ma_di[gref];
 
   for (int i = tid; i < ntab; i += kWarps * 32) {
     const int row = tab0 + i;
-    const int g = L.row0 + min(max(row, 0), L.nrows - 1);
-    const bool rin = (row >= 0 && row < L.nrows);
+    // global row: a slab holds rows row0 .. row0 + nrows - 1 of an nrows_glob-row grid (row0 = 0, nrows_glob =
+    // nrows when not decomposed); only rows outside the GLOBAL grid are Dirichlet rows
+    const int gg = L.row0 + row;
+    const int g = min(max(gg, 0), L.nrows_glob - 1);
+    const bool rin = (gg >= 0 && gg < L.nrows_glob);
     RowCoef rc;
     // Rows outside the grid get an all-zero operator row: with zero-filled inputs every stage then
     // reproduces the Dirichlet zeros there by itself (x + w (0 - 0) = 0), so the hot loop needs no masks.
@@ -123,10 +127,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     // diagonal different from the reference row's, i.e. the step needs the division path
     double slow = 0.0;
     for (int d = 1; d <= NSTAGE; ++d) {
-      const int r2 = row - d;
-      if (r2 < 0 || r2 >= L.nrows) continue;
-      const double mad2 = FIVE ? 1.0 : L.ma_di[L.row0 + r2];
-      if (L.ka_di[L.row0 + r2] != kad_ref || mad2 != mad_ref) slow = 1.0;
+      const int g2 = gg - d;
+      if (g2 < 0 || g2 >= L.nrows_glob) continue;
+      const double mad2 = FIVE ? 1.0 : L.ma_di[g2];
+      if (L.ka_di[g2] != kad_ref || mad2 != mad_ref) slow = 1.0;
     }
     rc.slow = slow;
     rc.pad = 0.0;
@@ -147,7 +151,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
 #pragma unroll
   for (int q = 0; q < C; ++q) {
     const int j = c0 + q;
-    rlim[q] = (j >= 0 && j < L.ncols) ? (unsigned)L.nrows : 0u;
+    rlim[q] = (j >= 0 && j < L.ncols) ? (unsigned)L.nrows_glob : 0u;
     colout[q] = (j >= u0 && j < u1);
     const int jc = min(max(j, 0), L.ncols - 1);
     const bool cin = (j >= 0 && j < L.ncols);
@@ -174,7 +178,8 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
 
   // ---- asynchronous row fetch -------------------------------------------------------------------
   auto issue = [&](int t, int fslot) {
-    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last;
+    // rows outside the slab array or outside the global grid are zero-filled
+    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last && (unsigned)(t + L.row0) < (unsigned)L.nrows_glob;
     if (!ZEROV) {
       double2 *dst = my_v + (t & (kVRing - 1)) * (C / 2) * NT;
 #pragma unroll
@@ -193,8 +198,9 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     }
     if (PROLONG && (t & 1) == 0) {
       // coarse row I = t/2 is first needed by fine row t (even); coarse columns c0/2 .. c0/2+CE-1
-      const int I = t >> 1;
-      const bool rowc = (t >= 0) && I < nrc && t <= t_last;
+      const int I = (t >> 1) + cs;
+      const int Gc = ((t + L.row0) >> 1);  // global coarse row
+      const bool rowc = I >= 0 && I < nrc && t <= t_last && Gc >= 0 && Gc < (L.nrows_glob >> 1);
       double *dst = my_e + (I & (kERing - 1)) * ESLOT;
 #pragma unroll
       for (int g = 0; g < CE; ++g) {
@@ -244,7 +250,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
         // fine col c0+2g+1 = E[J], J = c0/2 + g.  Lane 0 has no left neighbour: its first column is the
         // outermost halo column of the strip; the up leg has no residual stage, so HALO = NU + 2 leaves
         // two columns of slack and that error never reaches a useful column.
-        const double *src = my_e + ((t >> 1) & (kERing - 1)) * ESLOT;
+        const double *src = my_e + (((t >> 1) + cs) & (kERing - 1)) * ESLOT;
         double e[CE];
 #pragma unroll
         for (int g = 0; g < CE; ++g) e[g] = src[g * NT];
@@ -266,7 +272,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     }
     if (PROLONG) {  // the interpolated correction is the only input that is not already zero outside the grid
 #pragma unroll
-      for (int q = 0; q < C; ++q) x[q] = ((unsigned)t < rlim[q]) ? x[q] : 0.0;
+      for (int q = 0; q < C; ++q) x[q] = ((unsigned)(t + L.row0) < rlim[q]) ? x[q] : 0.0;
     }
 
     // refill the ring slot that row t just vacated (f slots are vacated NU+2 rows later; the f ring is
@@ -357,8 +363,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
           crr[g] = 0.25 * x[2 * g] + 0.5 * x[2 * g + 1] + 0.25 * r2;
         }
         if (!RHO_ODD) {
-          const int I = (rho >> 1) - 1;  // coarse row completed by this fine row (as its row 2I+2)
-          const bool rowok = (I >= (r0 >> 1) && I < (r1 >> 1));
+          const int I = (rho >> 1) - 1 + cs;  // coarse row completed by this fine row (as its row 2I+2)
+          const int G = ((rho + L.row0) >> 1) - 1;  // its global coarse row: rows outside the coarse grid are never written
+          const bool rowok = (I >= (r0 >> 1) + cs && I < (r1 >> 1) + cs && I >= 0 && I < nrc && G >= 0 &&
+                              G < (L.nrows_glob >> 1));
 #pragma unroll
           for (int g = 0; g < CE; ++g) {
             if (rowok && colout[2 * g]) r_coarse[(size_t)I * ncc + (c0 >> 1) + g] = racc[g] + 0.25 * crr[g];

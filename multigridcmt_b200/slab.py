@@ -1,0 +1,264 @@
+"""Row-slab decomposition of the 2-D V-cycle across GPUs.
+
+One process per GPU.  Rank r owns the rows [r N/G, (r+1) N/G) of the finest grid and the matching rows of
+every *distributed* level; each slab array carries HALO = 6 rows above and below its owned rows.  A V(4,4)
+leg is ONE fused kernel per level (csrc/fused.cu: 4 sweeps + transfer), whose dependency cone is exactly
+those 6 rows -- so halos are exchanged once per leg, not once per sweep:
+
+    down, level l:   leg(v_l, f_l) -> tmp_l, f_{l+1}(owned rows);   exchange halos of f_{l+1}
+    coarse part:     levels narrower than `gather_cols` are REPLICATED: the restricted residual of the last slab
+                     level is written straight into a full-size array, all-gathered (NCCL over NVLink), and every
+                     rank runs the same small V-cycle (mgcmt_vcycle_from) -- no scatter back is needed
+    up, level l:     exchange halos of tmp_l and of the coarse correction;   leg(tmp_l + P e, f_l) -> v_l
+
+Slab cuts sit on multiples of 2^(number of slab levels), so coarse row j <-> fine rows 2j, 2j+1, 2j+2 stays aligned on
+every level (the reference's coarse point sits on the odd fine point, MGCMTStencilMaker.py:39-42).
+
+The communicator is abstract: `TorchDistComm` uses torch.distributed (NCCL on GPUs, gloo in the CPU tests of the
+exchange plumbing); `LocalComm` keeps all ranks in one process and copies between their arrays, which lets a single GPU
+run -- and check bit-for-bit against the undecomposed V-cycle -- the exact kernels and halo logic of the multi-GPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .operators import SeparableOperator
+
+HALO = 6
+MODE_DOWN, MODE_DOWN_ZERO, MODE_UP = 1, 2, 3
+
+
+def plan_levels(n, world, gather_cols=2048, min_own_rows=64):
+    """Number of slab (distributed) levels for an n x n grid on `world` ranks: levels wider than gather_cols,
+    while every rank still owns >= min_own_rows rows and the cuts stay even on every slab level."""
+    if n % world:
+        raise ValueError("grid rows must divide evenly among the ranks")
+    own = n // world
+    nlev = 0
+    while (n >> nlev) > gather_cols and (own >> nlev) >= min_own_rows and own % (1 << (nlev + 1)) == 0:
+        nlev += 1
+    return nlev
+
+
+# ----------------------------------------------------------------------------------------------------
+# halo exchange plumbing (device-agnostic: works on any torch tensors, so gloo/CPU can test it)
+# ----------------------------------------------------------------------------------------------------
+def halo_views(x, own_rows, ncols, halo=HALO):
+    """(top_halo, top_owned, bottom_owned, bottom_halo) row-block views of a slab array of (own + 2 halo) rows."""
+    a = x.view(own_rows + 2 * halo, ncols)
+    return a[:halo], a[halo:2 * halo], a[own_rows:own_rows + halo], a[own_rows + halo:]
+
+
+class LocalComm:
+    """All ranks live in this process (their slab arrays are passed in as lists)."""
+
+    def __init__(self, world):
+        self.world = world
+
+    def exchange(self, arrays, own_rows, ncols):
+        for r in range(self.world):
+            _, top_own, bot_own, _ = halo_views(arrays[r], own_rows, ncols)
+            if r > 0:
+                halo_views(arrays[r - 1], own_rows, ncols)[3].copy_(top_own)
+            if r + 1 < self.world:
+                halo_views(arrays[r + 1], own_rows, ncols)[0].copy_(bot_own)
+
+    def allgather_rows(self, fulls, own_rows, ncols):
+        """every rank's full array gets every rank's owned row block"""
+        for src in range(self.world):
+            blk = fulls[src].view(-1, ncols)[src * own_rows:(src + 1) * own_rows]
+            for dst in range(self.world):
+                if dst != src:
+                    fulls[dst].view(-1, ncols)[src * own_rows:(src + 1) * own_rows].copy_(blk)
+
+    def allreduce_sum(self, scalars):
+        tot = sum(scalars[1:], scalars[0].clone())
+        for s in scalars:
+            s.copy_(tot)
+
+
+class TorchDistComm:
+    """One rank per process over torch.distributed (NCCL: send/recv pairs over NVLink; gloo for CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def exchange(self, arrays, own_rows, ncols):
+        dist = self.dist
+        (x,) = arrays
+        top_halo, top_own, bot_own, bot_halo = halo_views(x, own_rows, ncols)
+        ops = []
+        if self.rank > 0:
+            ops += [dist.P2POp(dist.isend, top_own, self.rank - 1, self.group),
+                    dist.P2POp(dist.irecv, top_halo, self.rank - 1, self.group)]
+        if self.rank + 1 < self.world:
+            ops += [dist.P2POp(dist.isend, bot_own, self.rank + 1, self.group),
+                    dist.P2POp(dist.irecv, bot_halo, self.rank + 1, self.group)]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def allgather_rows(self, fulls, own_rows, ncols):
+        (full,) = fulls
+        mine = full.view(-1, ncols)[self.rank * own_rows:(self.rank + 1) * own_rows].clone()
+        self.dist.all_gather_into_tensor(full.view(-1), mine.view(-1), group=self.group)
+
+    def allreduce_sum(self, scalars):
+        (s,) = scalars
+        self.dist.all_reduce(s, group=self.group)
+
+
+# ----------------------------------------------------------------------------------------------------
+# per-rank device state
+# ----------------------------------------------------------------------------------------------------
+class _RankState:
+    def __init__(self, op, rank, world, nlev_slab, lowest_level):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        N = op.ncols
+        self.rank, self.world, self.N = rank, world, N
+        self.own0 = N // world
+        self.begin0 = rank * self.own0
+        self.nlev = nlev_slab
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.slab = C.c_void_p()
+        _lib.check(lib.mgcmt_hier_create_slab(C.byref(self.slab), N, N, self.begin0, self.own0, nlev_slab, HALO,
+                                              hp(op.row[0]), hp(op.row[1]), hp(op.row[2]),
+                                              hp(op.col[0]), hp(op.col[1]), hp(op.col[2]), stream))
+        # replicated coarse part: full hierarchy whose first nlev_slab levels carry operators only
+        self.coarse = C.c_void_p()
+        _lib.check(lib.mgcmt_hier_create2(C.byref(self.coarse), N, N, 1, hp(op.row[0]), hp(op.row[1]), hp(op.row[2]),
+                                          hp(op.col[0]), hp(op.col[1]), hp(op.col[2]), int(lowest_level), nlev_slab, stream))
+        f64 = torch.float64
+        self.v, self.f, self.tmp = [], [], []
+        for l in range(nlev_slab):
+            n = ((self.own0 >> l) + 2 * HALO) * (N >> l)
+            self.v.append(torch.zeros(n, dtype=f64, device="cuda"))
+            self.f.append(torch.zeros(n, dtype=f64, device="cuda"))
+            self.tmp.append(torch.zeros(n, dtype=f64, device="cuda"))
+        ng = (N >> nlev_slab) ** 2
+        self.fg = torch.zeros(ng, dtype=f64, device="cuda")   # full (replicated) coarse right-hand side
+        self.vg = torch.zeros(ng, dtype=f64, device="cuda")   # full coarse correction
+        self.scal = torch.zeros(8, dtype=f64, device="cuda")
+
+    def close(self):
+        lib = _lib.load()
+        for h in (self.slab, self.coarse):
+            if h:
+                lib.mgcmt_hier_destroy(h)
+        self.slab = self.coarse = None
+
+    def own_rows(self, l):
+        return self.own0 >> l
+
+    def ncols(self, l):
+        return self.N >> l
+
+    def owned(self, x, l):
+        """view of the owned rows of a slab array of level l"""
+        return x.view(self.own_rows(l) + 2 * HALO, self.ncols(l))[HALO:HALO + self.own_rows(l)]
+
+
+class SlabVCycle:
+    """V(4,4) weighted-Jacobi cycles on a row-slab decomposed N x N grid.
+
+    states: one _RankState per rank handled by THIS process (all ranks with LocalComm, one with TorchDistComm)."""
+
+    def __init__(self, op: SeparableOperator, world, comm, ranks, lowest_level=8, gather_cols=2048, omega=2. / 3.):
+        if op.nrows != op.ncols:
+            raise ValueError("slab decomposition is for square 2-D grids")
+        self.op, self.world, self.comm = op, world, comm
+        self.omega = omega
+        self.nlev = plan_levels(op.ncols, world, gather_cols)
+        if self.nlev < 1:
+            raise ValueError("grid too small to decompose over %d ranks (use the single-GPU path)" % world)
+        self.states = [_RankState(op, r, world, self.nlev, lowest_level) for r in ranks]
+
+    def close(self):
+        for s in self.states:
+            s.close()
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _leg(self, st, l, mode, vin, f, vout, e=None, rc=None):
+        torch = _lib.require_cuda()
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(_lib.load().mgcmt_fused_leg(st.slab, l, mode, 4, float(self.shift), float(self.omega), p(vin), p(f),
+                                               p(vout), p(e), p(rc), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def _exchange(self, name, l):
+        arrs = [getattr(st, name)[l] for st in self.states]
+        st0 = self.states[0]
+        self.comm.exchange(arrs, st0.own_rows(l), st0.ncols(l))
+
+    # -- the cycle ------------------------------------------------------------------------------------
+    def vcycle(self, shift, v0_is_zero=True):
+        """In: st.f[0] owned rows (and st.v[0] owned rows unless v0_is_zero).  Out: st.v[0] owned rows."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        self.shift = shift
+        nl = self.nlev
+        self._exchange("f", 0)
+        if not v0_is_zero:
+            self._exchange("v", 0)
+        for l in range(nl):
+            last = (l + 1 == nl)
+            for st in self.states:
+                mode = MODE_DOWN_ZERO if (l > 0 or v0_is_zero) else MODE_DOWN
+                self._leg(st, l, mode, None if mode == MODE_DOWN_ZERO else st.v[l], st.f[l], st.tmp[l],
+                          rc=(st.fg if last else st.f[l + 1]))
+            if last:
+                st0 = self.states[0]
+                self.comm.allgather_rows([st.fg for st in self.states], st0.own_rows(nl), st0.ncols(nl))
+            else:
+                self._exchange("f", l + 1)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for st in self.states:   # replicated coarse part (identical on every rank)
+            _lib.check(lib.mgcmt_vcycle_from(st.coarse, nl, float(shift), _lib.SMOOTH_WJACOBI, float(self.omega),
+                                             C.c_void_p(st.vg.data_ptr()), C.c_void_p(st.fg.data_ptr()), stream))
+        for l in range(nl - 1, -1, -1):
+            last = (l + 1 == nl)
+            self._exchange("tmp", l)
+            for st in self.states:
+                self._leg(st, l, MODE_UP, st.tmp[l], st.f[l], st.v[l], e=(st.vg if last else st.v[l + 1]))
+            if l > 0:
+                self._exchange("v", l)
+
+    def rayleigh(self):
+        """Rayleigh quotients x^T H x / x^T x of st.v[0] (halos of v[0] are refreshed first); returns a float."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        self._exchange("v", 0)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for st in self.states:
+            _lib.check(lib.mgcmt_slab_rayleigh(st.slab, 0, C.c_void_p(st.v[0].data_ptr()),
+                                               C.c_void_p(st.scal.data_ptr()), stream))
+        self.comm.allreduce_sum([st.scal[:2] for st in self.states])
+        num, den = self.states[0].scal[:2].cpu().tolist()
+        return num / den, den
+
+    def scale_v(self, alpha):
+        for st in self.states:
+            st.v[0].mul_(alpha)
+
+    # -- host <-> slab helpers (tests, bench) ----------------------------------------------------------
+    def scatter(self, name, full_host):
+        """full N*N numpy vector -> owned rows of st.<name>[0] on every local rank"""
+        torch = _lib.require_cuda()
+        N = self.op.ncols
+        a = np.asarray(full_host, dtype=np.float64).reshape(N, N)
+        for st in self.states:
+            blk = torch.from_numpy(np.ascontiguousarray(a[st.begin0:st.begin0 + st.own0])).cuda()
+            st.owned(getattr(st, name)[0], 0).copy_(blk)
+
+    def gather_local(self, name):
+        """owned rows of all LOCAL ranks stacked (LocalComm: the full vector)"""
+        torch = _lib.require_cuda()
+        return torch.cat([st.owned(getattr(st, name)[0], 0).reshape(-1) for st in self.states]).cpu().numpy()

@@ -500,3 +500,37 @@ def test_full_size_properties(T, prod, N):
     h.rayleigh(0, v, out2)
     num, den = out2.cpu().tolist()
     assert abs(num / den - lam11) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------
+# row-slab decomposition (multi-GPU path) emulated on one GPU: same kernels, halo copies instead of NCCL
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,world,gather", [(512, 2, 128), (1024, 4, 256), (1024, 8, 512)])
+def test_slab_vcycle_equals_single_gpu(T, prod, N, world, gather):
+    from multigridcmt_b200.slab import LocalComm, SlabVCycle
+    sm, s, _ = prod
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    f = rand(N * N, 3)
+    v0 = rand(N * N, 4)
+    shift = 4.38639582
+    sv = SlabVCycle(H, world, LocalComm(world), range(world), lowest_level=8, gather_cols=gather)
+    try:
+        assert sv.nlev >= 1
+        # zero initial guess (the shift-method drivers)
+        sv.scatter("f", f)
+        sv.vcycle(shift, v0_is_zero=True)
+        got = sv.gather_local("v")
+        want = s.vcycle(np.zeros(N * N), f.copy(), H, sm, shift=shift, lowest_level=8, dimension="2d")
+        assert rel(got, want) < 1e-12
+        # general initial guess
+        sv.scatter("f", f); sv.scatter("v", v0)
+        sv.vcycle(shift, v0_is_zero=False)
+        got = sv.gather_local("v")
+        want = s.vcycle(v0.copy(), f.copy(), H, sm, shift=shift, lowest_level=8, dimension="2d")
+        assert rel(got, want) < 1e-12
+        # Rayleigh quotient over slabs == single GPU
+        rq, den = sv.rayleigh()
+        assert abs(rq - s.rayleigh_quotient(H, want, "2d")) < 1e-12 * abs(rq)
+        assert abs(den - float(want @ want)) < 1e-12 * den
+    finally:
+        sv.close()
