@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-n", type=int, default=2048, help="grid size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--replicas", action="store_true", help="multi-GPU: independent replicas instead of row slabs")
+    ap.add_argument("--gather-cols", type=int, default=2048, help="slab path: levels at most this wide are replicated")
     return ap.parse_args()
 
 
@@ -410,10 +412,131 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_slab(args):
+    """--gpus N > 1: 2-D well 16384^2, row-slab decomposed over N B200s (one rank per GPU), NCCL halo exchange
+    per fused leg, coarse levels (<= 2048^2) replicated after an all-gather.  Same step as the single-GPU arm."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from multigridcmt_b200 import MGCMTStencilMaker, _lib
+    from multigridcmt_b200.slab import HALO, SlabVCycle, TorchDistComm
+    lib = _lib.load()
+    N = args.n or 16384
+    lowest = args.lowest
+    k = len(MODES)
+    sm = MGCMTStencilMaker()
+    H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    sv = SlabVCycle(H, world, TorchDistComm(), [rank], lowest_level=lowest, gather_cols=args.gather_cols)
+    st = sv.states[0]
+    own, begin = st.own0, st.begin0
+    P = interp1(N)
+    shifts = [ev1(N0, a) + ev1(N0, b) for a, b in MODES]
+    V = [sv.new_vector() for _ in range(k)]   # block in slab layout: V[c][0] = this rank's array
+    W = [sv.new_vector() for _ in range(k)]
+    for c, (a, b) in enumerate(MODES):
+        ya, yb = P @ vec1(N0, a), P @ vec1(N0, b)
+        blk = np.outer(ya[begin:begin + own], yb) / (np.linalg.norm(ya) * np.linalg.norm(yb))
+        st.owned(V[c][0], 0).copy_(torch.from_numpy(blk).cuda())
+    lam = torch.zeros(k, 2, dtype=torch.float64, device="cuda")
+
+    def step():
+        for c in range(k):
+            sv.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
+            sv.rayleigh(W[c], sync=False)
+            lam[c].copy_(st.scal[:2])
+        sv.gramschmidt(W)
+        for c in range(k):
+            V[c], W[c] = W[c], V[c]
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start(); clocks.wait_first()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    launches0 = lib.mgcmt_launch_count()
+    lib.mgcmt_profile_enable(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t_end = time.time()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = lib.mgcmt_launch_count() - launches0
+    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
+    lam_h = (lam[:, 0] / lam[:, 1]).cpu().tolist()
+    exact = [ev1(N, a) + ev1(N, b) for a, b in MODES]
+    ups_step = k * updates_per_cycle(N, lowest)
+    value = ups_step * args.steps / (ms * 1e-3)
+
+    # e2e: owned rows of f come from pinned host memory, the owned rows of the result go back, every cycle
+    e2e = None
+    if args.e2e_steps > 0:
+        hostf = torch.empty(own * N, dtype=torch.float64).pin_memory()
+        hostv = torch.empty(own * N, dtype=torch.float64).pin_memory()
+        hostf.copy_(st.owned(V[0][0], 0).reshape(-1))
+        def e2e_step():
+            for c in range(k):
+                st.owned(V[c][0], 0).reshape(-1).copy_(hostf, non_blocking=True)
+                sv.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
+                hostv.copy_(st.owned(W[c][0], 0).reshape(-1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+        e2e_step()
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": ups_step * args.e2e_steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": k * own * N * 8 * world, "d2h_bytes_per_step": k * own * N * 8 * world,
+               "steps": args.e2e_steps, "call": "SlabVCycle.vcycle on owned rows copied from / to pinned host memory"}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "2D infinite well %d^2 slab-decomposed over %d GPUs (rows), lowest 4 eigenpairs, shift method: "
+                                   "4 x V(4,4) + Rayleigh quotient + MGS per step" % (N, world),
+                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": sv.nlev, "halo_rows": HALO,
+                       "replicated_from": "%d^2" % (N >> sv.nlev), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
+                       "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9)},
+            "vcycles_per_s": k * args.steps / (ms * 1e-3),
+            "eigenvalues": lam_h, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam_h, exact)],
+            "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": 304.0 * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": 304.0 * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
+                         "kernel": "whole step per GPU at 304 B per fine unknown and V-cycle (SURVEY 8d); per-kernel numbers: N=1 run",
+                         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
+    sv.close()
+    dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.replicas:
+        run_slab(args)
     else:
         run_ours(args)
 

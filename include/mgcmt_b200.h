@@ -175,6 +175,9 @@ int mgcmt_dot(long long n, const double *d_x, const double *d_y, double *d_out, 
 int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream);
 /* x *= 1/||x||_2          -- `w / np.linalg.norm(w)`, e.g. 2DPotGS.py:96; MGCMTProcessor.normalize */
 int mgcmt_normalize(long long n, double *d_x, void *stream);
+/* x /= sqrt(*d_sumsq) with the sum of squares read from device memory (e.g. after an all-reduce of per-rank
+ * partial sums in the slab-decomposed path) */
+int mgcmt_scale_inv_norm(long long n, double *d_x, const double *d_sumsq, void *stream);
 /* y = alpha*x + y with alpha read from device memory, scaled by `sign` */
 int mgcmt_axpy_dev(long long n, const double *d_alpha, double sign, const double *d_x, double *d_y,
                    void *stream);

@@ -792,6 +792,12 @@ int mgcmt_normalize(long long n, double *d_x, void *stream) {
   return MGCMT_OK;
 }
 
+int mgcmt_scale_inv_norm(long long n, double *d_x, const double *d_sumsq, void *stream) {
+  if (n < 0 || !d_x || !d_sumsq) return fail(MGCMT_ERR_ARG, "bad scale arguments");
+  CU(launch_scale_by_inv_norm(n, d_x, d_sumsq, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
 int mgcmt_axpy_dev(long long n, const double *d_alpha, double sign, const double *d_x, double *d_y,
                    void *stream) {
   if (n < 0 || !d_alpha || !d_x || !d_y) return fail(MGCMT_ERR_ARG, "bad axpy arguments");

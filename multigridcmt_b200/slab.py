@@ -198,12 +198,38 @@ class SlabVCycle:
         st0 = self.states[0]
         self.comm.exchange(arrs, st0.own_rows(l), st0.ncols(l))
 
+    def new_vector(self):
+        """one finest-level slab array (owned rows + halos, zero) per local rank"""
+        torch = _lib.require_cuda()
+        return [torch.zeros_like(st.v[0]) for st in self.states]
+
     # -- the cycle ------------------------------------------------------------------------------------
-    def vcycle(self, shift, v0_is_zero=True):
-        """In: st.f[0] owned rows (and st.v[0] owned rows unless v0_is_zero).  Out: st.v[0] owned rows."""
+    def vcycle(self, shift, v0_is_zero=True, f0=None, v0=None):
+        """In: the owned rows of f (and of v unless v0_is_zero).  Out: the owned rows of v (halo rows are scratch).
+        f0 / v0: per-local-rank finest-level slab arrays to use instead of st.f[0] / st.v[0] (so a block of
+        eigenvectors kept in slab layout needs no staging copies); f0's halo rows are refreshed in place."""
         torch = _lib.require_cuda()
         lib = _lib.load()
         self.shift = shift
+        nl = self.nlev
+        saved = None
+        if f0 is not None or v0 is not None:
+            saved = [(st.f[0], st.v[0]) for st in self.states]
+            for i, st in enumerate(self.states):
+                if f0 is not None:
+                    st.f[0] = f0[i]
+                if v0 is not None:
+                    st.v[0] = v0[i]
+        try:
+            self._vcycle_impl(shift, v0_is_zero)
+        finally:
+            if saved is not None:
+                for st, (f, v) in zip(self.states, saved):
+                    st.f[0], st.v[0] = f, v
+
+    def _vcycle_impl(self, shift, v0_is_zero):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
         nl = self.nlev
         self._exchange("f", 0)
         if not v0_is_zero:
@@ -231,18 +257,52 @@ class SlabVCycle:
             if l > 0:
                 self._exchange("v", l)
 
-    def rayleigh(self):
-        """Rayleigh quotients x^T H x / x^T x of st.v[0] (halos of v[0] are refreshed first); returns a float."""
+    def rayleigh(self, x=None, sync=True):
+        """x^T H x and x^T x of a finest-level slab vector (default st.v[0]); its halo rows are refreshed first.
+        sync=True returns (quotient, x^T x) as floats; sync=False leaves [num, den] in st.scal[:2] on the device."""
         torch = _lib.require_cuda()
         lib = _lib.load()
-        self._exchange("v", 0)
+        arrs = x if x is not None else [st.v[0] for st in self.states]
+        st0 = self.states[0]
+        self.comm.exchange(arrs, st0.own_rows(0), st0.ncols(0))
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for st in self.states:
-            _lib.check(lib.mgcmt_slab_rayleigh(st.slab, 0, C.c_void_p(st.v[0].data_ptr()),
+        for st, a in zip(self.states, arrs):
+            _lib.check(lib.mgcmt_slab_rayleigh(st.slab, 0, C.c_void_p(a.data_ptr()),
                                                C.c_void_p(st.scal.data_ptr()), stream))
         self.comm.allreduce_sum([st.scal[:2] for st in self.states])
+        if not sync:
+            return None
         num, den = self.states[0].scal[:2].cpu().tolist()
         return num / den, den
+
+    def gramschmidt(self, block):
+        """Modified Gram-Schmidt (MGCMTProcessor.py:44-50) of k slab vectors; block[c] = per-local-rank arrays.
+        Dots run over the owned rows of each rank and are all-reduced (one scalar vector per column)."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        k = len(block)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        own = [st.owned(block[0][i], 0).numel() for i, st in enumerate(self.states)]
+        views = [[st.owned(block[c][i], 0).reshape(-1) for i, st in enumerate(self.states)] for c in range(k)]
+        for i in range(k):
+            for r, st in enumerate(self.states):
+                _lib.check(lib.mgcmt_dot(own[r], p(views[i][r]), p(views[i][r]), p(st.scal[0:1]), stream))
+            self.comm.allreduce_sum([st.scal[0:1] for st in self.states])
+            for r, st in enumerate(self.states):                   # q_i = w_i / ||w_i||
+                _lib.check(lib.mgcmt_scale_inv_norm(own[r], p(views[i][r]), p(st.scal[0:1]), stream))
+            if i + 1 == k:
+                break
+            for r, st in enumerate(self.states):                   # <q_i,q_i> and <w_j,q_i>, j > i
+                _lib.check(lib.mgcmt_dot(own[r], p(views[i][r]), p(views[i][r]), p(st.scal[0:1]), stream))
+                for j in range(i + 1, k):
+                    _lib.check(lib.mgcmt_dot(own[r], p(views[j][r]), p(views[i][r]), p(st.scal[j - i:j - i + 1]), stream))
+            self.comm.allreduce_sum([st.scal[:k - i] for st in self.states])
+            for r, st in enumerate(self.states):
+                st.scal[1:k - i].div_(st.scal[0])                  # <w_j,q_i> / <q_i,q_i> (MGCMTProcessor.py:10-20)
+                for j in range(i + 1, k):
+                    _lib.check(lib.mgcmt_axpy_dev(own[r], p(st.scal[j - i:j - i + 1]), -1.0, p(views[i][r]), p(views[j][r]), stream))
+        return block
 
     def scale_v(self, alpha):
         for st in self.states:

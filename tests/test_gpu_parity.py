@@ -534,3 +534,39 @@ def test_slab_vcycle_equals_single_gpu(T, prod, N, world, gather):
         assert abs(den - float(want @ want)) < 1e-12 * den
     finally:
         sv.close()
+
+
+def test_slab_block_step_matches_single_gpu(T, prod):
+    """One outer shift-method step on a block kept in slab layout (external f0/v0 arrays, slab Rayleigh quotient,
+    distributed modified Gram-Schmidt) == the same step with the drop-in classes on one GPU."""
+    from multigridcmt_b200.slab import LocalComm, SlabVCycle
+    sm, s, p = prod
+    N, world, k = 512, 4, 3
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    shifts = [1.76659015, 4.38639582, 7.00620149]
+    Vh = rand(N * N * k, 8).reshape(N * N, k)
+    sv = SlabVCycle(H, world, LocalComm(world), range(world), lowest_level=8, gather_cols=128)
+    try:
+        V = [sv.new_vector() for _ in range(k)]
+        W = [sv.new_vector() for _ in range(k)]
+        for c in range(k):
+            a = Vh[:, c].reshape(N, N)
+            for i, st in enumerate(sv.states):
+                st.owned(V[c][i], 0).copy_(T.from_numpy(np.ascontiguousarray(a[st.begin0:st.begin0 + st.own0])).cuda())
+        lam = []
+        for c in range(k):
+            sv.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
+            lam.append(sv.rayleigh(W[c])[0])
+        sv.gramschmidt(W)
+        got = np.stack([T.cat([st.owned(W[c][i], 0).reshape(-1) for i, st in enumerate(sv.states)]).cpu().numpy()
+                        for c in range(k)], axis=1)
+    finally:
+        sv.close()
+    Wh = np.zeros((N * N, k)); lam_ref = []
+    for c in range(k):
+        w = s.vcycle(np.zeros(N * N), Vh[:, c].copy(), H, sm, shift=shifts[c], lowest_level=8, dimension="2d")
+        Wh[:, c] = w
+        lam_ref.append(s.rayleigh_quotient(H, w, "2d"))
+    want = p.gramschmidt(Wh)
+    assert np.allclose(lam, lam_ref, rtol=1e-12, atol=0)
+    assert rel(got, want) < 1e-11
