@@ -272,10 +272,12 @@ def run_ours(args):
     streams = [torch.cuda.Stream() for _ in range(nstreams)]
     # replicas: with N ranks every rank runs the same independent block (data-parallel over problems);
     # the path has no exchange step at this problem size.  (Slab decomposition of 16384^2: later round.)
-    V = torch.from_numpy(V_host).cuda()            # (k, n) vector-major block, resident in HBM
-    W = torch.zeros_like(V)
+    blocks = [torch.from_numpy(V_host).cuda(), None]   # (k, n) vector-major blocks, resident in HBM
+    blocks[1] = torch.zeros_like(blocks[0])
+    cur = [0]                                          # blocks[cur] = V (input), blocks[1 - cur] = W (output)
     rq = torch.zeros(k, 2, dtype=torch.float64, device="cuda")
     def step(serial=False):
+        V, W = blocks[cur[0]], blocks[1 - cur[0]]
         main = torch.cuda.current_stream()
         if not serial:
             for st_ in streams:
@@ -293,7 +295,7 @@ def run_ours(args):
             for st_ in streams:
                 main.wait_stream(st_)
         _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(W), 1, _stream_ptr(torch)))
-        V.copy_(W)
+        cur[0] = 1 - cur[0]                            # the orthonormalised block is the next step's input
 
     clocks = Clocks(local)
     if rank == 0:

@@ -109,6 +109,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   const int gref = min(max(L.row0 + (r0 + r1) / 2, 0), L.nrows_glob - 1);
   const double kad_ref = L.ka_di[gref];
   const double mad_ref = FIVE ? 1.0 : L.ma_di[gref];
+  // all six row coefficients of the reference row: steps whose rows all look like it (every interior step of a
+  // constant-coefficient operator) use these registers instead of the shared-memory row table
+  const double kal_ref = L.ka_lo[gref], kau_ref = L.ka_up[gref];
+  const double mal_ref = FIVE ? 0.0 : L.ma_lo[gref], mau_ref = FIVE ? 0.0 : L.ma_up[gref];
 
   for (int i = tid; i < ntab; i += kWarps * 32) {
     const int row = tab0 + i;
@@ -123,14 +127,16 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     rc.ka_lo = rin ? L.ka_lo[g] : 0.0; rc.ka_di = rin ? L.ka_di[g] : 0.0; rc.ka_up = rin ? L.ka_up[g] : 0.0;
     if (FIVE) { rc.ma_lo = 0.0; rc.ma_di = rin ? 1.0 : 0.0; rc.ma_up = 0.0; }
     else { rc.ma_lo = rin ? L.ma_lo[g] : 0.0; rc.ma_di = rin ? L.ma_di[g] : 0.0; rc.ma_up = rin ? L.ma_up[g] : 0.0; }
-    // slow = 1 if any row finalised while row `row` is the newest input (rows row-NSTAGE .. row-1) has a
-    // diagonal different from the reference row's, i.e. the step needs the division path
+    // slow = 1 if, while row `row` is the newest input, any row the stages touch (row-NSTAGE .. row+1) lies outside
+    // the grid or has coefficients different from the reference row's: that step reads the table (and may
+    // recompute omega/diag); all other steps run on the reference registers
     double slow = 0.0;
-    for (int d = 1; d <= NSTAGE; ++d) {
+    for (int d = -1; d <= NSTAGE; ++d) {
       const int g2 = gg - d;
-      if (g2 < 0 || g2 >= L.nrows_glob) continue;
-      const double mad2 = FIVE ? 1.0 : L.ma_di[g2];
-      if (L.ka_di[g2] != kad_ref || mad2 != mad_ref) slow = 1.0;
+      if (g2 < 0 || g2 >= L.nrows_glob) { slow = 1.0; continue; }
+      bool same = (L.ka_lo[g2] == kal_ref && L.ka_di[g2] == kad_ref && L.ka_up[g2] == kau_ref);
+      if (!FIVE) same = same && (L.ma_lo[g2] == mal_ref && L.ma_di[g2] == mad_ref && L.ma_up[g2] == mau_ref);
+      if (!same) slow = 1.0;
     }
     rc.slow = slow;
     rc.pad = 0.0;
@@ -289,9 +295,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       const int n = t - k;       // arriving row (of stage k's input)
       const int rho = n - 1;     // finalised row
       const RowCoef *tb = rowtab + (rho - tab0);
-      const double cr_ka_up = tb[0].ka_up, cr_ma_up = FIVE ? 0.0 : tb[0].ma_up;
-      const double cn_ka_di = tb[1].ka_di, cn_ma_di = FIVE ? 1.0 : tb[1].ma_di;
-      const double cp_ka_lo = tb[2].ka_lo, cp_ma_lo = FIVE ? 0.0 : tb[2].ma_lo;
+      const double cr_ka_up = SLOW ? tb[0].ka_up : kau_ref, cr_ma_up = FIVE ? 0.0 : (SLOW ? tb[0].ma_up : mau_ref);
+      const double cn_ka_di = SLOW ? tb[1].ka_di : kad_ref, cn_ma_di = FIVE ? 1.0 : (SLOW ? tb[1].ma_di : mad_ref);
+      const double cn_ka_lo = SLOW ? tb[1].ka_lo : kal_ref;
+      const double cp_ka_lo = SLOW ? tb[2].ka_lo : kal_ref, cp_ma_lo = FIVE ? 0.0 : (SLOW ? tb[2].ma_lo : mal_ref);
       // horizontal part of the arriving row
       const double xl = __shfl_up_sync(0xffffffffu, x[C - 1], 1);
       const double xr = __shfl_down_sync(0xffffffffu, x[0], 1);
@@ -334,8 +341,13 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
         const double o = is_res ? (ff - acc) : (st[k].xc[q] + w[q] * (ff - acc));
         out[q] = o;
         // scatter the arriving row into the two rows still open
-        st[k].a1[q] = st[k].a2[q] + ((FIVE ? (T[q] + cn_ka_di * S[q]) : (cn_ma_di * T[q] + cn_ka_di * S[q])) - shift * x[q]);
-        st[k].a2[q] = FIVE ? cp_ka_lo * S[q] : (cp_ma_lo * T[q] + cp_ka_lo * S[q]);
+        if (FIVE) {
+          // 5-point: the lower-neighbour part of row n is ka_lo[n] * x[n-1] = ka_lo[n] * xc -- no second open sum needed
+          st[k].a1[q] = cn_ka_lo * st[k].xc[q] + ((T[q] + cn_ka_di * x[q]) - shift * x[q]);
+        } else {
+          st[k].a1[q] = st[k].a2[q] + ((cn_ma_di * T[q] + cn_ka_di * S[q]) - shift * x[q]);
+          st[k].a2[q] = cp_ma_lo * T[q] + cp_ka_lo * S[q];
+        }
         st[k].xc[q] = x[q];
       }
       // the finalised row is the next stage's arriving row
