@@ -175,6 +175,10 @@ int mgcmt_dot(long long n, const double *d_x, const double *d_y, double *d_out, 
 int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream);
 /* x *= 1/||x||_2          -- `w / np.linalg.norm(w)`, e.g. 2DPotGS.py:96; MGCMTProcessor.normalize */
 int mgcmt_normalize(long long n, double *d_x, void *stream);
+/* the two halves of modified == 2 for vectors `stride` doubles apart (slab-decomposed blocks: the packed upper Gram
+ * matrix d_out[k(k+1)/2] of the owned rows is all-reduced between the two calls) */
+int mgcmt_gram(long long n, int k, const double *d_V, long long stride, double *d_out, void *stream);
+int mgcmt_cholqr_apply(long long n, int k, double *d_V, long long stride, const double *d_gram, void *stream);
 /* x /= sqrt(*d_sumsq) with the sum of squares read from device memory (e.g. after an all-reduce of per-rank
  * partial sums in the slab-decomposed path) */
 int mgcmt_scale_inv_norm(long long n, double *d_x, const double *d_sumsq, void *stream);
@@ -186,7 +190,10 @@ int mgcmt_axpby(long long n, double a, const double *d_x, double b, const double
                 void *stream);
 /* Gram-Schmidt of k vectors of length n stored one after another (vector-major: d_V + c*n is
  * column c).  modified != 0: MGS exactly as MGCMTProcessor.gramschmidt (MGCMTProcessor.py:44-50);
- * modified == 0: classical GS followed by normalisation (MGCMTProcessor.py:35-42). In place. */
+ * modified == 0: classical GS followed by normalisation (MGCMTProcessor.py:35-42). In place.
+ * modified == 2: Gram-matrix (Cholesky-QR) form -- Q = W R^-1 with W^T W = R^T R, the same Q in exact arithmetic
+ *   (QR with positive diagonal is unique) in 3k instead of ~k^2+3k vector passes; rounding differs from MGS by
+ *   O(cond(W)^2 eps), so it is meant for the nearly orthonormal blocks of the eigen-iteration (k <= 6). */
 int mgcmt_gramschmidt(long long n, int k, double *d_V, int modified, void *stream);
 
 #ifdef __cplusplus

@@ -61,7 +61,9 @@ class MGCMTProcessor:
         if was_dev and blk.data_ptr() == vectors.data_ptr():
             blk = blk.clone()  # the reference returns a new array and leaves its input alone
         k, n = blk.shape
-        _lib.check(_lib.load().mgcmt_gramschmidt(n, k, _ptr(blk), 1 if modified else 0, _stream_ptr(torch)))
+        # modified=2 (extension): Gram-matrix / Cholesky-QR form, same Q in exact arithmetic, 3k vector passes
+        mode = 2 if modified == 2 else (1 if modified else 0)
+        _lib.check(_lib.load().mgcmt_gramschmidt(n, k, _ptr(blk), mode, _stream_ptr(torch)))
         return _from_block(blk, was_dev)
 
     def normalize(self, vectors):

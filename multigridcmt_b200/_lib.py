@@ -59,6 +59,8 @@ SIGNATURES = {
     "mgcmt_dot": (_I, [_LL, _P, _P, _P, _P]),
     "mgcmt_rayleigh": (_I, [_P, _I, _P, _P, _P]),
     "mgcmt_normalize": (_I, [_LL, _P, _P]),
+    "mgcmt_gram": (_I, [_LL, _I, _P, _LL, _P, _P]),
+    "mgcmt_cholqr_apply": (_I, [_LL, _I, _P, _LL, _P, _P]),
     "mgcmt_scale_inv_norm": (_I, [_LL, _P, _P, _P]),
     "mgcmt_axpy_dev": (_I, [_LL, _P, _D, _P, _P, _P]),
     "mgcmt_gramschmidt": (_I, [_LL, _I, _P, _I, _P]),

@@ -66,8 +66,9 @@ bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // scratch for reductions that do not belong to a hierarchy (one per device, single-stream use)
 struct Scratch {
-  double *partials = nullptr;  // 16 * kReduceBlocks
+  double *partials = nullptr;  // 32 * kReduceBlocks
   double *scal = nullptr;      // 64 scalars
+  int *status = nullptr;
 };
 Scratch g_scratch[64];
 
@@ -77,8 +78,10 @@ int get_scratch(Scratch **out) {
   if (dev < 0 || dev >= 64) return fail(MGCMT_ERR_STATE, "device index out of range");
   Scratch &s = g_scratch[dev];
   if (!s.partials) {
-    CU(cudaMalloc(&s.partials, sizeof(double) * 16 * kReduceBlocks));
+    CU(cudaMalloc(&s.partials, sizeof(double) * 32 * kReduceBlocks));
     CU(cudaMalloc(&s.scal, sizeof(double) * 64));
+    CU(cudaMalloc(&s.status, sizeof(int)));
+    CU(cudaMemset(s.status, 0, sizeof(int)));
   }
   *out = &s;
   return MGCMT_OK;
@@ -792,6 +795,27 @@ int mgcmt_normalize(long long n, double *d_x, void *stream) {
   return MGCMT_OK;
 }
 
+int mgcmt_gram(long long n, int k, const double *d_V, long long stride, double *d_out, void *stream) {
+  if (n <= 0 || k < 1 || k > 6 || (n & 1) || !d_V || !d_out || !al16(d_V) || (stride & 1))
+    return fail(MGCMT_ERR_ARG, "bad gram arguments (k <= 6, even n and stride, aligned vectors)");
+  Scratch *sc;
+  int rc = get_scratch(&sc);
+  if (rc) return rc;
+  CU(launch_gram(n, k, d_V, stride, sc->partials, d_out, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_cholqr_apply(long long n, int k, double *d_V, long long stride, const double *d_gram, void *stream) {
+  if (n <= 0 || k < 1 || k > 6 || (n & 1) || !d_V || !d_gram || !al16(d_V) || (stride & 1))
+    return fail(MGCMT_ERR_ARG, "bad cholqr arguments");
+  Scratch *sc;
+  int rc = get_scratch(&sc);
+  if (rc) return rc;
+  CU(launch_chol_inverse(k, d_gram, sc->scal + 24, sc->status, (cudaStream_t)stream));
+  CU(launch_cholqr_apply(n, k, d_V, stride, sc->scal + 24, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
 int mgcmt_scale_inv_norm(long long n, double *d_x, const double *d_sumsq, void *stream) {
   if (n < 0 || !d_x || !d_sumsq) return fail(MGCMT_ERR_ARG, "bad scale arguments");
   CU(launch_scale_by_inv_norm(n, d_x, d_sumsq, (cudaStream_t)stream));
@@ -812,6 +836,14 @@ int mgcmt_gramschmidt(long long n, int k, double *d_V, int modified, void *strea
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   double *scal = sc->scal;  // [0] sumsq / <q,q>, [1..16] dots, [32..] <u_i,u_i> (classical)
+  if (modified == 2) {
+    // Gram-matrix (Cholesky-QR) form: same Q in exact arithmetic, 3k vector passes (see reduce.cu)
+    if (k > 6 || (n & 1) || !al16(d_V)) return fail(MGCMT_ERR_ARG, "Gram-matrix orthonormalisation needs k <= 6, even n, aligned block");
+    CU(launch_gram(n, k, d_V, n, sc->partials, scal, s));                 // scal[0..k(k+1)/2)
+    CU(launch_chol_inverse(k, scal, scal + 24, sc->status, s));           // scal[24..24+k*k)
+    CU(launch_cholqr_apply(n, k, d_V, n, scal + 24, s));
+    return MGCMT_OK;
+  }
   if (modified && (n % 2 == 0) && al16(d_V) && k <= 8) {
     // MGCMTProcessor.py:44-50, two fused passes per column (reduce.cu): 29 instead of 42 vector passes at k = 4
     CU(launch_dot(n, d_V, d_V, sc->partials, scal, s));  // ||w_0||^2

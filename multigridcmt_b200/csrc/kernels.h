@@ -88,6 +88,11 @@ cudaError_t launch_mgs_scale_dots(long long n, int m, double *wi, const double *
                                   long long stride, double *partials, double *out, cudaStream_t s);
 cudaError_t launch_mgs_update(long long n, int m, const double *qi, const double *dots, double *wj0, long long stride,
                               double *partials, double *out_sumsq, cudaStream_t s);
+// Gram-matrix (Cholesky-QR) orthonormalisation pieces: packed upper Gram matrix (k(k+1)/2 dots), the inverse of its
+// Cholesky factor, and Q = W R^-1 in place; k <= 6
+cudaError_t launch_gram(long long n, int k, const double *w0, long long stride, double *partials, double *out, cudaStream_t s);
+cudaError_t launch_chol_inverse(int k, const double *g, double *rinv, int *status, cudaStream_t s);
+cudaError_t launch_cholqr_apply(long long n, int k, double *w0, long long stride, const double *rinv, cudaStream_t s);
 cudaError_t launch_scale_by_inv_norm(long long n, double *x, const double *sumsq, cudaStream_t s);
 cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *denom, double sign,
                             const double *x, double *y, cudaStream_t s);

@@ -66,6 +66,10 @@ class LocalComm:
             if r + 1 < self.world:
                 halo_views(arrays[r + 1], own_rows, ncols)[0].copy_(bot_own)
 
+    def exchange_many(self, items):
+        for (arrays, own_rows, ncols) in items:
+            self.exchange(arrays, own_rows, ncols)
+
     def allgather_rows(self, fulls, own_rows, ncols):
         """every rank's full array gets every rank's owned row block"""
         for src in range(self.world):
@@ -91,16 +95,21 @@ class TorchDistComm:
         self.rank = dist.get_rank(group)
 
     def exchange(self, arrays, own_rows, ncols):
+        self.exchange_many([(arrays, own_rows, ncols)])
+
+    def exchange_many(self, items):
+        """items: [(arrays, own_rows, ncols), ...] -- all halo exchanges of one phase in ONE NCCL group call"""
         dist = self.dist
-        (x,) = arrays
-        top_halo, top_own, bot_own, bot_halo = halo_views(x, own_rows, ncols)
         ops = []
-        if self.rank > 0:
-            ops += [dist.P2POp(dist.isend, top_own, self.rank - 1, self.group),
-                    dist.P2POp(dist.irecv, top_halo, self.rank - 1, self.group)]
-        if self.rank + 1 < self.world:
-            ops += [dist.P2POp(dist.isend, bot_own, self.rank + 1, self.group),
-                    dist.P2POp(dist.irecv, bot_halo, self.rank + 1, self.group)]
+        for (arrays, own_rows, ncols) in items:
+            (x,) = arrays
+            top_halo, top_own, bot_own, bot_halo = halo_views(x, own_rows, ncols)
+            if self.rank > 0:
+                ops += [dist.P2POp(dist.isend, top_own, self.rank - 1, self.group),
+                        dist.P2POp(dist.irecv, top_halo, self.rank - 1, self.group)]
+            if self.rank + 1 < self.world:
+                ops += [dist.P2POp(dist.isend, bot_own, self.rank + 1, self.group),
+                        dist.P2POp(dist.irecv, bot_halo, self.rank + 1, self.group)]
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
@@ -147,7 +156,7 @@ class _RankState:
         ng = (N >> nlev_slab) ** 2
         self.fg = torch.zeros(ng, dtype=f64, device="cuda")   # full (replicated) coarse right-hand side
         self.vg = torch.zeros(ng, dtype=f64, device="cuda")   # full coarse correction
-        self.scal = torch.zeros(8, dtype=f64, device="cuda")
+        self.scal = torch.zeros(32, dtype=f64, device="cuda")
 
     def close(self):
         lib = _lib.load()
@@ -249,13 +258,16 @@ class SlabVCycle:
         for st in self.states:   # replicated coarse part (identical on every rank)
             _lib.check(lib.mgcmt_vcycle_from(st.coarse, nl, float(shift), _lib.SMOOTH_WJACOBI, float(self.omega),
                                              C.c_void_p(st.vg.data_ptr()), C.c_void_p(st.fg.data_ptr()), stream))
+        st0 = self.states[0]
         for l in range(nl - 1, -1, -1):
             last = (l + 1 == nl)
-            self._exchange("tmp", l)
+            # halos of the smoothed iterate and (below the last slab level) of the coarse correction: one NCCL group
+            items = [([st.tmp[l] for st in self.states], st0.own_rows(l), st0.ncols(l))]
+            if not last:
+                items.append(([st.v[l + 1] for st in self.states], st0.own_rows(l + 1), st0.ncols(l + 1)))
+            self.comm.exchange_many(items)
             for st in self.states:
                 self._leg(st, l, MODE_UP, st.tmp[l], st.f[l], st.v[l], e=(st.vg if last else st.v[l + 1]))
-            if l > 0:
-                self._exchange("v", l)
 
     def rayleigh(self, x=None, sync=True):
         """x^T H x and x^T x of a finest-level slab vector (default st.v[0]); its halo rows are refreshed first.
@@ -274,6 +286,33 @@ class SlabVCycle:
             return None
         num, den = self.states[0].scal[:2].cpu().tolist()
         return num / den, den
+
+    def new_block(self, k):
+        """k finest-level slab vectors in one (k, slab_size) tensor per local rank (equal stride: what the Gram-matrix
+        kernels want); block[i][c] is vector c of local rank i"""
+        torch = _lib.require_cuda()
+        return [torch.zeros(k, st.v[0].numel(), dtype=torch.float64, device="cuda") for st in self.states]
+
+    def gramschmidt_gram(self, blocks):
+        """Orthonormalise the k vectors of a block (new_block layout) in Gram-matrix / Cholesky-QR form: local packed
+        Gram matrix of the owned rows -> one all-reduce of k(k+1)/2 scalars -> Q = W R^-1 locally."""
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        k = blocks[0].shape[0]
+        ng = k * (k + 1) // 2
+        for st, blk in zip(self.states, blocks):
+            off = HALO * st.ncols(0)
+            n_own = st.own_rows(0) * st.ncols(0)
+            base = C.c_void_p(blk.data_ptr() + 8 * off)
+            _lib.check(lib.mgcmt_gram(n_own, k, base, blk.shape[1], C.c_void_p(st.scal.data_ptr()), stream))
+        self.comm.allreduce_sum([st.scal[:ng] for st in self.states])
+        for st, blk in zip(self.states, blocks):
+            off = HALO * st.ncols(0)
+            n_own = st.own_rows(0) * st.ncols(0)
+            base = C.c_void_p(blk.data_ptr() + 8 * off)
+            _lib.check(lib.mgcmt_cholqr_apply(n_own, k, base, blk.shape[1], C.c_void_p(st.scal.data_ptr()), stream))
+        return blocks
 
     def gramschmidt(self, block):
         """Modified Gram-Schmidt (MGCMTProcessor.py:44-50) of k slab vectors; block[c] = per-local-rank arrays.

@@ -387,6 +387,18 @@ def test_gramschmidt_large_and_deterministic(T, prod, o):
     assert np.max(np.abs(oc - np.eye(k))) < 1e-13
 
 
+def test_gram_form_equals_mgs_on_eigen_blocks(T, prod):
+    """modified=2 (Gram matrix + Cholesky) gives the Gram-Schmidt Q on the nearly orthonormal blocks of the eigen-loop."""
+    _, _, p = prod
+    n, k = 1 << 16, 4
+    base = np.stack([orc.well_eigenvector_1d(n, m + 1) for m in range(k)], axis=1)
+    a = base + 1e-3 * rand(n * k, 5).reshape(n, k)
+    q1 = p.gramschmidt(a.copy(), modified=1)
+    q2 = p.gramschmidt(a.copy(), modified=2)
+    assert rel(q2, q1) < 1e-12
+    assert np.max(np.abs(q2.T @ q2 - np.eye(k))) < 1e-13
+
+
 def test_rq_family_matches_reference_golden(prod, golden, o):
     """rqmin / vcycle_rqmg (MGCMTSolver.py:17-122) against the real reference's outputs."""
     sm, s, _ = prod
@@ -557,9 +569,17 @@ def test_slab_block_step_matches_single_gpu(T, prod):
         for c in range(k):
             sv.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
             lam.append(sv.rayleigh(W[c])[0])
+        # the same block also through the Gram-matrix form (block layout)
+        blocks = sv.new_block(k)
+        for i in range(len(sv.states)):
+            for c in range(k):
+                blocks[i][c].copy_(W[c][i])
         sv.gramschmidt(W)
+        sv.gramschmidt_gram(blocks)
         got = np.stack([T.cat([st.owned(W[c][i], 0).reshape(-1) for i, st in enumerate(sv.states)]).cpu().numpy()
                         for c in range(k)], axis=1)
+        got2 = np.stack([T.cat([st.owned(blocks[i][c], 0).reshape(-1) for i, st in enumerate(sv.states)]).cpu().numpy()
+                         for c in range(k)], axis=1)
     finally:
         sv.close()
     Wh = np.zeros((N * N, k)); lam_ref = []
@@ -570,3 +590,5 @@ def test_slab_block_step_matches_single_gpu(T, prod):
     want = p.gramschmidt(Wh)
     assert np.allclose(lam, lam_ref, rtol=1e-12, atol=0)
     assert rel(got, want) < 1e-11
+    assert np.max(np.abs(got2.T @ got2 - np.eye(k))) < 1e-12     # (random block: compare the invariants, not the bits)
+    assert rel(got2 @ (got2.T @ want), want) < 1e-10
