@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="grid size N (N x N unknowns); default 4096")
+    ap.add_argument("--n", "--grid", dest="n", type=int, default=0, help="grid size N (N x N unknowns); default 4096 (16384 for --gpus > 1)")
     ap.add_argument("--lowest", type=int, default=8, help="lowest_level (reference's 2-D choice: 8, 2DPot.py:89)")
     ap.add_argument("--smoother", default="wjacobi", choices=["wjacobi", "rbgs"])
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -487,7 +487,7 @@ def run_slab(args):
     Vb, Wb = sv.new_block(k)[0], sv.new_block(k)[0]       # (k, slab_size) blocks in slab layout
     V = [[Vb[c]] for c in range(k)]                       # V[c][0] = this rank's slab array of vector c
     W = [[Wb[c]] for c in range(k)]
-    blk = {"V": Vb, "W": Wb}
+    bd = {"V": Vb, "W": Wb}
     for c, (a, b) in enumerate(MODES):
         ya, yb = P @ vec1(N0, a), P @ vec1(N0, b)
         blk = np.outer(ya[begin:begin + own], yb) / (np.linalg.norm(ya) * np.linalg.norm(yb))
@@ -507,10 +507,10 @@ def run_slab(args):
         for s_ in streams:
             main.wait_stream(s_)
         if args.ortho == "gram":
-            sv.gramschmidt_gram([blk["W"]])
+            sv.gramschmidt_gram([bd["W"]])
         else:
             sv.gramschmidt(W)
-        blk["V"], blk["W"] = blk["W"], blk["V"]
+        bd["V"], bd["W"] = bd["W"], bd["V"]
         for c in range(k):
             V[c], W[c] = W[c], V[c]
 
