@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams for the independent V-cycles of a step")
     ap.add_argument("--ortho", default="gram", choices=["mgs", "gram"],
                     help="block orthonormalisation: column-by-column MGS (MGCMTProcessor.py:44-50) or its Gram-matrix form")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--replicas", action="store_true", help="multi-GPU: independent replicas instead of row slabs")
     ap.add_argument("--gather-cols", type=int, default=2048, help="slab path: levels at most this wide are replicated")
     return ap.parse_args()
@@ -320,15 +321,19 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = lib.mgcmt_launch_count()
+    step(); step()
+    launches_per_step = (lib.mgcmt_launch_count() - launches0) // 2
+    run, graphed = make_runner(step, torch, not args.no_graph)
+    run(2)
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.time()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    run(args.steps)
     e1.record()
     torch.cuda.synchronize()
     t_end = time.time()
-    launches_timed = lib.mgcmt_launch_count() - launches0
+    launches_timed = launches_per_step * args.steps
     # roofline pass: the same step, run serially on one stream so that the CUDA events bracketing every
     # finest-level leg (on its launching stream) time that kernel alone, not its share of an overlapped GPU
     lib.mgcmt_profile_enable(1)
@@ -442,7 +447,7 @@ def run_ours(args):
         "config": {"workload": "2D infinite well %d^2, lowest 4 eigenpairs, shift method: 4 x V(4,4) + normalise + "
                                "Rayleigh quotient + MGS per step" % N,
                    "smoother": args.smoother, "lowest_level": lowest, "levels": h.num_levels,
-                   "parallelism": "replicas x%d" % world if world > 1 else "1 GPU", "streams": nstreams,
+                   "parallelism": "replicas x%d" % world if world > 1 else "1 GPU", "streams": nstreams, "cuda_graph": graphed,
                    "ortho": ("Gram-matrix form of the Gram-Schmidt step (12 instead of 29 vector passes); rel. difference to "
                              "column-by-column MGS on this block: %.1e" % ortho_check) if ortho_mode == 2 else "column-by-column MGS",
                    "l2": "working set %.1f GB >> 126 MB L2 (inputs larger than L2)" % (10 * n * 8 / 1e9)},
@@ -455,6 +460,38 @@ def run_ours(args):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+def make_runner(step, torch, use_graph):
+    """Returns (run(nsteps), graphed?).  With CUDA graphs, two consecutive steps (the block buffers swap roles every
+    step) are captured once and replayed: the ~100 kernel launches / NCCL calls of a step then cost no CPU time."""
+    if not use_graph:
+        return (lambda n: [step() for _ in range(n)]), False
+    try:
+        g = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            step(); step()                      # warm the capture stream (allocator, NCCL channels)
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=cap):
+            step(); step()
+        torch.cuda.synchronize()
+
+        def run(n):
+            for _ in range(n // 2):
+                g.replay()
+            if n % 2:
+                step()
+        return run, True
+    except Exception as e:      # capture not possible (e.g. an NCCL build without graph support): eager launches
+        sys.stderr.write("bench.py: CUDA graph capture failed (%s); running eagerly\n" % (str(e).splitlines()[0] if str(e) else type(e).__name__))
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        return (lambda n: [step() for _ in range(n)]), False
 
 def run_slab(args):
     """--gpus N > 1: 2-D well 16384^2, row-slab decomposed over N B200s (one rank per GPU), NCCL halo exchange
@@ -520,13 +557,17 @@ def run_slab(args):
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    launches0 = lib.mgcmt_launch_count()
     lib.mgcmt_profile_enable(0)
+    launches0 = lib.mgcmt_launch_count()
+    step(); step()
+    launches_per_step = (lib.mgcmt_launch_count() - launches0) // 2
+    run, graphed = make_runner(step, torch, not args.no_graph)
+    run(2)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.time()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    run(args.steps)
     e1.record()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     t_end = time.time()
@@ -534,7 +575,7 @@ def run_slab(args):
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    launches = lib.mgcmt_launch_count() - launches0
+    launches = launches_per_step * args.steps
     clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     lam_h = (lam[:, 0] / lam[:, 1]).cpu().tolist()
     exact = [ev1(N, a) + ev1(N, b) for a, b in MODES]
@@ -577,7 +618,7 @@ def run_slab(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "2D infinite well %d^2 slab-decomposed over %d GPUs (rows), lowest 4 eigenpairs, shift method: "
                                    "4 x V(4,4) + Rayleigh quotient + MGS per step" % (N, world),
-                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": sv.nlev, "halo_rows": HALO, "streams": nstreams,
+                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": sv.nlev, "halo_rows": HALO, "streams": nstreams, "cuda_graph": graphed,
                        "replicated_from": "%d^2" % (N >> sv.nlev), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
                        "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9)},
             "vcycles_per_s": k * args.steps / (ms * 1e-3),
