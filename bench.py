@@ -561,7 +561,9 @@ def run_slab(args):
     launches0 = lib.mgcmt_launch_count()
     step(); step()
     launches_per_step = (lib.mgcmt_launch_count() - launches0) // 2
-    run, graphed = make_runner(step, torch, not args.no_graph)
+    # eager launches on the slab path: capturing the NCCL send/recv groups of the halo exchange into a CUDA graph
+    # hung on this stack (torch 2.11 / NCCL 2.28), so the step is launched call by call here
+    run, graphed = make_runner(step, torch, False)
     run(2)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
