@@ -157,6 +157,8 @@ int mgcmt_slab_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d
  *   mode 2: as mode 1 with d_vin == 0 (d_vin is not read; the zero start of every coarse level, :316)
  *   mode 3: d_vout = J^nu(d_vin + P d_ecoarse)                         MGCMTSolver.py:323-326
  * For nu == 0, modes 1/2 leave d_vout untouched (the residual is taken of d_vin).
+ * mode | 32: the nu sweeps are four-colour (red-black on the 5-point level) Gauss-Seidel/SOR sweeps instead of Jacobi
+ *   sweeps (omega = SOR factor; 1..4 sweeps per pass on the 5-point level, 1..2 on the 9-point levels).
  * mode | 16 selects the shared-memory tile implementation (used for mid-size levels) instead of the
  * register-streaming one; both compute the same thing. */
 int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, double omega,

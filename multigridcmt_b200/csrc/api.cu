@@ -243,26 +243,40 @@ bool use_fused(const mgcmt_hier *h, int l, int smoother) {
          L.dev.ncols >= 16 && (L.dev.ncols >= g_opt_fused_min_cols || use_tile(h, l)) && L.dev.row0 == 0;
 }
 
-// down leg with the fused kernels: nu1 sweeps (in passes of <= 4) + residual + restriction into C.f.
+bool use_fused_gs(const mgcmt_hier *h, int l) {
+  const Level &L = h->lev[l];
+  return g_opt_fused && h->coarsen_rows && L.dev.nrows >= 16 && L.dev.ncols >= 64 && L.dev.row0 == 0;
+}
+
+// one fused pass of `nu` sweeps (Jacobi: streaming or tile legs; gs: colour-stage streaming legs)
+cudaError_t launch_pass(const mgcmt_hier *h, int l, bool gs, int mode, int nu, double shift, double omega,
+                        const double *vin, const double *f, double *vout, const double *e, double *rc, cudaStream_t s) {
+  if (gs) return launch_fused_gs_leg(h->lev[l].dev, mode, nu, shift, omega, vin, f, vout, e, rc, s);
+  return launch_leg(h, l, mode, nu, shift, omega, vin, f, vout, e, rc, s);
+}
+
+// down leg with the fused kernels: nu1 sweeps (in passes of <= maxpass) + residual + restriction into C.f.
 // Returns in *cur the buffer that holds the smoothed iterate (v or L.tmp).
-int fused_down(mgcmt_hier *h, int l, double shift, double omega, int nu1, double *v, const double *f,
+int fused_down(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu1, double *v, const double *f,
                bool v_zero, double **cur, cudaStream_t s) {
   Level &L = h->lev[l];
   Level &C = h->lev[l + 1];
+  const int maxpass = gs ? (L.dev.five ? 4 : 2) : 4;
   double *a = v, *b = L.tmp;
   int left = nu1;
-  while (left > 4) {
+  while (left > maxpass) {
     if (l == 0) prof_mark(s);
-    CU(launch_leg(h, l, FUSED_SMOOTH, 4, shift, omega, a, f, b, nullptr, nullptr, s));
+    if (v_zero) CU(cudaMemsetAsync(a, 0, sizeof(double) * L.n, s));  // smooth-only passes read their input
+    CU(launch_pass(h, l, gs, FUSED_SMOOTH, maxpass, shift, omega, a, f, b, nullptr, nullptr, s));
     if (l == 0) prof_mark(s);
     double *t = a; a = b; b = t;
-    left -= 4;
+    left -= maxpass;
     v_zero = false;
   }
   if (v_zero && left == 0) CU(cudaMemsetAsync(a, 0, sizeof(double) * L.n, s));
   if (l == 0) prof_mark(s);
-  CU(launch_leg(h, l, (v_zero && left > 0) ? FUSED_DOWN_ZERO : FUSED_DOWN, left, shift, omega, a, f, b, nullptr,
-                C.f, s));
+  CU(launch_pass(h, l, gs, (v_zero && left > 0) ? FUSED_DOWN_ZERO : FUSED_DOWN, left, shift, omega, a, f, b, nullptr,
+                 C.f, s));
   if (l == 0) prof_mark(s);
   if (left > 0) { double *t = a; a = b; b = t; }
   *cur = a;
@@ -270,21 +284,22 @@ int fused_down(mgcmt_hier *h, int l, double shift, double omega, int nu1, double
 }
 
 // up leg: cur (+ P e) -> nu2 sweeps; result must end in v
-int fused_up(mgcmt_hier *h, int l, double shift, double omega, int nu2, double *v, const double *f, double *cur,
+int fused_up(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu2, double *v, const double *f, double *cur,
              const double *e, cudaStream_t s) {
   Level &L = h->lev[l];
+  const int maxpass = gs ? (L.dev.five ? 4 : 2) : 4;
   double *a = cur, *b = (cur == v) ? L.tmp : v;
   int left = nu2;
-  const int first = left > 4 ? 4 : left;
+  const int first = left > maxpass ? maxpass : left;
   if (l == 0) prof_mark(s);
-  CU(launch_leg(h, l, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
+  CU(launch_pass(h, l, gs, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
   if (l == 0) prof_mark(s);
   { double *t = a; a = b; b = t; }
   left -= first;
   while (left > 0) {
-    const int nu = left > 4 ? 4 : left;
+    const int nu = left > maxpass ? maxpass : left;
     if (l == 0) prof_mark(s);
-    CU(launch_leg(h, l, FUSED_SMOOTH, nu, shift, omega, a, f, b, nullptr, nullptr, s));
+    CU(launch_pass(h, l, gs, FUSED_SMOOTH, nu, shift, omega, a, f, b, nullptr, nullptr, s));
     if (l == 0) prof_mark(s);
     double *t = a; a = b; b = t;
     left -= nu;
@@ -314,14 +329,15 @@ int vcycle_level(mgcmt_hier *h, int l, double shift, int nu1, int nu2, int smoot
     CU(launch_tail(devs, h->nlev - l, inv, shift, omega, f, v, s));
     return MGCMT_OK;
   }
-  if (use_fused(h, l, smoother)) {
+  const bool gs = (smoother == MGCMT_SMOOTH_RBGS) && use_fused_gs(h, l);
+  if (use_fused(h, l, smoother) || gs) {
     double *cur = nullptr;
-    rc = fused_down(h, l, shift, omega, nu1, v, f, v_zero, &cur, s);
+    rc = fused_down(h, l, gs, shift, omega, nu1, v, f, v_zero, &cur, s);
     if (rc) return rc;
     // coarse levels always run 4/4 (MGCMTSolver.py:320 does not forward nu1/nu2); their start is zero
     rc = vcycle_level(h, l + 1, shift, 4, 4, smoother, omega, C.v, C.f, true, s);
     if (rc) return rc;
-    return fused_up(h, l, shift, omega, nu2, v, f, cur, C.v, s);
+    return fused_up(h, l, gs, shift, omega, nu2, v, f, cur, C.v, s);
   }
   if (v_zero) CU(cudaMemsetAsync(v, 0, sizeof(double) * L.n, s));
   rc = smooth_impl(h, l, smoother, shift, omega, nu1, v, f, nullptr, s);
@@ -689,14 +705,20 @@ int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, 
   if (h->slab && (mode & 16)) return fail(MGCMT_ERR_ARG, "slab levels use the streaming legs");
   if (!h->coarsen_rows || h->lev[level].dev.nrows < 2) return fail(MGCMT_ERR_ARG, "fused legs are 2-D only");
   const bool force_tile = (mode & 16) != 0;  // bit 4: use the shared-memory tile implementation
+  const bool gs_leg = (mode & 32) != 0;      // bit 5: nu = Gauss-Seidel colour sweeps instead of Jacobi sweeps
   mode &= 15;
   if (nu < 0 || nu > 4 || mode < 0 || mode > 3) return fail(MGCMT_ERR_ARG, "bad fused leg mode / nu");
+  if (gs_leg && (force_tile || nu < 1 || nu > (h->lev[level].dev.five ? 4 : 2)))
+    return fail(MGCMT_ERR_ARG, "Gauss-Seidel legs: 1..4 sweeps per pass on the 5-point level, 1..2 on 9-point levels");
   if (d_vin == d_vout) return fail(MGCMT_ERR_ARG, "fused legs are out of place");
   NEED_ALIGNED(d_f, d_vout);
   if (mode != FUSED_DOWN_ZERO) NEED_ALIGNED(d_vin);
   if (mode == FUSED_UP) NEED_ALIGNED(d_ecoarse);
   if (mode == FUSED_DOWN || mode == FUSED_DOWN_ZERO) NEED_ALIGNED(d_rcoarse);
-  if (force_tile)
+  if (gs_leg)
+    CU(launch_fused_gs_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
+                           (cudaStream_t)stream));
+  else if (force_tile)
     CU(launch_tile_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
                        (cudaStream_t)stream));
   else

@@ -37,8 +37,9 @@ namespace {
 #define MGCMT_MIN_CTAS 2
 #endif
 constexpr int kVRing = MGCMT_VRING;  // prefetch depth of the v ring (rows, power of two)
-constexpr int kFRing = kVRing + 8;   // f ring: prefetch depth + up to NU + 2 rows of queue (not a power of
-                                     // two: slots are tracked incrementally)
+// f ring depth = prefetch depth + NSTAGE + 2 rows of queue (per instantiation; not a power of two: slots are
+// tracked incrementally)
+__host__ __device__ constexpr int f_ring_slots(int nstage) { return kVRing + nstage + 2; }
 constexpr int kERing = 4;    // coarse-row ring (PROLONG)
 constexpr int kWarps = 4;    // warps per CTA (independent strips)
 
@@ -71,7 +72,12 @@ struct Stage {
 
 }  // namespace
 
-template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C>
+// GS = 0: NU weighted-Jacobi sweeps.  GS = 1: NU colour stages of Gauss-Seidel/SOR -- two per sweep on the 5-point
+// level (red, black), four per sweep on 9-point levels ((0,0),(1,1),(0,1),(1,0): the order of gs.cu and of the CPU twin
+// oracle Solver.rbgs).  A colour stage is a Jacobi stage that only writes the points of its colour and passes the others
+// through; which points those are is known at compile time (row parity from the unrolled step, column parity from the
+// lane's even first column), so the skipped half / three quarters of the arithmetic is simply not generated.
+template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS>
 __global__ void __launch_bounds__(kWarps * 32, (C == 4 ? MGCMT_MIN_CTAS : 1))
 fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v_in,
                  const double *__restrict__ f, double *__restrict__ v_out,
@@ -80,6 +86,8 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   constexpr int WCOLS = 32 * C;
   constexpr int USEFUL = WCOLS - 2 * HALO;
   constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);  // pipeline stages after the input
+  constexpr int kFRing = f_ring_slots(NSTAGE);
+  constexpr int NCOL = FIVE ? 2 : 4;               // colours of the Gauss-Seidel ordering
   constexpr int CE = C / 2;                        // coarse columns per thread
   static_assert(C == 2 || C == 4, "C must be 2 or 4");
   static_assert(USEFUL % 2 == 0, "strip width must be even");
@@ -312,6 +320,18 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       }
       constexpr bool kIsRes = RESTRICT;  // (only the last stage, tested below with the unrolled k)
       const bool is_res = kIsRes && (k == NSTAGE - 1);
+      // Gauss-Seidel colour of this stage and the (compile-time) parity of the finalised row rho = t - k - 1
+      // (t_begin, the slab row offset and every lane's first column are even)
+      const bool gs_stage = (GS != 0) && !is_res;
+      const int colour = k % NCOL;
+      const int prho = (ODD ? 1 : 0) ^ ((k + 1) & 1);
+      auto in_colour = [&](int prow, int pcol) {
+        if (!gs_stage) return true;
+        if (FIVE) return ((prow + pcol) & 1) == colour;
+        return colour == 0 ? (prow == 0 && pcol == 0)
+             : colour == 1 ? (prow == 1 && pcol == 1)
+             : colour == 2 ? (prow == 0 && pcol == 1) : (prow == 1 && pcol == 0);
+      };
       int frho = fs - (k + 1);  // slot of row rho = t - k - 1 (slots of rows before t_begin hold garbage that
       frho += (frho < 0) ? kFRing : 0;  // only ever reaches rows outside every valid region)
       const double2 *fsrc = my_f + frho * (C / 2) * NT;
@@ -336,17 +356,23 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       double out[C];
 #pragma unroll
       for (int q = 0; q < C; ++q) {
-        const double acc = st[k].a1[q] + (FIVE ? cr_ka_up * S[q] : (cr_ma_up * T[q] + cr_ka_up * S[q]));
-        const double ff = ffv[q];
-        const double o = is_res ? (ff - acc) : (st[k].xc[q] + w[q] * (ff - acc));
-        out[q] = o;
-        // scatter the arriving row into the two rows still open
+        if (in_colour(prho, q & 1)) {
+          const double acc = st[k].a1[q] + (FIVE ? cr_ka_up * S[q] : (cr_ma_up * T[q] + cr_ka_up * S[q]));
+          const double ff = ffv[q];
+          out[q] = is_res ? (ff - acc) : (st[k].xc[q] + w[q] * (ff - acc));
+        } else {
+          out[q] = st[k].xc[q];  // not this stage's colour: passes through
+        }
+        // scatter the arriving row n = rho + 1 into the rows still open (only where they will be finalised here)
         if (FIVE) {
           // 5-point: the lower-neighbour part of row n is ka_lo[n] * x[n-1] = ka_lo[n] * xc -- no second open sum needed
-          st[k].a1[q] = cn_ka_lo * st[k].xc[q] + ((T[q] + cn_ka_di * x[q]) - shift * x[q]);
+          if (in_colour(prho ^ 1, q & 1))
+            st[k].a1[q] = cn_ka_lo * st[k].xc[q] + ((T[q] + cn_ka_di * x[q]) - shift * x[q]);
         } else {
-          st[k].a1[q] = st[k].a2[q] + ((cn_ma_di * T[q] + cn_ka_di * S[q]) - shift * x[q]);
-          st[k].a2[q] = cp_ma_lo * T[q] + cp_ka_lo * S[q];
+          if (in_colour(prho ^ 1, q & 1))
+            st[k].a1[q] = st[k].a2[q] + ((cn_ma_di * T[q] + cn_ka_di * S[q]) - shift * x[q]);
+          if (in_colour(prho, q & 1))
+            st[k].a2[q] = cp_ma_lo * T[q] + cp_ka_lo * S[q];
         }
         st[k].xc[q] = x[q];
       }
@@ -421,14 +447,14 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
 
 // ---------------------------------------------------------------------------------------------------
 template <int C>
-static size_t fused_smem_bytes(bool prolong, int rows_per_chunk) {
-  size_t b = sizeof(double) * (size_t)(kVRing + kFRing) * kWarps * 32 * C;
+static size_t fused_smem_bytes(bool prolong, int rows_per_chunk, int nstage) {
+  size_t b = sizeof(double) * (size_t)(kVRing + f_ring_slots(nstage)) * kWarps * 32 * C;
   if (prolong) b += sizeof(double) * (size_t)kERing * kWarps * 32 * (C / 2);
-  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 24);  // rows t_begin-NSTAGE-1 .. t_last+2 (<= rpc + 22)
+  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 3 * nstage + 12);  // rows t_begin-NSTAGE-1 .. t_last+2
   return b;
 }
 
-template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C>
+template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS>
 static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega, const double *v_in,
                                   const double *f, double *v_out, const double *e_coarse, double *r_coarse,
                                   cudaStream_t s) {
@@ -438,8 +464,8 @@ static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega,
   int rpc = 128;
   while (rpc > 16 && (long long)gx * ((L.nrows + rpc - 1) / rpc) < 264) rpc >>= 1;  // ~90 % of 148 SMs x 2 CTAs
   if (rpc > L.nrows) rpc = L.nrows;  // nrows is a power of two >= 2 here (even chunks)
-  const size_t smem = fused_smem_bytes<C>(PROLONG, rpc);
-  auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C>;
+  const size_t smem = fused_smem_bytes<C>(PROLONG, rpc, NU + (RESTRICT ? 1 : 0));
+  auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C, GS>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -452,20 +478,41 @@ static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega,
   return cudaGetLastError();
 }
 
-template <bool FIVE, int NU, int C>
+template <bool FIVE, int NU, int C, int GS = 0>
 static cudaError_t dispatch_mode(const LevelDev &L, int mode, double shift, double omega, const double *v_in,
                                  const double *f, double *v_out, const double *e_coarse, double *r_coarse,
                                  cudaStream_t s) {
   switch (mode) {
     case FUSED_SMOOTH:
       if (NU == 0) return cudaErrorInvalidValue;
-      return launch_fused_t<FIVE, NU, false, false, false, C>(L, shift, omega, v_in, f, v_out, nullptr, nullptr, s);
+      return launch_fused_t<FIVE, NU, false, false, false, C, GS>(L, shift, omega, v_in, f, v_out, nullptr, nullptr, s);
     case FUSED_DOWN:
-      return launch_fused_t<FIVE, NU, false, true, false, C>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s);
+      return launch_fused_t<FIVE, NU, false, true, false, C, GS>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s);
     case FUSED_DOWN_ZERO:
-      return launch_fused_t<FIVE, NU, false, true, true, C>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s);
+      return launch_fused_t<FIVE, NU, false, true, true, C, GS>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s);
     case FUSED_UP:
-      return launch_fused_t<FIVE, NU, true, false, false, C>(L, shift, omega, v_in, f, v_out, e_coarse, nullptr, s);
+      return launch_fused_t<FIVE, NU, true, false, false, C, GS>(L, shift, omega, v_in, f, v_out, e_coarse, nullptr, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Gauss-Seidel legs: `sweeps` full colour sweeps (1..4 on the 5-point level, 1..2 on 9-point levels) per pass
+cudaError_t launch_fused_gs_leg(const LevelDev &L, int mode, int sweeps, double shift, double omega,
+                                const double *v_in, const double *f, double *v_out, const double *e_coarse,
+                                double *r_coarse, cudaStream_t s) {
+  if (L.nrows < 2) return cudaErrorInvalidValue;
+  if (L.five) {
+    switch (sweeps) {
+      case 1: return dispatch_mode<true, 2, 2, 1>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+      case 2: return dispatch_mode<true, 4, 2, 1>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+      case 3: return dispatch_mode<true, 6, 2, 1>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+      case 4: return dispatch_mode<true, 8, 2, 1>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+    }
+    return cudaErrorInvalidValue;
+  }
+  switch (sweeps) {
+    case 1: return dispatch_mode<false, 4, 2, 1>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+    case 2: return dispatch_mode<false, 8, 2, 1>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
   }
   return cudaErrorInvalidValue;
 }

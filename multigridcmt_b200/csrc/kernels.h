@@ -62,6 +62,10 @@ size_t tail_smem_bytes(const LevelDev *levels, int nlev);
 cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, double shift, double omega,
                         const double *f_first, double *v_first, cudaStream_t s);
 
+cudaError_t launch_fused_gs_leg(const LevelDev &L, int mode, int sweeps, double shift, double omega,
+                                const double *v_in, const double *f, double *v_out, const double *e_coarse,
+                                double *r_coarse, cudaStream_t s);
+
 // gs.cu
 cudaError_t launch_rbgs(const LevelDev &L, double shift, double omega, int nu, double *v, const double *f,
                         cudaStream_t s);

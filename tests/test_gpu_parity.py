@@ -191,6 +191,68 @@ def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift, impl):
             assert rel(out.cpu().numpy(), want_u) < RTOL, ("up", l, nu)
 
 
+@pytest.mark.parametrize("N,shift", [(128, 4.38639582), (512, 0.0)])
+def test_fused_gauss_seidel_legs_match_colour_kernels(T, prod, o, N, shift):
+    """colour-stage legs (mode | 32) == the one-kernel-per-colour smoother + the un-fused transfers, and the CPU twin"""
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    from multigridcmt_b200.operators import recognise
+    sm = prod[0]
+    osolver = o[1]
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    h = get_hierarchy(recognise(H, "2d"), 8)
+    mats, Rs, Ps = oracle_levels(o, H, N, "2d", 3)
+    for l in range(2):
+        n, nc = h.level_size(l), h.level_size(l + 1)
+        A = mats[l] - sp.eye(n) * shift
+        v = rand(n, 70 + l); f = rand(n, 80 + l); e = rand(nc, 90 + l)
+        dv, df, de = dev(T, v), dev(T, f), dev(T, e)
+        for om in (1.0, 1.3):
+            for nu in ((1, 2, 4) if l == 0 else (1, 2)):
+                want = dv.clone()
+                h.smooth(l, _lib.SMOOTH_RBGS, shift, om, nu, want, df)
+                wv = want.cpu().numpy()
+                if om == 1.0 and nu <= 2:
+                    assert rel(wv, osolver.rbgs(v.copy(), f.copy(), A, nu=nu, omega=1.0, dimension="2d")) < 1e-11
+                out = T.full_like(dv, 7.0); rc = T.full((nc,), 7.0, dtype=T.float64, device="cuda")
+                h.fused_leg(l, 32 | 0, nu, shift, om, dv, df, out)
+                assert rel(out.cpu().numpy(), wv) < RTOL, ("gs smooth", l, nu, om)
+                out.fill_(7.0)
+                h.fused_leg(l, 32 | 1, nu, shift, om, dv, df, out, None, rc)
+                assert rel(out.cpu().numpy(), wv) < RTOL, ("gs down v", l, nu, om)
+                assert rel(rc.cpu().numpy(), Rs[l] @ (f - A @ wv)) < 1e-11, ("gs down r", l, nu, om)
+                z = T.zeros_like(dv)
+                h.smooth(l, _lib.SMOOTH_RBGS, shift, om, nu, z, df)
+                out.fill_(7.0); rc.fill_(7.0)
+                h.fused_leg(l, 32 | 2, nu, shift, om, None, df, out, None, rc)
+                assert rel(out.cpu().numpy(), z.cpu().numpy()) < RTOL, ("gs down0", l, nu, om)
+                vc = dv.clone()
+                h.prolong_correct(l, de, vc)
+                h.smooth(l, _lib.SMOOTH_RBGS, shift, om, nu, vc, df)
+                out.fill_(7.0)
+                h.fused_leg(l, 32 | 3, nu, shift, om, dv, df, out, de, None)
+                assert rel(out.cpu().numpy(), vc.cpu().numpy()) < RTOL, ("gs up", l, nu, om)
+
+
+def test_rbgs_vcycle_fused_equals_unfused(T, prod):
+    from multigridcmt_b200 import _lib
+    sm, s, _ = prod
+    lib = _lib.load()
+    N = 512
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    v0 = rand(N * N, 1); f = rand(N * N, 2)
+    try:
+        outs = []
+        for fused in (1, 0):
+            lib.mgcmt_set_option(b"fused", fused)
+            outs.append((s.vcycle(v0.copy(), f.copy(), H, sm, nu1=3, nu2=5, shift=4.386, lowest_level=8, dimension="2d", smoother=s.rbgs),
+                         s.vcycle(np.zeros(N * N), f.copy(), H, sm, shift=1.7, lowest_level=8, dimension="2d", smoother=s.rbgs)))
+    finally:
+        lib.mgcmt_set_option(b"fused", 1)
+    for a, b in zip(outs[0], outs[1]):
+        assert rel(a, b) < 1e-11
+
+
 def test_all_vcycle_paths_agree(T, prod):
     """streaming legs / tile legs / single-CTA tail / one-kernel-per-operator: same V-cycle."""
     from multigridcmt_b200 import _lib
