@@ -418,9 +418,9 @@ def run_ours(args):
             kname = "fused_leg_kernel<FIVE,NU=4> (finest-level leg: 4 sweeps + transfer fused)"
             actual = 26.0 * n
         else:
-            dom_bytes = 24.0 * n * 4  # one bracket = 4 four-colour sweeps
-            kname = "rbgs_colour_kernel x16 (finest-level, 4 sweeps)"
-            actual = None
+            dom_bytes = 114.0 * n
+            kname = "fused_leg_kernel<FIVE,GS,NU=8> (finest-level leg: 4 red-black sweeps = 8 colour stages + transfer fused)"
+            actual = 26.0 * n
         achieved = dom_bytes / (per_launch_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": TRAFFIC_NCU.get(args.smoother if N == 4096 else ""), "kernel": kname,

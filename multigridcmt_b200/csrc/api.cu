@@ -225,12 +225,17 @@ cudaError_t launch_leg(const mgcmt_hier *h, int l, int mode, int nu, double shif
 
 // can levels l .. coarsest run inside the single-CTA tail kernel?
 bool use_tail(const mgcmt_hier *h, int l, int smoother, int nu1, int nu2, bool v_zero) {
-  if (!g_opt_fused || smoother != MGCMT_SMOOTH_WJACOBI || !h->coarsen_rows || !v_zero) return false;
+  if (!g_opt_fused || smoother != MGCMT_SMOOTH_WJACOBI || !v_zero || g_opt_tail_max_cols <= 0) return false;
   if (nu1 != 4 || nu2 != 4) return false;
   const int nl = h->nlev - l;
   if (nl < 2 || nl > kTailMaxLevels) return false;
   const Level &L = h->lev[l];
-  if (L.dev.ncols > g_opt_tail_max_cols || L.dev.nrows != L.dev.ncols || L.dev.row0 != 0) return false;
+  if (h->slab || L.dev.row0 != 0) return false;
+  if (h->coarsen_rows) {
+    if (L.dev.ncols > g_opt_tail_max_cols || L.dev.nrows != L.dev.ncols) return false;
+  } else {
+    if (L.dev.nrows != 1 || L.dev.ncols > 1024) return false;  // 1-D: the whole cycle of a <= 1024-point grid fits one CTA
+  }
   if (h->lev[h->nlev - 1].n > 256) return false;  // the dense inverse is read by one CTA
   LevelDev devs[kTailMaxLevels];
   for (int k = l; k < h->nlev; ++k) devs[k - l] = h->lev[k].dev;
@@ -326,7 +331,7 @@ int vcycle_level(mgcmt_hier *h, int l, double shift, int nu1, int nu2, int smoot
     if (rc) return rc;
     LevelDev devs[kTailMaxLevels];
     for (int k = l; k < h->nlev; ++k) devs[k - l] = h->lev[k].dev;
-    CU(launch_tail(devs, h->nlev - l, inv, shift, omega, f, v, s));
+    CU(launch_tail(devs, h->nlev - l, h->coarsen_rows, inv, shift, omega, f, v, s));
     return MGCMT_OK;
   }
   const bool gs = (smoother == MGCMT_SMOOTH_RBGS) && use_fused_gs(h, l);

@@ -56,11 +56,11 @@ cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, 
 cudaError_t launch_tile_leg(const LevelDev &L, int mode, int nu, double shift, double omega, const double *v_in,
                             const double *f, double *v_out, const double *e_coarse, double *r_coarse,
                             cudaStream_t s);
-constexpr int kTailMaxLevels = 8;
+constexpr int kTailMaxLevels = 12;
 constexpr size_t kTailMaxSmem = 216 * 1024;
 size_t tail_smem_bytes(const LevelDev *levels, int nlev);
-cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, double shift, double omega,
-                        const double *f_first, double *v_first, cudaStream_t s);
+cudaError_t launch_tail(const LevelDev *levels, int nlev, bool coarsen_rows, const double *inv, double shift,
+                        double omega, const double *f_first, double *v_first, cudaStream_t s);
 
 cudaError_t launch_fused_gs_leg(const LevelDev &L, int mode, int sweeps, double shift, double omega,
                                 const double *v_in, const double *f, double *v_out, const double *e_coarse,

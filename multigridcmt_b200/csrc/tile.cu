@@ -232,6 +232,7 @@ struct TailArgs {
   int arena_doubles;
   const double *inv;        // dense inverse of the coarsest shifted operator (n_c x n_c, row-major)
   double shift, omega;
+  int coarsen_rows;         // 0: 1-D hierarchy (single-row levels, transfers act along the row only)
 };
 
 namespace {
@@ -339,15 +340,20 @@ __global__ void __launch_bounds__(1024) tail_kernel(TailArgs a, const double *__
     }
     tail_pass<true>(nr, nc, lgc, c, a.shift, V, F, W, T);
     __syncthreads();
-    const int nrc = nr >> 1, ncc = nc >> 1, lgcc = lgc - 1;
+    const int nrc = a.coarsen_rows ? nr >> 1 : nr, ncc = nc >> 1, lgcc = lgc - 1;
     double *Fc = arena + a.lev[l + 1].foff;
     for (int idx = tid; idx < nrc * ncc; idx += nt) {
       const int I = idx >> lgcc, J = idx & (ncc - 1);
-      const double *p = T + (2 * I + 1) * P + (2 * J + 1);  // haloed: fine (2I, 2J); row/col n are the zero halo
-      const double a0 = 0.25 * p[0] + 0.5 * p[1] + 0.25 * p[2];
-      const double a1 = 0.25 * p[P] + 0.5 * p[P + 1] + 0.25 * p[P + 2];
-      const double a2 = 0.25 * p[2 * P] + 0.5 * p[2 * P + 1] + 0.25 * p[2 * P + 2];
-      Fc[idx] = 0.25 * a0 + 0.5 * a1 + 0.25 * a2;
+      if (a.coarsen_rows) {
+        const double *p = T + (2 * I + 1) * P + (2 * J + 1);  // haloed: fine (2I, 2J); row/col n are the zero halo
+        const double a0 = 0.25 * p[0] + 0.5 * p[1] + 0.25 * p[2];
+        const double a1 = 0.25 * p[P] + 0.5 * p[P + 1] + 0.25 * p[P + 2];
+        const double a2 = 0.25 * p[2 * P] + 0.5 * p[2 * P + 1] + 0.25 * p[2 * P + 2];
+        Fc[idx] = 0.25 * a0 + 0.5 * a1 + 0.25 * a2;
+      } else {
+        const double *p = T + (I + 1) * P + (2 * J + 1);      // 1-D: full weighting along the row only
+        Fc[idx] = 0.25 * p[0] + 0.5 * p[1] + 0.25 * p[2];
+      }
     }
     __syncthreads();
   }
@@ -377,10 +383,12 @@ __global__ void __launch_bounds__(1024) tail_kernel(TailArgs a, const double *__
     const double *E = arena + a.lev[l + 1].voff;
     for (int idx = tid; idx < nr * nc; idx += nt) {
       const int i = idx >> lgc, j = idx & (nc - 1);
-      const int I = i >> 1, J = j >> 1;
+      const int I = a.coarsen_rows ? i >> 1 : i, J = j >> 1;
       const double *e = E + (I + 1) * Pc + (J + 1);  // e[-1], e[-Pc]: coarse neighbours (zero halo at the edges)
       double pe;
-      if (i & 1) {
+      if (!a.coarsen_rows) {
+        pe = (j & 1) ? e[0] : 0.5 * (e[-1] + e[0]);   // 1-D: interpolation along the row only
+      } else if (i & 1) {
         pe = (j & 1) ? e[0] : 0.5 * (e[-1] + e[0]);
       } else {
         const double top = (j & 1) ? e[-Pc] : 0.5 * (e[-Pc - 1] + e[-Pc]);
@@ -424,11 +432,12 @@ static size_t tail_layout(const LevelDev *levels, int nlev, TailArgs *a) {
 
 size_t tail_smem_bytes(const LevelDev *levels, int nlev) { return tail_layout(levels, nlev, nullptr); }
 
-cudaError_t launch_tail(const LevelDev *levels, int nlev, const double *inv, double shift, double omega,
-                        const double *f_first, double *v_first, cudaStream_t s) {
+cudaError_t launch_tail(const LevelDev *levels, int nlev, bool coarsen_rows, const double *inv, double shift,
+                        double omega, const double *f_first, double *v_first, cudaStream_t s) {
   if (nlev < 2 || nlev > kTailMaxLevels) return cudaErrorInvalidValue;
   TailArgs a;
   a.nlev = nlev;
+  a.coarsen_rows = coarsen_rows ? 1 : 0;
   a.inv = inv;
   a.shift = shift;
   a.omega = omega;
