@@ -531,18 +531,19 @@ def run_slab(args):
         st.owned(V[c][0], 0).copy_(torch.from_numpy(blk).cuda())
     lam = torch.zeros(k, 2, dtype=torch.float64, device="cuda")
 
+    from multigridcmt_b200.slab import vcycle_block
+    lockstep = (nstreams == k)
+
     def step():
-        main = torch.cuda.current_stream()
-        for s_ in streams:
-            s_.wait_stream(main)
-        for c in range(k):
-            svc = svs[c % nstreams]
-            with torch.cuda.stream(streams[c % nstreams]):
+        if lockstep:
+            # the k cycles advance level by level together: every halo-exchange phase is one NCCL group for all k
+            vcycle_block(svs, shifts, V, W, lam=[lam])
+        else:
+            for c in range(k):
+                svc = svs[c % nstreams]
                 svc.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
                 svc.rayleigh(W[c], sync=False)
                 lam[c].copy_(svc.states[0].scal[:2])
-        for s_ in streams:
-            main.wait_stream(s_)
         if args.ortho == "gram":
             sv.gramschmidt_gram([bd["W"]])
         else:
@@ -620,7 +621,7 @@ def run_slab(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "2D infinite well %d^2 slab-decomposed over %d GPUs (rows), lowest 4 eigenpairs, shift method: "
                                    "4 x V(4,4) + Rayleigh quotient + MGS per step" % (N, world),
-                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": sv.nlev, "halo_rows": HALO, "streams": nstreams, "cuda_graph": graphed,
+                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": sv.nlev, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
                        "replicated_from": "%d^2" % (N >> sv.nlev), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
                        "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9)},
             "vcycles_per_s": k * args.steps / (ms * 1e-3),

@@ -654,3 +654,37 @@ def test_slab_block_step_matches_single_gpu(T, prod):
     assert rel(got, want) < 1e-11
     assert np.max(np.abs(got2.T @ got2 - np.eye(k))) < 1e-12     # (random block: compare the invariants, not the bits)
     assert rel(got2 @ (got2.T @ want), want) < 1e-10
+
+
+def test_slab_lockstep_block_equals_separate_cycles(T, prod):
+    """vcycle_block (k cycles in lock-step, batched halo exchanges) == k separate slab cycles, bit for bit"""
+    from multigridcmt_b200.slab import LocalComm, SlabVCycle, vcycle_block
+    sm, s, _ = prod
+    N, world, k = 512, 4, 3
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    shifts = [1.76659015, 4.38639582, 7.00620149]
+    Vh = rand(N * N * k, 18).reshape(N * N, k)
+    comm = LocalComm(world)
+    svs = [SlabVCycle(H, world, comm, range(world), lowest_level=8, gather_cols=128) for _ in range(k)]
+    try:
+        V = [svs[0].new_vector() for _ in range(k)]
+        W1 = [svs[0].new_vector() for _ in range(k)]
+        W2 = [svs[0].new_vector() for _ in range(k)]
+        for c in range(k):
+            a = Vh[:, c].reshape(N, N)
+            for i, st in enumerate(svs[0].states):
+                st.owned(V[c][i], 0).copy_(T.from_numpy(np.ascontiguousarray(a[st.begin0:st.begin0 + st.own0])).cuda())
+        lam = [T.zeros(k, 2, dtype=T.float64, device="cuda") for _ in range(world)]
+        vcycle_block(svs, shifts, V, W1, lam=lam)
+        ref = []
+        for c in range(k):
+            svs[0].vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W2[c])
+            ref.append(svs[0].rayleigh(W2[c])[0])
+        for c in range(k):
+            for i, st in enumerate(svs[0].states):
+                assert T.equal(st.owned(W1[c][i], 0), st.owned(W2[c][i], 0))
+        got = (lam[0][:, 0] / lam[0][:, 1]).cpu().numpy()
+        assert np.allclose(got, ref, rtol=1e-13, atol=0)
+    finally:
+        for sv in svs:
+            sv.close()
