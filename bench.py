@@ -57,7 +57,7 @@ def parse():
                     help="block orthonormalisation: column-by-column MGS (MGCMTProcessor.py:44-50) or its Gram-matrix form")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--replicas", action="store_true", help="multi-GPU: independent replicas instead of row slabs")
-    ap.add_argument("--gather-cols", type=int, default=2048, help="slab path: levels at most this wide are replicated")
+    ap.add_argument("--gather-cols", type=int, default=512, help="slab path: levels at most this wide are replicated")
     return ap.parse_args()
 
 
@@ -537,7 +537,7 @@ def run_slab(args):
     def step():
         if lockstep:
             # the k cycles advance level by level together: every halo-exchange phase is one NCCL group for all k
-            vcycle_block(svs, shifts, V, W, lam=[lam])
+            vcycle_block(svs, shifts, V, W, lam=[lam], streams=streams)
         else:
             for c in range(k):
                 svc = svs[c % nstreams]

@@ -366,15 +366,37 @@ class SlabVCycle:
 # ----------------------------------------------------------------------------------------------------
 # block of independent cycles in lock-step: one NCCL group per phase for ALL vectors
 # ----------------------------------------------------------------------------------------------------
-def vcycle_block(svs, shifts, f0s, v0s, lam=None):
+def vcycle_block(svs, shifts, f0s, v0s, lam=None, streams=None):
     """k independent V(4,4) cycles (zero initial guess), one SlabVCycle (= one set of level buffers) per vector, advanced
     level by level together so that every halo-exchange phase is ONE batched NCCL send/recv group for all k vectors
     (the exchanges are latency-bound: 6 rows each).  svs[c] solves (H - shifts[c]) w = f0s[c] into v0s[c]
     (f0s[c] / v0s[c]: per-local-rank finest-level slab arrays).  If `lam` (k x 2 device tensor per local rank, list) is
-    given, the Rayleigh numerators / denominators w^T H w, w^T w of the results are left in it (all-reduced)."""
+    given, the Rayleigh numerators / denominators w^T H w, w^T w of the results are left in it (all-reduced).
+    streams: optional list of k CUDA streams -- within a phase vector c's kernels run on streams[c] (forked from /
+    joined to the current stream around every phase), so the latency-bound legs of the small slab levels and the
+    replicated coarse parts of different vectors overlap; the exchanges stay on the current stream."""
     torch = _lib.require_cuda()
     lib = _lib.load()
     k = len(svs)
+    main = torch.cuda.current_stream()
+
+    class _On:   # run vector c's launches on its stream, ordered after everything already on the main stream
+        def __init__(self, c):
+            self.c = c
+        def __enter__(self):
+            if streams is not None:
+                streams[self.c].wait_stream(main)
+                self.ctx = torch.cuda.stream(streams[self.c])
+                self.ctx.__enter__()
+        def __exit__(self, *a):
+            if streams is not None:
+                self.ctx.__exit__(*a)
+
+    def join():
+        if streams is not None:
+            for st_ in streams:
+                main.wait_stream(st_)
+
     sv0 = svs[0]
     comm, nl, st0 = sv0.comm, sv0.nlev, sv0.states[0]
     saved = []
@@ -389,34 +411,43 @@ def vcycle_block(svs, shifts, f0s, v0s, lam=None):
         comm.exchange_many(items("f", 0))
         for l in range(nl):
             last = (l + 1 == nl)
-            for sv in svs:
-                for st in sv.states:
-                    sv._leg(st, l, MODE_DOWN_ZERO, None, st.f[l], st.tmp[l], rc=(st.fg if last else st.f[l + 1]))
+            for c, sv in enumerate(svs):
+                with _On(c):
+                    for st in sv.states:
+                        sv._leg(st, l, MODE_DOWN_ZERO, None, st.f[l], st.tmp[l], rc=(st.fg if last else st.f[l + 1]))
+            join()
             if last:
                 for sv in svs:
                     comm.allgather_rows([st.fg for st in sv.states], st0.own_rows(nl), st0.ncols(nl))
             else:
                 comm.exchange_many(items("f", l + 1))
-        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for sv in svs:
-            for st in sv.states:
-                _lib.check(lib.mgcmt_vcycle_from(st.coarse, nl, float(sv.shift), _lib.SMOOTH_WJACOBI, float(sv.omega),
-                                                 C.c_void_p(st.vg.data_ptr()), C.c_void_p(st.fg.data_ptr()), stream))
+        for c, sv in enumerate(svs):
+            with _On(c):
+                stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                for st in sv.states:
+                    _lib.check(lib.mgcmt_vcycle_from(st.coarse, nl, float(sv.shift), _lib.SMOOTH_WJACOBI, float(sv.omega),
+                                                     C.c_void_p(st.vg.data_ptr()), C.c_void_p(st.fg.data_ptr()), stream))
+        join()
         for l in range(nl - 1, -1, -1):
             last = (l + 1 == nl)
             it = items("tmp", l)
             if not last:
                 it += items("v", l + 1)
             comm.exchange_many(it)
-            for sv in svs:
-                for st in sv.states:
-                    sv._leg(st, l, MODE_UP, st.tmp[l], st.f[l], st.v[l], e=(st.vg if last else st.v[l + 1]))
+            for c, sv in enumerate(svs):
+                with _On(c):
+                    for st in sv.states:
+                        sv._leg(st, l, MODE_UP, st.tmp[l], st.f[l], st.v[l], e=(st.vg if last else st.v[l + 1]))
+            join()
         if lam is not None:
             comm.exchange_many(items("v", 0))
             for c, sv in enumerate(svs):
-                for i, st in enumerate(sv.states):
-                    _lib.check(lib.mgcmt_slab_rayleigh(st.slab, 0, C.c_void_p(st.v[0].data_ptr()),
-                                                       C.c_void_p(lam[i][c].data_ptr()), stream))
+                with _On(c):
+                    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                    for i, st in enumerate(sv.states):
+                        _lib.check(lib.mgcmt_slab_rayleigh(st.slab, 0, C.c_void_p(st.v[0].data_ptr()),
+                                                           C.c_void_p(lam[i][c].data_ptr()), stream))
+            join()
             comm.allreduce_sum(lam)
     finally:
         for sv, sav in zip(svs, saved):

@@ -675,7 +675,7 @@ def test_slab_lockstep_block_equals_separate_cycles(T, prod):
             for i, st in enumerate(svs[0].states):
                 st.owned(V[c][i], 0).copy_(T.from_numpy(np.ascontiguousarray(a[st.begin0:st.begin0 + st.own0])).cuda())
         lam = [T.zeros(k, 2, dtype=T.float64, device="cuda") for _ in range(world)]
-        vcycle_block(svs, shifts, V, W1, lam=lam)
+        vcycle_block(svs, shifts, V, W1, lam=lam, streams=[T.cuda.Stream() for _ in range(k)])
         ref = []
         for c in range(k):
             svs[0].vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W2[c])
