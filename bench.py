@@ -282,6 +282,7 @@ def run_ours(args):
     ortho_mode = 2 if args.ortho == "gram" else 1
 
     def step(serial=False):
+        nonlocal smoother_code, omega
         V, W = blocks[cur[0]], blocks[1 - cur[0]]
         main = torch.cuda.current_stream()
         if not serial:
@@ -352,12 +353,32 @@ def run_ours(args):
     dom_ms, dom_cnt = C.c_double(), C.c_longlong()
     lib.mgcmt_profile_read(C.byref(dom_ms), C.byref(dom_cnt))
     lib.mgcmt_profile_enable(0)
+    lam = (rq[:, 0] / rq[:, 1]).cpu().tolist()   # eigenvalue estimates of the measured (Jacobi) run
+    # the other smoother of the path, same step (BASELINE config 3 names red-black Gauss-Seidel): a short side run
+    other = None
+    if world == 1 and args.smoother == "wjacobi":
+        keep = (smoother_code, omega)
+        smoother_code, omega = _lib.SMOOTH_RBGS, 1.0
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        eo0, eo1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eo0.record()
+        for _ in range(20):
+            step()
+        eo1.record()
+        torch.cuda.synchronize()
+        ms_o = eo0.elapsed_time(eo1) / 20
+        lam_o = (rq[:, 0] / rq[:, 1]).cpu().tolist()
+        other = {"smoother": "rbgs (four-colour = red-black on the 5-point level, omega = 1)", "ms_per_step": ms_o,
+                 "vcycles_per_s": k / (ms_o * 1e-3), "value": k * updates_per_cycle(N, lowest) / (ms_o * 1e-3),
+                 "eigenvalues": lam_o}
+        smoother_code, omega = keep
     clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    lam = (rq[:, 0] / rq[:, 1]).cpu().tolist()
     exact = [ev1(N, a) + ev1(N, b) for a, b in MODES]
 
     ups_step = k * updates_per_cycle(N, lowest)
@@ -454,7 +475,7 @@ def run_ours(args):
         "vcycles_per_s": world * k * args.steps / (ms * 1e-3),
         "eigenvalues": lam, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam, exact)],
         "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
+        "cpu_baseline": cpu_baseline, "other_smoother": other,
     }
     print(json.dumps(line))
     if world > 1:

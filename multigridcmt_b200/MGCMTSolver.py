@@ -230,11 +230,26 @@ class MGCMTSolver:
         F = block(f_matrix)
         lib = _lib.load()
 
-        def cycle(level, V, F, n1, n2):
+        def cycle(level, V, F, n1, n2, zero_start=False):
             nl = h.level_size(level)
             if level == h.num_levels - 1:
                 for i in range(k):
                     h.coarse_solve(shifts[i], F[i], V[i])
+                return V
+            nr_, nc_ = h.level_shape(level)
+            if code == _lib.SMOOTH_WJACOBI and nr_ >= 32 and nc_ >= 32 and 0 < n1 <= 4 and 0 < n2 <= 4:
+                # one fused pass per leg and column (csrc/fused.cu): sweeps + residual/restriction, then
+                # interpolation/correction + sweeps; Gram-Schmidt of the block on the way up (MGCMTSolver.py:434)
+                ncs = h.level_size(level + 1)
+                Tm = torch.empty_like(V)
+                Rc = torch.empty(k, ncs, dtype=torch.float64, device="cuda")
+                for i in range(k):
+                    h.fused_leg(level, 2 if zero_start else 1, n1, shifts[i], omega, None if zero_start else V[i], F[i],
+                                Tm[i], None, Rc[i])
+                E = cycle(level + 1, torch.zeros(k, ncs, dtype=torch.float64, device="cuda"), Rc, 4, 4, True)
+                for i in range(k):
+                    h.fused_leg(level, 3, n2, shifts[i], omega, Tm[i], F[i], V[i], E[i], None)
+                _lib.check(lib.mgcmt_gramschmidt(nl, k, _ptr(V), 1, _stream_ptr(torch)))
                 return V
             for i in range(k):
                 h.smooth(level, code, shifts[i], omega, n1, V[i], F[i])
@@ -242,7 +257,7 @@ class MGCMTSolver:
             Rc = torch.empty(k, nc, dtype=torch.float64, device="cuda")
             for i in range(k):
                 h.residual_restrict(level, shifts[i], V[i], F[i], Rc[i])
-            E = cycle(level + 1, torch.zeros(k, nc, dtype=torch.float64, device="cuda"), Rc, 4, 4)
+            E = cycle(level + 1, torch.zeros(k, nc, dtype=torch.float64, device="cuda"), Rc, 4, 4, True)
             for i in range(k):
                 h.prolong_correct(level, E[i], V[i])
                 h.smooth(level, code, shifts[i], omega, n2, V[i], F[i])

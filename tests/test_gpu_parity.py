@@ -422,6 +422,20 @@ def test_vcycle_matrix_matches_reference_golden(prod, golden, tag):
     assert rel(out, golden["vm_%s_out" % tag]) < 1e-9
 
 
+def test_vcycle_matrix_fused_matches_oracle(prod, o):
+    """block cycle at a size where the fused legs are used (MGCMTSolver.py:375-436 semantics, per-column shifts)"""
+    sm, s, _ = prod
+    osm, os_, _ = o
+    N, k = 128, 3
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    shifts = np.array([1.76659015, 4.38639582, 7.00620149])
+    V0 = rand(N * N * k, 27).reshape(N * N, k); F = rand(N * N * k, 28).reshape(N * N, k)
+    got = s.vcycle_matrix(V0.copy(), F.copy(), H, sm, shifts=shifts, lowest_level=8, dimension="2d")
+    want = os_.vcycle_matrix(V0.copy(), F.copy(), (-1. / np.pi ** 2) * osm.laplacian(N, "2d"), osm, shifts=shifts,
+                             lowest_level=8, dimension="2d")
+    assert got.shape == want.shape and rel(got, want) < 1e-9
+
+
 # ---------------------------------------------------------------------------------------------------
 # Gram-Schmidt / normalise / dots
 # ---------------------------------------------------------------------------------------------------
