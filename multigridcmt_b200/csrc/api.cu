@@ -694,6 +694,11 @@ int mgcmt_set_option(const char *name, int value) {
   if (!strcmp(name, "fused_min_cols")) { g_opt_fused_min_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tile_max_cols")) { g_opt_tile_max_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tail_max_cols")) { g_opt_tail_max_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "fused_c9")) {
+    if (value != 0 && value != 2 && value != 4) return fail(MGCMT_ERR_ARG, "fused_c9 must be 0 (auto), 2 or 4");
+    mgcmt::g_fused_c9 = value;
+    return MGCMT_OK;
+  }
   if (!strcmp(name, "fused_c5")) {
     if (value != 2 && value != 4) return fail(MGCMT_ERR_ARG, "fused_c5 must be 2 or 4");
     mgcmt::g_fused_c5 = value;

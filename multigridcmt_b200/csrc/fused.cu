@@ -517,7 +517,9 @@ cudaError_t launch_fused_gs_leg(const LevelDev &L, int mode, int sweeps, double 
   return cudaErrorInvalidValue;
 }
 
-int g_fused_c5 = MGCMT_FUSED_C5;  // columns per lane on the 5-point level (2 or 4), switchable for A/B timing
+int g_fused_c5 = MGCMT_FUSED_C5;
+int g_fused_c9 = 0;  // columns per lane on 9-point levels: 2, 4, or 0 = 4 on levels >= 4096 wide (enough strips to
+                     // fill the GPU; measured 8 % faster per cycle at 16384^2, no gain at 4096^2), else 2  // columns per lane on the 5-point level (2 or 4), switchable for A/B timing
 
 cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,
@@ -527,8 +529,10 @@ cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, 
   case NUV:                                                                                                  \
     if (L.five && g_fused_c5 == 4)                                                                           \
       return dispatch_mode<true, NUV, 4>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);      \
+    if (!L.five && (g_fused_c9 == 4 || (g_fused_c9 == 0 && L.ncols >= 4096)))                                \
+      return dispatch_mode<false, NUV, 4>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);     \
     return L.five ? dispatch_mode<true, NUV, 2>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s) \
-                  : dispatch_mode<false, NUV, MGCMT_FUSED_C9>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+                  : dispatch_mode<false, NUV, 2>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
   switch (nu) {
     NU_CASE(0) NU_CASE(1) NU_CASE(2) NU_CASE(3) NU_CASE(4)
   }

@@ -46,7 +46,7 @@ enum { FUSED_SMOOTH = 0,     // v_out = J^nu(v_in)
 #ifndef MGCMT_FUSED_C9
 #define MGCMT_FUSED_C9 2     // columns per lane, 9-point (Galerkin) levels
 #endif
-extern int g_fused_c5;
+extern int g_fused_c5, g_fused_c9;
 cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,
                              double *r_coarse, cudaStream_t s);

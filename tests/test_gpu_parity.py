@@ -261,7 +261,8 @@ def test_all_vcycle_paths_agree(T, prod):
     N = 512
     H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
     v0 = rand(N * N, 1); f = rand(N * N, 2)
-    configs = [dict(fused=0), dict(fused=1, tile_max_cols=0, tail_max_cols=0), dict(fused=1, tile_max_cols=1024, tail_max_cols=0),
+    configs = [dict(fused=0), dict(fused=1, tile_max_cols=0, tail_max_cols=0), dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_c9=4),
+               dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_c9=2, fused_c5=2), dict(fused=1, tile_max_cols=1024, tail_max_cols=0, fused_c5=4),
                dict(fused=1, tile_max_cols=1024, tail_max_cols=64), dict(fused=1, tile_max_cols=0, tail_max_cols=32)]
     try:
         outs = []
@@ -273,7 +274,7 @@ def test_all_vcycle_paths_agree(T, prod):
                          s.vcycle(np.zeros(64 * 64), f[:4096].copy(), (-1. / np.pi ** 2) * sm.laplacian(64, "2d"), sm,
                                   shift=1.7, lowest_level=4, dimension="2d")))
     finally:
-        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=32).items():
+        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=32, fused_c9=0, fused_c5=4).items():
             lib.mgcmt_set_option(k.encode(), v)
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
