@@ -1,0 +1,18 @@
+"""CPU: the matrix-free C/OpenMP oracle (oracle/mgcmt_oracle.c, the timed CPU baseline) against the numpy oracle."""
+import numpy as np
+import pytest
+
+import c_oracle
+import mgcmt_oracle as orc
+
+
+@pytest.mark.parametrize("N,low,shift,nu", [(32, 8, 0.0, (4, 4)), (64, 8, 4.38639582, (4, 4)), (128, 8, 1.76659015, (2, 3)),
+                                             (64, 2, 0.0, (4, 4))])
+def test_c_oracle_matches_numpy_oracle(N, low, shift, nu):
+    osm, osv = orc.StencilMaker(), orc.Solver()
+    H = (-1. / np.pi ** 2) * osm.laplacian(N, "2d")
+    rs = np.random.RandomState(N)
+    v0, f = rs.random_sample(N * N), rs.random_sample(N * N)
+    want = osv.vcycle(v0.copy(), f.copy(), H, osm, nu1=nu[0], nu2=nu[1], shift=shift, lowest_level=low, dimension="2d")
+    got = c_oracle.WellHierarchy(N, low).vcycle(v0, f, shift, nu1=nu[0], nu2=nu[1])
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-11
