@@ -381,6 +381,22 @@ def test_vcycle_matches_oracle(prod, o, dim, N, low, shift):
     assert rel(got, want) < 1e-10, rel(got, want)
 
 
+@pytest.mark.parametrize("N,low,shift", [(1024, 8, 4.38639582), (2048, 8, 1.76659015), (2048, 16, 0.0)])
+def test_vcycle_matches_c_oracle_at_large_sizes(prod, N, low, shift):
+    """the matrix-free C oracle (held to the numpy oracle in tests/test_c_oracle.py) reaches sizes scipy cannot in seconds"""
+    import c_oracle
+    sm, s, _ = prod
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    rs = np.random.RandomState(N)
+    v0, f = rs.random_sample(N * N), rs.random_sample(N * N)
+    got = s.vcycle(v0.copy(), f.copy(), H, sm, shift=shift, lowest_level=low, dimension="2d")
+    want = c_oracle.WellHierarchy(N, low).vcycle(v0, f, shift)
+    assert rel(got, want) < 1e-10, rel(got, want)
+    got = s.vcycle(np.zeros(N * N), f.copy(), H, sm, nu1=3, nu2=2, shift=shift, lowest_level=low, dimension="2d")
+    want = c_oracle.WellHierarchy(N, low).vcycle(np.zeros(N * N), f, shift, nu1=3, nu2=2)
+    assert rel(got, want) < 1e-10, rel(got, want)
+
+
 def test_vcycle_api_conventions(prod, capsys, T):
     sm, s, _ = prod
     L = sm.laplacian(2)
