@@ -37,9 +37,19 @@ namespace {
 #define MGCMT_MIN_CTAS 2
 #endif
 constexpr int kVRing = MGCMT_VRING;  // prefetch depth of the v ring (rows, power of two)
-// f ring depth = prefetch depth + NSTAGE + 2 rows of queue (per instantiation; not a power of two: slots are
-// tracked incrementally)
-__host__ __device__ constexpr int f_ring_slots(int nstage) { return kVRing + nstage + 2; }
+// Pipeline skew: stage k works kSkew * k rows behind the input row.  With kSkew = 1 a stage consumes what its
+// predecessor produced in the SAME time step, so the stages of a step form one serial dependency chain.  With
+// kSkew = 2 a stage consumes what its predecessor produced in the PREVIOUS step (kept in C registers per stage):
+// all stages of a step are independent of each other; the price is NSTAGE-1 extra rows of pipeline fill per chunk and
+// a deeper f queue.  Measured on B200 (4096^2): no gain (down leg 132 vs 131 us) -- the stage-to-stage chain is not
+// what limits the kernel -- so the default stays 1; the variant is kept for the next profiling round.
+#ifndef MGCMT_SKEW
+#define MGCMT_SKEW 1
+#endif
+constexpr int kSkew = MGCMT_SKEW;
+// f ring depth = prefetch depth + kSkew * NSTAGE + 2 rows of queue (per instantiation; not a power of two: slots
+// are tracked incrementally)
+__host__ __device__ constexpr int f_ring_slots(int nstage) { return kVRing + kSkew * nstage + 2; }
 constexpr int kERing = 4;    // coarse-row ring (PROLONG)
 constexpr int kWarps = 4;    // warps per CTA (independent strips)
 
@@ -106,9 +116,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   // first / last input row the useful outputs depend on; the loop starts on an even row at or before
   // t_first (two rows earlier for PROLONG so both coarse rows of the first fine row are in hand)
   const int t_first = r0 - NU - (RESTRICT ? 1 : 0);
-  const int t_last = r1 - 1 + NU + (RESTRICT ? 2 : 0);  // inclusive
+  const int t_load_last = r1 - 1 + NU + (RESTRICT ? 2 : 0);                         // last input row that matters
+  const int t_last = t_load_last + (kSkew - 1) * (NSTAGE > 0 ? NSTAGE - 1 : 0);     // last time step (inclusive)
   const int t_begin = (t_first - (PROLONG ? 2 : 0)) & ~1;
-  const int tab0 = t_begin - NSTAGE - 1;                // first row held in rowtab
+  const int tab0 = t_begin - kSkew * NSTAGE - 1;        // first row held in rowtab
   const int ntab = t_last + 3 - tab0;                   // ... up to row t_last + 2
   const int nrc = L.nrows_coarse ? L.nrows_coarse : L.nrows / 2, ncc = L.ncols / 2;
   const int cs = L.crow_shift;
@@ -139,7 +150,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     // the grid or has coefficients different from the reference row's: that step reads the table (and may
     // recompute omega/diag); all other steps run on the reference registers
     double slow = 0.0;
-    for (int d = -1; d <= NSTAGE; ++d) {
+    for (int d = -1; d <= kSkew * NSTAGE; ++d) {
       const int g2 = gg - d;
       if (g2 < 0 || g2 >= L.nrows_glob) { slow = 1.0; continue; }
       bool same = (L.ka_lo[g2] == kal_ref && L.ka_di[g2] == kad_ref && L.ka_up[g2] == kau_ref);
@@ -193,7 +204,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   // ---- asynchronous row fetch -------------------------------------------------------------------
   auto issue = [&](int t, int fslot) {
     // rows outside the slab array or outside the global grid are zero-filled
-    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last && (unsigned)(t + L.row0) < (unsigned)L.nrows_glob;
+    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_load_last && (unsigned)(t + L.row0) < (unsigned)L.nrows_glob;
     if (!ZEROV) {
       double2 *dst = my_v + (t & (kVRing - 1)) * (C / 2) * NT;
 #pragma unroll
@@ -214,7 +225,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       // coarse row I = t/2 is first needed by fine row t (even); coarse columns c0/2 .. c0/2+CE-1
       const int I = (t >> 1) + cs;
       const int Gc = ((t + L.row0) >> 1);  // global coarse row
-      const bool rowc = I >= 0 && I < nrc && t <= t_last && Gc >= 0 && Gc < (L.nrows_glob >> 1);
+      const bool rowc = I >= 0 && I < nrc && t <= t_load_last && Gc >= 0 && Gc < (L.nrows_glob >> 1);
       double *dst = my_e + (I & (kERing - 1)) * ESLOT;
 #pragma unroll
       for (int g = 0; g < CE; ++g) {
@@ -227,10 +238,11 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   };
 
   Stage<C> st[NSTAGE > 0 ? NSTAGE : 1];
+  double pend[NSTAGE > 0 ? NSTAGE : 1][C];  // kSkew == 2: pend[k] = what stage k-1 finalised in the previous step
 #pragma unroll
   for (int k = 0; k < NSTAGE; ++k)
 #pragma unroll
-    for (int q = 0; q < C; ++q) st[k].a1[q] = st[k].a2[q] = st[k].xc[q] = 0.0;
+    for (int q = 0; q < C; ++q) st[k].a1[q] = st[k].a2[q] = st[k].xc[q] = pend[k][q] = 0.0;
 
   double eprev[C], ecur[C];  // column-interpolated coarse rows I-1 and I (PROLONG)
 #pragma unroll
@@ -298,10 +310,19 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     }
 
     // ---- stages 1..NSTAGE: row n of stage k-1 arrives, row n-1 of stage k is finalised -----------
+    // (kSkew == 2: in descending order, so a stage reads pend[k] before its predecessor overwrites it)
+    double xrow[C];
 #pragma unroll
-    for (int k = 0; k < NSTAGE; ++k) {
-      const int n = t - k;       // arriving row (of stage k's input)
-      const int rho = n - 1;     // finalised row
+    for (int q = 0; q < C; ++q) xrow[q] = x[q];
+#pragma unroll
+    for (int kk = 0; kk < NSTAGE; ++kk) {
+      const int k = (kSkew == 1) ? kk : NSTAGE - 1 - kk;
+      const int n = t - kSkew * k;  // arriving row (of stage k's input)
+      const int rho = n - 1;        // finalised row
+      if (kSkew != 1) {
+#pragma unroll
+        for (int q = 0; q < C; ++q) x[q] = (k == 0) ? xrow[q] : pend[k][q];
+      }
       const RowCoef *tb = rowtab + (rho - tab0);
       const double cr_ka_up = SLOW ? tb[0].ka_up : kau_ref, cr_ma_up = FIVE ? 0.0 : (SLOW ? tb[0].ma_up : mau_ref);
       const double cn_ka_di = SLOW ? tb[1].ka_di : kad_ref, cn_ma_di = FIVE ? 1.0 : (SLOW ? tb[1].ma_di : mad_ref);
@@ -324,7 +345,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
       // (t_begin, the slab row offset and every lane's first column are even)
       const bool gs_stage = (GS != 0) && !is_res;
       const int colour = k % NCOL;
-      const int prho = (ODD ? 1 : 0) ^ ((k + 1) & 1);
+      const int prho = (ODD ? 1 : 0) ^ ((kSkew * k + 1) & 1);
       auto in_colour = [&](int prow, int pcol) {
         if (!gs_stage) return true;
         if (FIVE) return ((prow + pcol) & 1) == colour;
@@ -332,7 +353,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
              : colour == 1 ? (prow == 1 && pcol == 1)
              : colour == 2 ? (prow == 0 && pcol == 1) : (prow == 1 && pcol == 0);
       };
-      int frho = fs - (k + 1);  // slot of row rho = t - k - 1 (slots of rows before t_begin hold garbage that
+      int frho = fs - (kSkew * k + 1);  // slot of row rho (slots of rows before t_begin hold garbage that
       frho += (frho < 0) ? kFRing : 0;  // only ever reaches rows outside every valid region)
       const double2 *fsrc = my_f + frho * (C / 2) * NT;
       double ffv[C];
@@ -376,9 +397,12 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
         }
         st[k].xc[q] = x[q];
       }
-      // the finalised row is the next stage's arriving row
+      // the finalised row is the next stage's arriving row (this step for kSkew == 1, the next one otherwise)
 #pragma unroll
-      for (int q = 0; q < C; ++q) x[q] = out[q];
+      for (int q = 0; q < C; ++q) {
+        x[q] = out[q];
+        if (kSkew != 1 && k + 1 < NSTAGE) pend[k + 1][q] = out[q];
+      }
 
       if (!is_res && k == NU - 1) {
         // x = row rho of the NU-th sweep: the smoothed iterate
@@ -392,7 +416,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
         // x = residual row rho (zero outside the grid): full weighting.  Columns first:
         //   coarse J = c0/2 + g  <-  1/4 r[2J] + 1/2 r[2J+1] + 1/4 r[2J+2]
         // rho = t - NU - 1 has the parity of t iff NU is odd
-        constexpr bool RHO_ODD = (ODD != ((NU + 1) % 2 != 0));
+        constexpr bool RHO_ODD = (ODD != ((kSkew * NU + 1) % 2 != 0));
         const double rnext = __shfl_down_sync(0xffffffffu, x[0], 1);
         double crr[CE];
 #pragma unroll
@@ -450,7 +474,7 @@ template <int C>
 static size_t fused_smem_bytes(bool prolong, int rows_per_chunk, int nstage) {
   size_t b = sizeof(double) * (size_t)(kVRing + f_ring_slots(nstage)) * kWarps * 32 * C;
   if (prolong) b += sizeof(double) * (size_t)kERing * kWarps * 32 * (C / 2);
-  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 3 * nstage + 12);  // rows t_begin-NSTAGE-1 .. t_last+2
+  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 3 * kSkew * nstage + 16);  // rows t_begin-kSkew*NSTAGE-1 .. t_last+2
   return b;
 }
 
