@@ -329,10 +329,10 @@ def run_ours(args):
             with torch.cuda.stream(main if serial else streams[c % nstreams]):
                 sp = _stream_ptr(torch)
                 # w0 = 0 as in the reference's drivers (2DPotGS.py:94): flagged, so the zero vector is not read
-                _lib.check(lib.mgcmt_vcycle(hc.handle, shifts[c], 4, 4, smoother_code, omega, _ptr(W[c]), _ptr(V[c]), 1, sp))
-                # Rayleigh quotient w^T H w / w^T w (one fused pass); the normalisation w/||w|| of 2DPotGS.py:96 is
-                # what the first step of the Gram-Schmidt below does for every column anyway
-                _lib.check(lib.mgcmt_rayleigh(hc.handle, 0, _ptr(W[c]), _ptr(rq[c]), sp))
+                # cycle + Rayleigh quotient w^T H w / w^T w (its sums are taken inside the finest up leg); the
+                # normalisation w/||w|| of 2DPotGS.py:96 is what the orthonormalisation below does to every column anyway
+                _lib.check(lib.mgcmt_vcycle_rq(hc.handle, shifts[c], 4, 4, smoother_code, omega, _ptr(W[c]), _ptr(V[c]), 1,
+                                               _ptr(rq[c]), sp))
         if not serial:
             for st_ in streams:
                 main.wait_stream(st_)

@@ -142,6 +142,12 @@ int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double 
 int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega,
                  double *d_v, const double *d_f, int v0_is_zero, void *stream);
 
+/* mgcmt_vcycle followed by the Rayleigh quotient of the result: d_out2[0] = w^T A_0 w, d_out2[1] = w^T w (the
+ * `w/||w||` + `v^T H v` the drivers do after every cycle, 2DPotGS.py:96,103).  On 2-D Jacobi cycles with nu2 = 4 the
+ * sums are taken inside the finest up leg (an extra pipeline stage evaluates A w on the final iterate), so no extra
+ * pass over w is made; otherwise it is mgcmt_vcycle + mgcmt_rayleigh. */
+int mgcmt_vcycle_rq(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega, double *d_v,
+                    const double *d_f, int v0_is_zero, double *d_out2, void *stream);
 /* The V-cycle restricted to levels level..coarsest with a zero initial guess and 4/4 sweeps -- what every
  * coarse level of MGCMTSolver.vcycle runs (MGCMTSolver.py:316-320).  d_v, d_f: vectors of that level. */
 int mgcmt_vcycle_from(mgcmt_hier_t *h, int level, double shift, int smoother, double omega, double *d_v,

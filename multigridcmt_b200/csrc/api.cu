@@ -109,6 +109,10 @@ struct mgcmt_hier {
   bool slab = false;   // row-slab piece of a decomposed grid: only single-level operators are valid
   int halo = 0;        // halo rows above and below the owned rows of every slab level
   int first_work = 0;  // levels below this one have no work vectors (replicated coarse part of a slab solver)
+  double *rq_partials = nullptr;  // per-warp Rayleigh partial sums of the finest up leg (mgcmt_vcycle_rq)
+  int rq_slots = 0;
+  double *rq_out = nullptr;       // set for the duration of a mgcmt_vcycle_rq call
+  bool rq_done = false;
   std::vector<Level> lev;
   std::vector<InvEntry> invs;
   uint64_t clock = 0;
@@ -297,7 +301,21 @@ int fused_up(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu2,
   int left = nu2;
   const int first = left > maxpass ? maxpass : left;
   if (l == 0) prof_mark(s);
-  CU(launch_pass(h, l, gs, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
+  // finest level, Rayleigh quotient requested and this pass is the last one: the up leg also leaves the partial sums
+  const int slots = (l == 0 && h->rq_out && !gs && first == 4 && left == 4 && !use_tile(h, l)) ? fused_rq_slots(L.dev) : 0;
+  if (slots > 0) {
+    if (slots > h->rq_slots) {
+      cudaFree(h->rq_partials);
+      h->rq_partials = nullptr;
+      CU(cudaMalloc(&h->rq_partials, sizeof(double) * 2 * slots));
+      h->rq_slots = slots;
+    }
+    CU(launch_fused_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, a, f, b, e, h->rq_partials, s));
+    CU(launch_finish(2, slots, h->rq_partials, h->rq_out, s));
+    h->rq_done = true;
+  } else {
+    CU(launch_pass(h, l, gs, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
+  }
   if (l == 0) prof_mark(s);
   { double *t = a; a = b; b = t; }
   left -= first;
@@ -557,6 +575,7 @@ int mgcmt_hier_destroy(mgcmt_hier_t *h) {
     cudaFree(L.zrow);
   }
   for (auto &e : h->invs) cudaFree(e.inv);
+  cudaFree(h->rq_partials);
   cudaFree(h->status);
   delete h;
   return MGCMT_OK;
@@ -745,6 +764,23 @@ int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, 
   if (nu1 < 0 || nu2 < 0) return fail(MGCMT_ERR_ARG, "negative sweep count");
   if (h->slab || h->first_work > 0) return fail(MGCMT_ERR_STATE, "this hierarchy has no full finest level (slab piece / coarse part)");
   return vcycle_level(h, 0, shift, nu1, nu2, smoother, omega, d_v, d_f, v0_is_zero != 0, (cudaStream_t)stream);
+}
+
+int mgcmt_vcycle_rq(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega, double *d_v,
+                    const double *d_f, int v0_is_zero, double *d_out2, void *stream) {
+  if (!h) return fail(MGCMT_ERR_ARG, "null hierarchy");
+  if (!d_out2) return fail(MGCMT_ERR_ARG, "null output");
+  h->rq_out = d_out2;
+  h->rq_done = false;
+  int rc = mgcmt_vcycle(h, shift, nu1, nu2, smoother, omega, d_v, d_f, v0_is_zero, stream);
+  h->rq_out = nullptr;
+  if (rc) return rc;
+  if (h->rq_done) {
+    // the fused stage summed w^T (A - shift I) w: add shift * w^T w
+    CU(launch_rq_unshift(d_out2, shift, (cudaStream_t)stream));
+    return MGCMT_OK;
+  }
+  return mgcmt_rayleigh(h, 0, d_v, d_out2, stream);  // levels / smoothers without the fused stage: one extra pass
 }
 
 int mgcmt_vcycle_from(mgcmt_hier_t *h, int level, double shift, int smoother, double omega, double *d_v,

@@ -163,9 +163,17 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   }
   __syncthreads();
 
+  // PROLONG && RESTRICT = "up leg + Rayleigh quotient": the extra stage after the sweeps evaluates A_s w on the final
+  // iterate and every warp leaves its partial sums of w^T A_s w and w^T w in r_coarse[slot], r_coarse[nslots + slot]
+  constexpr bool RQ = PROLONG && RESTRICT;
+  const int rq_slot = (blockIdx.y * gridDim.x + blockIdx.x) * kWarps + warp;
+  const int rq_nslots = gridDim.x * gridDim.y * kWarps;
   const int strip = blockIdx.x * kWarps + warp;
   const int u0 = strip * USEFUL;  // first useful fine column of this strip
-  if (u0 >= L.ncols) return;      // surplus warp (no CTA-wide barrier after this point)
+  if (u0 >= L.ncols) {            // surplus warp (no CTA-wide barrier after this point)
+    if (RQ && lane == 0) { r_coarse[rq_slot] = 0.0; r_coarse[rq_nslots + rq_slot] = 0.0; }
+    return;
+  }
   const int u1 = min(u0 + USEFUL, L.ncols);
   const int c0 = u0 - HALO + C * lane;  // first column of this thread (even)
 
@@ -247,6 +255,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   double eprev[C], ecur[C];  // column-interpolated coarse rows I-1 and I (PROLONG)
 #pragma unroll
   for (int q = 0; q < C; ++q) eprev[q] = ecur[q] = 0.0;
+  double rq_num = 0.0, rq_den = 0.0;  // RQ mode
   double racc[CE];           // running full-weighting row sum (RESTRICT)
 #pragma unroll
   for (int g = 0; g < CE; ++g) racc[g] = 0.0;
@@ -381,6 +390,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
           const double acc = st[k].a1[q] + (FIVE ? cr_ka_up * S[q] : (cr_ma_up * T[q] + cr_ka_up * S[q]));
           const double ff = ffv[q];
           out[q] = is_res ? (ff - acc) : (st[k].xc[q] + w[q] * (ff - acc));
+          if (RQ && is_res && rho >= r0 && rho < r1 && colout[q]) {  // each useful point exactly once
+            rq_num += st[k].xc[q] * acc;
+            rq_den += st[k].xc[q] * st[k].xc[q];
+          }
         } else {
           out[q] = st[k].xc[q];  // not this stage's colour: passes through
         }
@@ -412,7 +425,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
           if (rowok && colout[2 * g])
             st_stream2(v_out + (size_t)rho * L.ncols + c0 + 2 * g, make_double2(x[2 * g], x[2 * g + 1]));
       }
-      if (is_res) {
+      if (is_res && !RQ) {
         // x = residual row rho (zero outside the grid): full weighting.  Columns first:
         //   coarse J = c0/2 + g  <-  1/4 r[2J] + 1/2 r[2J+1] + 1/4 r[2J+2]
         // rho = t - NU - 1 has the parity of t iff NU is odd
@@ -467,6 +480,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
     }
   }
   cpa_wait<0>();
+  if (RQ) {
+    const double a = warp_sum(rq_num), b = warp_sum(rq_den);
+    if (lane == 0) { r_coarse[rq_slot] = a; r_coarse[rq_nslots + rq_slot] = b; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -478,16 +495,23 @@ static size_t fused_smem_bytes(bool prolong, int rows_per_chunk, int nstage) {
   return b;
 }
 
+template <int NU, int C>
+static void fused_geometry(const LevelDev &L, int *gx, int *rpc_out) {
+  constexpr int USEFUL = 32 * C - 2 * ((NU + 3) & ~1);
+  const int strips = (L.ncols + USEFUL - 1) / USEFUL;
+  *gx = (strips + kWarps - 1) / kWarps;
+  int rpc = 128;
+  while (rpc > 16 && (long long)*gx * ((L.nrows + rpc - 1) / rpc) < 264) rpc >>= 1;  // ~90 % of 148 SMs x 2 CTAs
+  if (rpc > L.nrows) rpc = L.nrows;  // nrows is a power of two >= 2 here (even chunks)
+  *rpc_out = rpc;
+}
+
 template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS>
 static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega, const double *v_in,
                                   const double *f, double *v_out, const double *e_coarse, double *r_coarse,
                                   cudaStream_t s) {
-  constexpr int USEFUL = 32 * C - 2 * ((NU + 3) & ~1);
-  const int strips = (L.ncols + USEFUL - 1) / USEFUL;
-  const int gx = (strips + kWarps - 1) / kWarps;
-  int rpc = 128;
-  while (rpc > 16 && (long long)gx * ((L.nrows + rpc - 1) / rpc) < 264) rpc >>= 1;  // ~90 % of 148 SMs x 2 CTAs
-  if (rpc > L.nrows) rpc = L.nrows;  // nrows is a power of two >= 2 here (even chunks)
+  int gx, rpc;
+  fused_geometry<NU, C>(L, &gx, &rpc);
   const size_t smem = fused_smem_bytes<C>(PROLONG, rpc, NU + (RESTRICT ? 1 : 0));
   auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C, GS>;
   static bool attr_set = false;  // per instantiation
@@ -516,6 +540,11 @@ static cudaError_t dispatch_mode(const LevelDev &L, int mode, double shift, doub
       return launch_fused_t<FIVE, NU, false, true, true, C, GS>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s);
     case FUSED_UP:
       return launch_fused_t<FIVE, NU, true, false, false, C, GS>(L, shift, omega, v_in, f, v_out, e_coarse, nullptr, s);
+    case FUSED_UP_RQ:  // only the Jacobi NU = 4 up leg of the finest level carries the Rayleigh-quotient stage
+      if constexpr (GS == 0 && NU == 4 && FIVE && C == 4)
+        return launch_fused_t<true, 4, true, true, false, 4, 0>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+      else
+        return cudaErrorInvalidValue;
   }
   return cudaErrorInvalidValue;
 }
@@ -541,9 +570,19 @@ cudaError_t launch_fused_gs_leg(const LevelDev &L, int mode, int sweeps, double 
   return cudaErrorInvalidValue;
 }
 
-int g_fused_c5 = MGCMT_FUSED_C5;
+int g_fused_c5 = MGCMT_FUSED_C5;  // columns per lane on the 5-point level (2 or 4), switchable for A/B timing
+
+// number of per-warp partial-sum slots a FUSED_UP_RQ launch on this level writes (2 * slots doubles), or 0 if that
+// mode is not available for the level
+int fused_rq_slots(const LevelDev &L) {
+  if (!L.five || g_fused_c5 != 4 || L.nrows < 2) return 0;
+  int gx, rpc;
+  fused_geometry<4, 4>(L, &gx, &rpc);
+  return gx * ((L.nrows + rpc - 1) / rpc) * kWarps;
+}
+
 int g_fused_c9 = 0;  // columns per lane on 9-point levels: 2, 4, or 0 = 4 on levels >= 4096 wide (enough strips to
-                     // fill the GPU; measured 8 % faster per cycle at 16384^2, no gain at 4096^2), else 2  // columns per lane on the 5-point level (2 or 4), switchable for A/B timing
+                     // fill the GPU; measured 8 % faster per cycle at 16384^2, no gain at 4096^2), else 2
 
 cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,

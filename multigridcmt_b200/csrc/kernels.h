@@ -39,7 +39,8 @@ cudaError_t launch_prolong(const LevelDev &Lf, bool coarsen_rows, bool accumulat
 enum { FUSED_SMOOTH = 0,     // v_out = J^nu(v_in)
        FUSED_DOWN = 1,       // v_out = J^nu(v_in), r_coarse = R (f - A v_out)
        FUSED_DOWN_ZERO = 2,  // same with v_in == 0 (not read)
-       FUSED_UP = 3 };       // v_out = J^nu(v_in + P e_coarse)
+       FUSED_UP = 3,         // v_out = J^nu(v_in + P e_coarse)
+       FUSED_UP_RQ = 4 };    // FUSED_UP (Jacobi, nu = 4, 5-point level) + per-warp partials of w^T A_s w, w^T w of v_out
 #ifndef MGCMT_FUSED_C5
 #define MGCMT_FUSED_C5 4     // columns per lane, 5-point (finest) level
 #endif
@@ -47,6 +48,7 @@ enum { FUSED_SMOOTH = 0,     // v_out = J^nu(v_in)
 #define MGCMT_FUSED_C9 2     // columns per lane, 9-point (Galerkin) levels
 #endif
 extern int g_fused_c5, g_fused_c9;
+int fused_rq_slots(const LevelDev &L);
 cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,
                              double *r_coarse, cudaStream_t s);
@@ -100,6 +102,7 @@ cudaError_t launch_cholqr_apply(long long n, int k, double *w0, long long stride
 cudaError_t launch_scale_by_inv_norm(long long n, double *x, const double *sumsq, cudaStream_t s);
 cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *denom, double sign,
                             const double *x, double *y, cudaStream_t s);
+cudaError_t launch_rq_unshift(double *out2, double shift, cudaStream_t s);
 cudaError_t launch_axpby(long long n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s);
 cudaError_t launch_scale_to(long long n, const double *x, const double *sumsq, double *y, cudaStream_t s);
 

@@ -397,6 +397,13 @@ cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *deno
   return cudaGetLastError();
 }
 
+__global__ void rq_unshift_kernel(double *out2, double shift) { out2[0] += shift * out2[1]; }
+cudaError_t launch_rq_unshift(double *out2, double shift, cudaStream_t s) {
+  rq_unshift_kernel<<<1, 1, 0, s>>>(out2, shift);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // out = a x + b y   (host scalars)
 __global__ void axpby_kernel(long long n, double a, const double *__restrict__ x, double b, const double *__restrict__ y,
                              double *__restrict__ out) {

@@ -522,6 +522,28 @@ def test_rq_family_matches_reference_golden(prod, golden, o):
     assert out.shape == (64, 2) and rel(out[:, 0], want[:, 0]) < 1e-6
 
 
+def test_vcycle_rq_fused_stage(T, prod):
+    """mgcmt_vcycle_rq: same iterate as mgcmt_vcycle, Rayleigh sums == a separate pass (fused stage at 512^2, fallback at 32^2)"""
+    import ctypes as C
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import _ptr, _stream_ptr, get_hierarchy
+    sm, s, _ = prod
+    lib = _lib.load()
+    for N, smoother in ((512, _lib.SMOOTH_WJACOBI), (32, _lib.SMOOTH_WJACOBI), (512, _lib.SMOOTH_RBGS)):
+        H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+        h = get_hierarchy(H, 8)
+        f = dev(T, rand(N * N, 33))
+        w1 = T.zeros(N * N, dtype=T.float64, device="cuda"); w2 = T.zeros_like(w1)
+        out = T.zeros(2, dtype=T.float64, device="cuda"); ref = T.zeros(2, dtype=T.float64, device="cuda")
+        om = 2. / 3. if smoother == _lib.SMOOTH_WJACOBI else 1.0
+        _lib.check(lib.mgcmt_vcycle_rq(h.handle, 4.38639582, 4, 4, smoother, om, _ptr(w1), _ptr(f), 1, _ptr(out), _stream_ptr(T)))
+        _lib.check(lib.mgcmt_vcycle(h.handle, 4.38639582, 4, 4, smoother, om, _ptr(w2), _ptr(f), 1, _stream_ptr(T)))
+        h.rayleigh(0, w2, ref)
+        assert T.equal(w1, w2)
+        o, r = out.cpu().numpy(), ref.cpu().numpy()
+        assert abs(o[1] - r[1]) <= 1e-13 * abs(r[1]) and abs(o[0] - r[0]) <= 1e-12 * abs(r[0]), (N, smoother, o, r)
+
+
 def test_rayleigh_quotient(prod):
     sm, s, _ = prod
     N = 128
