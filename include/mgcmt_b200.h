@@ -204,6 +204,39 @@ int mgcmt_axpby(long long n, double a, const double *d_x, double b, const double
  *   O(cond(W)^2 eps), so it is meant for the nearly orthonormal blocks of the eigen-iteration (k <= 6). */
 int mgcmt_gramschmidt(long long n, int k, double *d_V, int modified, void *stream);
 
+/* ---- banded operators: general complex128 matrices kept by diagonals (1-D multiband Hamiltonians) -------------
+ * ThesisProblem.py:26-104 hands MGCMTSolver.vcycle the complex sparse matrix PotWellSolver.makeMatrix builds
+ * (PotWellSolver.py:54-233): 4 (or 6) coupled bands, every block tridiagonal -- a dozen diagonals.  It is treated as
+ * a 1-D problem of n = bands * gridpoints unknowns, exactly as the reference does (transfer operators included).
+ * Vectors and diagonals are complex interleaved (re, im): n complex numbers = 2n doubles, 16-byte aligned.
+ * Storage: d_vals[(k*n + i)] (complex) = A[i, i + h_offsets[k]], zero where the column falls outside the matrix;
+ * offsets strictly ascending and containing 0.  Coarse operators are the Galerkin products R A P
+ * (MGCMTSolver.py:318), formed on the device; n must be lowest_level * 2^L, lowest_level <= 512.
+ * Smoothers: MGCMT_SMOOTH_WJACOBI, MGCMT_SMOOTH_GSLEX (omega == 1: gseidel; otherwise sor with quirk Q6). */
+typedef struct mgcmt_band mgcmt_band_t;
+int mgcmt_band_create(int n, int ndiag, const int *h_offsets, const double *d_vals, int lowest_level, void *stream,
+                      mgcmt_band_t **out);
+int mgcmt_band_destroy(mgcmt_band_t *h);
+int mgcmt_band_num_levels(const mgcmt_band_t *h, int *out);
+int mgcmt_band_level_shape(const mgcmt_band_t *h, int level, int *n, int *ndiag);
+/* host copies of a level's offsets (ndiag ints) and diagonals (2*ndiag*n doubles); either may be NULL */
+int mgcmt_band_level_diags(const mgcmt_band_t *h, int level, int *h_offsets, double *h_vals);
+/* y = (A_l - shift I) x                                   -- `shifted_matrix * v`, MGCMTSolver.py:315 */
+int mgcmt_band_apply(mgcmt_band_t *h, int level, double shift, const double *d_x, double *d_y, void *stream);
+/* nu sweeps of wjacobi / gseidel / sor on (A_l - shift I) v = f, in place   -- MGCMTSolver.py:182-246 */
+int mgcmt_band_smooth(mgcmt_band_t *h, int level, int smoother, int nu, double shift, double omega, double *d_v,
+                      const double *d_f, void *stream);
+/* rc = R (f - (A_l - shift I) v)                           -- MGCMTSolver.py:315 */
+int mgcmt_band_residual_restrict(mgcmt_band_t *h, int level, double shift, const double *d_v, const double *d_f,
+                                 double *d_rc, void *stream);
+/* v += P ec                                                -- MGCMTSolver.py:323-324 */
+int mgcmt_band_prolong_correct(mgcmt_band_t *h, int level, const double *d_ec, double *d_v, void *stream);
+/* v = (A_coarsest - shift I)^-1 f                          -- MGCMTSolver.py:305-308 */
+int mgcmt_band_coarse_solve(mgcmt_band_t *h, double shift, const double *d_f, double *d_v, void *stream);
+/* one V-cycle on (A_0 - shift I) v = f, v holds the start vector on entry  -- MGCMTSolver.py:281-329 */
+int mgcmt_band_vcycle(mgcmt_band_t *h, double shift, int nu1, int nu2, int smoother, double omega, double *d_v,
+                      const double *d_f, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

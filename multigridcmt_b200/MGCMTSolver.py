@@ -15,8 +15,11 @@ Reference conventions kept on purpose (SURVEY.md section 5 and the quirk table):
   * `sor` adds w (D-L)^-1 f (quirk Q6).
 What is NOT kept: the O(n^2) iteration matrices and the per-call rebuild of R, P, R*A*P.
 
-There is no CPU fallback: an operator that is not a separable radius-1 stencil, a foreign smoother
-callable or a foreign stencil_maker raises (loudly) instead of silently running somewhere else.
+Operators: the real separable radius-1 stencils of the well problems take the fused path (hierarchy.py);
+any other 1-D operator -- complex, or more than three diagonals, e.g. the multiband Hamiltonians of
+ThesisProblem.py:26-104 -- takes the general banded complex path (banded.py).  There is no CPU fallback: a 2-D
+operator that is not separable, a foreign smoother callable or a foreign stencil_maker raises (loudly) instead
+of silently running somewhere else.
 """
 from __future__ import annotations
 
@@ -28,7 +31,14 @@ from . import _lib
 from .MGCMTProcessor import MGCMTProcessor
 from .MGCMTStencilMaker import MGCMTStencilMaker
 from .hierarchy import (_ptr, _stream_ptr, get_hierarchy, is_device_tensor, to_device, to_host)
-from .operators import recognise
+from .operators import SeparableOperator, UnsupportedOperator, recognise
+from .banded import (BandedOperator, get_banded_hierarchy, recognise_banded, to_device_complex)
+
+
+def _is_complex(x):
+    if is_device_tensor(x) or hasattr(x, "is_complex"):
+        return bool(x.is_complex())
+    return np.iscomplexobj(x)
 
 
 def _inplace_column(x, n):
@@ -82,6 +92,63 @@ class MGCMTSolver:
                 "exactly that class's full-weighting restriction / linear interpolation")
 
     # ------------------------------------------------------------------------------------------
+    # operator routing: real separable stencil -> fused path; any other 1-D operator -> banded complex path
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _route(A, dimension, *vectors):
+        if isinstance(A, BandedOperator):
+            return A
+        if dimension == "1d" and not isinstance(A, SeparableOperator):
+            if any(_is_complex(x) for x in vectors) or np.iscomplexobj(getattr(A, "data", np.zeros(0))):
+                return recognise_banded(A)
+            try:
+                return recognise(A, dimension)
+            except UnsupportedOperator:
+                return recognise_banded(A)
+        if any(_is_complex(x) for x in vectors):
+            if dimension == "1d":
+                return recognise_banded(A.tocsc())
+            raise UnsupportedOperator("complex vectors are supported on 1-D operators only (the reference's "
+                                      "multiband problems are 1-D, ThesisProblem.py:80-101)")
+        return recognise(A, dimension)
+
+    @staticmethod
+    def _banded_result(op, out, dev_in, *inputs):
+        """complex128 device vector -> what the reference would hand back: complex if anything was complex."""
+        real = op.is_real and not any(_is_complex(x) for x in inputs)
+        if real:
+            out = out.real.contiguous()
+        return out if dev_in else out.cpu().numpy()
+
+    def _smooth_banded(self, op, code, v0, f, nu, omega):
+        if code == _lib.SMOOTH_RBGS:
+            raise NotImplementedError("red-black Gauss-Seidel needs a radius-1 stencil; banded operators take "
+                                      "wjacobi, gseidel and sor")
+        n = len(v0)
+        low = n            # any hierarchy exposes level 0; build the shallowest legal one
+        while low > 512:
+            if low % 2:
+                raise UnsupportedOperator("operator size %d cannot be coarsened to <= 512 unknowns" % n)
+            low //= 2
+        h = get_banded_hierarchy(op, low)
+        v = to_device_complex(v0)
+        fd = to_device_complex(f)
+        h.smooth(0, code, nu, 0.0, omega, v, fd)
+        return self._banded_result(op, v, is_device_tensor(v0), v0, f).reshape(n, 1)
+
+    def _vcycle_banded(self, op, v0, f, nu1, nu2, code, omega, shift, low):
+        if code == _lib.SMOOTH_RBGS:
+            raise NotImplementedError("red-black Gauss-Seidel needs a radius-1 stencil; banded operators take "
+                                      "wjacobi, gseidel and sor")
+        n = len(v0)
+        h = get_banded_hierarchy(op, low)
+        v = to_device_complex(v0)
+        fd = to_device_complex(f)
+        h.vcycle(shift, nu1, nu2, code, omega, v, fd)
+        out = self._banded_result(op, v, is_device_tensor(v0), v0, f)
+        return out.reshape(n, 1) if h.num_levels == 1 else out
+
+    # ------------------------------------------------------------------------------------------
     # single-level smoothers (MGCMTSolver.py:182-246): return an (n, 1) array like the reference
     # ------------------------------------------------------------------------------------------
     def _smooth(self, code, v0, f, A, nu, omega, dimension=None):
@@ -89,7 +156,9 @@ class MGCMTSolver:
         dev_in = is_device_tensor(v0)
         if dimension is None:
             dimension = self._guess_dimension(A, n)
-        op = recognise(A, dimension)
+        op = self._route(A, dimension, v0, f)
+        if isinstance(op, BandedOperator):
+            return self._smooth_banded(op, code, v0, f, nu, omega)
         h = get_hierarchy(op, self._any_lowest(op))
         v = to_device(v0)
         if dev_in:
@@ -103,9 +172,10 @@ class MGCMTSolver:
     @staticmethod
     def _guess_dimension(A, n):
         """The reference's smoothers take only the matrix; decide 1-D vs 2-D from its bandwidth."""
-        from .operators import SeparableOperator
-        if isinstance(A, SeparableOperator):
+        if isinstance(A, (SeparableOperator, BandedOperator)):
             return A.dimension
+        if np.iscomplexobj(getattr(A, "data", np.zeros(0))):
+            return "1d"     # complex operators exist in 1-D only (ThesisProblem.py)
         N = int(round(np.sqrt(n)))
         if N * N == n and N > 2:
             try:
@@ -166,7 +236,9 @@ class MGCMTSolver:
             # the reference would recurse until the stencil maker prints its power-of-two message
             print("Length of start vector is not a power of 2")
             return None
-        op = recognise(A, dimension)
+        op = self._route(A, dimension, v0, f)
+        if isinstance(op, BandedOperator):
+            return self._vcycle_banded(op, v0, f, nu1, nu2, code, omega, shift, low)
         h = get_hierarchy(op, low)
         v = to_device(v0)
         if dev_in:

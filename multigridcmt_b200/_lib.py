@@ -65,6 +65,17 @@ SIGNATURES = {
     "mgcmt_scale_inv_norm": (_I, [_LL, _P, _P, _P]),
     "mgcmt_axpy_dev": (_I, [_LL, _P, _D, _P, _P, _P]),
     "mgcmt_gramschmidt": (_I, [_LL, _I, _P, _I, _P]),
+    "mgcmt_band_create": (_I, [_I, _I, _P, _P, _I, _P, C.POINTER(_P)]),
+    "mgcmt_band_destroy": (_I, [_P]),
+    "mgcmt_band_num_levels": (_I, [_P, C.POINTER(_I)]),
+    "mgcmt_band_level_shape": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I)]),
+    "mgcmt_band_level_diags": (_I, [_P, _I, _P, _P]),
+    "mgcmt_band_apply": (_I, [_P, _I, _D, _P, _P, _P]),
+    "mgcmt_band_smooth": (_I, [_P, _I, _I, _I, _D, _D, _P, _P, _P]),
+    "mgcmt_band_residual_restrict": (_I, [_P, _I, _D, _P, _P, _P, _P]),
+    "mgcmt_band_prolong_correct": (_I, [_P, _I, _P, _P, _P]),
+    "mgcmt_band_coarse_solve": (_I, [_P, _D, _P, _P, _P]),
+    "mgcmt_band_vcycle": (_I, [_P, _D, _I, _I, _I, _D, _P, _P, _P]),
 }
 
 

@@ -1,0 +1,196 @@
+"""General banded complex operators: the multiband Hamiltonians of the reference's ThesisProblem driver.
+
+ThesisProblem.py:26-104 builds a 4-band (or 6-band) Luttinger-Kohn quantum-well Hamiltonian with
+PotWellSolver.makeMatrix (PotWellSolver.py:54-233) -- a complex128 scipy.sparse matrix whose 4x4 blocks are
+tridiagonal -- and runs `solver.vcycle(w, v, H, stencil_maker, shift=mu, lowest_level=2**5,
+smoother=solver.gseidel)` on it as a 1-D problem of 4*gridsize unknowns.  Such a matrix is a dozen diagonals;
+this module keeps it that way (`BandedOperator`: offsets + one complex array per diagonal) and drives the
+`mgcmt_band_*` entry points of the C ABI (include/mgcmt_b200.h; kernels in csrc/band.cu).  MGCMTSolver routes
+every 1-D operator or vector the real separable path cannot take (complex, or more than three diagonals) here.
+There is no CPU fallback: no CUDA device, no result.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from .operators import UnsupportedOperator
+
+MAX_DIAGS = 96          # kBandMaxDiags in csrc/kernels.h
+MAX_COARSEST = 512      # kBandMaxCoarse
+
+
+class BandedOperator:
+    """n x n complex matrix kept by diagonals: vals[k, i] = A[i, i + offsets[k]] (0 outside the matrix)."""
+
+    def __init__(self, n, offsets, vals):
+        self.n = int(n)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        self.vals = np.ascontiguousarray(vals, dtype=np.complex128)
+        if self.vals.shape != (len(self.offsets), self.n):
+            raise ValueError("vals must have shape (len(offsets), n)")
+        self.shape = (self.n, self.n)
+        self.dimension = "1d"
+        self.is_real = not np.any(self.vals.imag)
+        self._device = {}
+
+    @classmethod
+    def from_sparse(cls, A):
+        if isinstance(A, BandedOperator):
+            return A
+        if not sp.issparse(A):
+            A = sp.coo_matrix(np.asarray(A))
+        if A.shape[0] != A.shape[1]:
+            raise UnsupportedOperator("operator must be square")
+        n = A.shape[0]
+        coo = A.tocoo()
+        keep = coo.data != 0
+        rows = coo.row[keep].astype(np.int64)
+        cols = coo.col[keep].astype(np.int64)
+        data = coo.data[keep]
+        offsets = np.unique(np.concatenate([cols - rows, np.zeros(1, dtype=np.int64)]))
+        if len(offsets) > MAX_DIAGS:
+            raise UnsupportedOperator("operator has %d diagonals; the banded path takes at most %d"
+                                      % (len(offsets), MAX_DIAGS))
+        vals = np.zeros((len(offsets), n), dtype=np.complex128)
+        k = np.searchsorted(offsets, cols - rows)
+        np.add.at(vals, (k, rows), data)      # duplicates sum, like scipy's own conversions
+        return cls(n, offsets, vals)
+
+    def tocsc(self):
+        rows, cols, data = [], [], []
+        i = np.arange(self.n)
+        for k, off in enumerate(self.offsets):
+            ok = (i + off >= 0) & (i + off < self.n)
+            rows.append(i[ok]); cols.append(i[ok] + off); data.append(self.vals[k, ok])
+        return sp.csc_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=self.shape)
+
+    def diagonal(self):
+        return self.vals[int(np.searchsorted(self.offsets, 0))].copy()
+
+
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class BandedHierarchy:
+    """Owns one mgcmt_band_t: every level (Galerkin R A P, formed on the device) of one banded operator."""
+
+    def __init__(self, op: BandedOperator, lowest_level: int):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        self.op = op
+        self.lowest_level = int(lowest_level)
+        self.n = op.n
+        d_vals = torch.from_numpy(op.vals).cuda()
+        handle = C.c_void_p()
+        _lib.check(lib.mgcmt_band_create(op.n, len(op.offsets), op.offsets.ctypes.data_as(C.c_void_p), _ptr(d_vals),
+                                         self.lowest_level, _stream_ptr(torch), C.byref(handle)))
+        self.handle = handle
+        nl = C.c_int()
+        _lib.check(lib.mgcmt_band_num_levels(handle, C.byref(nl)))
+        self.num_levels = nl.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().mgcmt_band_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def level_shape(self, level):
+        n, nd = C.c_int(), C.c_int()
+        _lib.check(_lib.load().mgcmt_band_level_shape(self.handle, level, C.byref(n), C.byref(nd)))
+        return n.value, nd.value
+
+    def level_operator(self, level):
+        """Host copy of a level's operator as a BandedOperator (tests: Galerkin parity)."""
+        n, nd = self.level_shape(level)
+        offs = np.zeros(nd, dtype=np.int32)
+        vals = np.zeros((nd, n), dtype=np.complex128)
+        _lib.check(_lib.load().mgcmt_band_level_diags(self.handle, level, offs.ctypes.data_as(C.c_void_p),
+                                                      vals.ctypes.data_as(C.c_void_p)))
+        return BandedOperator(n, offs, vals)
+
+    # ---- single-level operators on torch cuda complex128 tensors ------------------------------
+    def apply(self, level, shift, x, y):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_band_apply(self.handle, level, float(shift), _ptr(x), _ptr(y), _stream_ptr(torch)))
+        return y
+
+    def smooth(self, level, smoother, nu, shift, omega, v, f):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_band_smooth(self.handle, level, int(smoother), int(nu), float(shift), float(omega),
+                                                 _ptr(v), _ptr(f), _stream_ptr(torch)))
+        return v
+
+    def residual_restrict(self, level, shift, v, f, rc):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_band_residual_restrict(self.handle, level, float(shift), _ptr(v), _ptr(f), _ptr(rc),
+                                                            _stream_ptr(torch)))
+        return rc
+
+    def prolong_correct(self, level, ec, v):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_band_prolong_correct(self.handle, level, _ptr(ec), _ptr(v), _stream_ptr(torch)))
+        return v
+
+    def coarse_solve(self, shift, f, v):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_band_coarse_solve(self.handle, float(shift), _ptr(f), _ptr(v), _stream_ptr(torch)))
+        return v
+
+    def vcycle(self, shift, nu1, nu2, smoother, omega, v, f):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_band_vcycle(self.handle, float(shift), int(nu1), int(nu2), int(smoother),
+                                                 float(omega), _ptr(v), _ptr(f), _stream_ptr(torch)))
+        return v
+
+
+def get_banded_hierarchy(op: BandedOperator, lowest_level: int) -> BandedHierarchy:
+    torch = _lib.require_cuda()
+    key = (torch.cuda.current_device(), int(lowest_level))
+    h = op._device.get(key)
+    if h is None:
+        if len(op._device) >= 4:
+            op._device.clear()
+        h = BandedHierarchy(op, lowest_level)
+        op._device[key] = h
+    return h
+
+
+_RECOGNISED = {}
+
+
+def recognise_banded(A):
+    """BandedOperator.from_sparse with a small identity cache (drivers pass the same matrix every call)."""
+    if isinstance(A, BandedOperator):
+        return A
+    data = getattr(A, "data", None)
+    fp = (id(A), A.shape, getattr(A, "nnz", None),
+          data.ctypes.data if isinstance(data, np.ndarray) else None,
+          complex(data[:8].sum()) if isinstance(data, np.ndarray) and data.size else 0.0)
+    hit = _RECOGNISED.get(id(A))
+    if hit is not None and hit[0] == fp:
+        return hit[1]
+    op = BandedOperator.from_sparse(A)
+    if len(_RECOGNISED) > 64:
+        _RECOGNISED.clear()
+    _RECOGNISED[id(A)] = (fp, op)
+    return op
+
+
+def to_device_complex(x):
+    """numpy / torch vector -> contiguous complex128 cuda tensor of shape (n,) (always a fresh buffer)."""
+    torch = _lib.require_cuda()
+    if isinstance(x, torch.Tensor):
+        return x.to(device="cuda", dtype=torch.complex128).reshape(-1).clone().contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x).reshape(-1), dtype=np.complex128)).cuda()

@@ -47,6 +47,11 @@ int fail(int code, const std::string &msg) {
   g_err = msg;
   return code;
 }
+}  // namespace
+namespace mgcmt {
+int set_error(int code, const std::string &msg) { return fail(code, msg); }
+}
+namespace {
 #define CU(expr)                                                                                      \
   do {                                                                                                \
     cudaError_t e__ = (expr);                                                                         \

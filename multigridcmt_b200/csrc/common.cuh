@@ -19,6 +19,16 @@ struct LevelDev {
   const double *kb_lo, *kb_di, *kb_up, *mb_lo, *mb_di, *mb_up;  // length ncols
 };
 
+// One level of the general banded complex128 path (band.cu): A kept by diagonals, vals[k*n + i] = A[i, i + offs[k]]
+// (0 where i + offs[k] falls outside [0, n)), complex interleaved (re, im).
+struct BandDev {
+  int n;        // unknowns
+  int ndiag;    // stored diagonals
+  int idiag;    // index of the main diagonal (offs[idiag] == 0)
+  const int *offs;      // device, ascending
+  const double2 *vals;  // device, ndiag * n
+};
+
 constexpr int kWarp = 32;
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -2,9 +2,14 @@
 // include/mgcmt_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <string>
+
 #include "common.cuh"
 
 namespace mgcmt {
+
+// sets the thread's mgcmt_last_error() text and returns `code` (api.cu)
+int set_error(int code, const std::string &msg);
 
 enum { OP_JACOBI = 0, OP_RESIDUAL = 1, OP_APPLY = 2, OP_RAYLEIGH = 3 };
 
@@ -105,5 +110,22 @@ cudaError_t launch_axpy_dev(long long n, const double *alpha, const double *deno
 cudaError_t launch_rq_unshift(double *out2, double shift, cudaStream_t s);
 cudaError_t launch_axpby(long long n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s);
 cudaError_t launch_scale_to(long long n, const double *x, const double *sumsq, double *y, cudaStream_t s);
+
+// band.cu: general banded complex128 operators (1-D multiband Hamiltonians); vectors are complex interleaved
+constexpr int kBandMaxCoarse = 512;  // largest coarsest level the dense complex solve takes
+constexpr int kBandMaxDiags = 96;
+cudaError_t launch_band_apply(const BandDev &L, double shift, const double *x, double *y, cudaStream_t s);
+cudaError_t launch_band_jacobi(const BandDev &L, double shift, double omega, const double *vin, const double *f,
+                               double *vout, cudaStream_t s);
+cudaError_t launch_band_residual_restrict(const BandDev &L, double shift, const double *v, const double *f, double *rc,
+                                          cudaStream_t s);
+cudaError_t launch_band_prolong_correct(int n_fine, const double *ec, double *v, cudaStream_t s);
+cudaError_t launch_band_galerkin(const BandDev &F, int nc, int ndiag_c, const int *offs_c, const int *lut, double *vals_c,
+                                 cudaStream_t s);
+cudaError_t launch_band_lower_solve(const BandDev &L, double shift, double wl, double cf, double cd, double cu,
+                                    double oscale, const double *vin, const double *f, double *y, const double *g,
+                                    double *vout, cudaStream_t s);
+cudaError_t launch_band_inverse(const BandDev &L, double shift, double *aug, int *status, cudaStream_t s);
+cudaError_t launch_band_gemv(int n, const double *aug, const double *f, double *y, cudaStream_t s);
 
 }  // namespace mgcmt

@@ -161,7 +161,9 @@ class Processor:
 # solver  (MGCMTSolver.py)
 # ----------------------------------------------------------------------------------------------
 def _col(x):
-    return np.asarray(x, dtype=float).reshape(-1, 1)
+    # complex stays complex (the multiband Hamiltonians of ThesisProblem.py are complex128)
+    x = np.asarray(x)
+    return x.astype(complex if np.iscomplexobj(x) else float, copy=False).reshape(-1, 1)
 
 
 class Solver:

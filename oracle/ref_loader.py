@@ -13,6 +13,9 @@ Rewrite rules:
   * Python-2 integer `/` -> `//` at MGCMTSolver.py:75-76,81,107-108,134-135,350,394,397
     (the places where the quotient is used as an array size / grid size)
   * `diags([1, -2, 1], ...)` integer literals: left alone (scipy only warns).
+  * PotWellSolver.py:151-152,177-178: the float slice bounds `np.floor(...)` produce are wrapped in
+    `int()` (old numpy accepted float indices); `from pylab import *` is served by a stub module that
+    re-exports numpy (+ `np`, `math`, `numpy.linalg`'s eigh/eigvalsh) because matplotlib is absent.
 """
 from __future__ import annotations
 
@@ -39,7 +42,13 @@ _INT_DIV_LINES = {
         350: [("(n/2)", "(n//2)")],
         394: [("n / 2", "n // 2")],
         397: [("n / 4", "n // 4")],
-    }
+    },
+    "PotWellSolver.py": {
+        151: [("0:self.potWellBoundary1", "0:int(self.potWellBoundary1)")],
+        152: [("self.potWellBoundary2:", "int(self.potWellBoundary2):")],
+        177: [("0:self.potWellBoundary1", "0:int(self.potWellBoundary1)")],
+        178: [("self.potWellBoundary2:", "int(self.potWellBoundary2):")],
+    },
 }
 
 
@@ -82,3 +91,34 @@ def load_reference():
     return (mods["MGCMTStencilMaker"].MGCMTStencilMaker,
             mods["MGCMTSolver"].MGCMTSolver,
             mods["MGCMTProcessor"].MGCMTProcessor)
+
+
+def _exec_module(name):
+    fn = name + ".py"
+    with open(os.path.join(REFERENCE_ROOT, fn), "r") as fh:
+        src = _translate(fn, fh.read())
+    mod = types.ModuleType(name)
+    mod.__file__ = os.path.join(REFERENCE_ROOT, fn)
+    sys.modules[name] = mod
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec(compile(src, mod.__file__, "exec"), mod.__dict__)
+    return mod
+
+
+def load_potwell():
+    """Return the reference's (baseCompounds, PotentialWell, PotWellSolver) modules -- the multiband
+    Hamiltonian builder ThesisProblem.py:26-40 drives (PotWellSolver.makeMatrix, PotWellSolver.py:54-233)."""
+    if not available():
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    if "pylab" not in sys.modules:
+        import math
+        import numpy
+        stub = types.ModuleType("pylab")
+        stub.__dict__.update({k: getattr(numpy, k) for k in dir(numpy) if not k.startswith("_")})
+        stub.np = numpy
+        stub.math = math
+        stub.eigh = numpy.linalg.eigh
+        stub.eigvalsh = numpy.linalg.eigvalsh
+        sys.modules["pylab"] = stub
+    return tuple(_exec_module(n) for n in ("baseCompounds", "PotentialWell", "PotWellSolver"))

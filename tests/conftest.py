@@ -21,3 +21,13 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     return np.load(GOLDEN)
+
+
+MULTIBAND = os.path.join(ROOT, "tests", "golden", "multiband_golden.npz")
+
+
+@pytest.fixture(scope="session")
+def multiband():
+    """Outputs of the REAL reference on its own 4-band Hamiltonians (oracle/make_golden_multiband.py)."""
+    import numpy as np
+    return np.load(MULTIBAND)

@@ -741,3 +741,181 @@ def test_slab_lockstep_block_equals_separate_cycles(T, prod):
     finally:
         for sv in svs:
             sv.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# banded complex operators: the multiband Hamiltonians of ThesisProblem.py (goldens from the REAL reference,
+# oracle/make_golden_multiband.py)
+MB_TAGS = ("z0", "z7", "x7")
+
+
+def crel(a, b):
+    a = np.asarray(a).reshape(-1)
+    b = np.asarray(b).reshape(-1)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def cdev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a, dtype=np.complex128)).cuda()
+
+
+def mb_case(multiband, tag):
+    H = sp.csc_matrix(multiband[tag + "_H"])
+    return H, H.shape[0], float(multiband[tag + "_shift"]), multiband[tag + "_x"], multiband[tag + "_f"]
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_banded_galerkin_levels(T, o, multiband, tag):
+    from multigridcmt_b200.banded import BandedHierarchy, BandedOperator
+    H, n, _, _, _ = mb_case(multiband, tag)
+    h = BandedHierarchy(BandedOperator.from_sparse(H), 8)
+    assert h.num_levels == 6
+    mats, _, _ = oracle_levels(o, H, n, "1d", h.num_levels)
+    assert abs(h.level_operator(0).tocsc() - H).max() == 0
+    A1 = h.level_operator(1).tocsc().toarray()
+    assert np.max(np.abs(A1 - multiband[tag + "_RAP"])) <= 1e-13 * np.max(np.abs(A1))
+    for l in range(1, h.num_levels):
+        A = h.level_operator(l).tocsc().toarray()
+        ref = mats[l].toarray()
+        assert np.max(np.abs(A - ref)) <= 1e-12 * np.max(np.abs(ref)), l
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_banded_single_level_ops(T, o, multiband, tag):
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.banded import BandedHierarchy, BandedOperator
+    H, n, shift, x, f = mb_case(multiband, tag)
+    h = BandedHierarchy(BandedOperator.from_sparse(H), 32)
+    mats, Rs, Ps = oracle_levels(o, H, n, "1d", h.num_levels)
+    xd, fd = cdev(T, x), cdev(T, f)
+    y = T.empty_like(xd)
+    h.apply(0, 0.0, xd, y)
+    assert crel(y.cpu().numpy(), multiband[tag + "_Hx"]) < RTOL
+    for l in range(h.num_levels - 1):
+        nl = n >> l
+        xl, fl = cdev(T, x[:nl]), cdev(T, f[:nl])
+        As = mats[l] - sp.eye(nl) * shift
+        h.apply(l, shift, xl, y[:nl])
+        assert crel(y[:nl].cpu().numpy(), As @ x[:nl]) < RTOL
+        rc = T.empty(nl // 2, dtype=T.complex128, device="cuda")
+        h.residual_restrict(l, shift, xl, fl, rc)
+        assert crel(rc.cpu().numpy(), Rs[l] @ (f[:nl] - As @ x[:nl])) < RTOL
+        v = xl.clone()
+        ec = cdev(T, f[:nl // 2])
+        h.prolong_correct(l, ec, v)
+        assert crel(v.cpu().numpy(), x[:nl] + Ps[l] @ f[:nl // 2]) < RTOL
+    nc = n >> (h.num_levels - 1)
+    assert nc == 32
+    Ac = (mats[-1] - sp.eye(nc) * shift).toarray()
+    out = T.empty(nc, dtype=T.complex128, device="cuda")
+    h.coarse_solve(shift, cdev(T, f[:nc]), out)
+    assert crel(out.cpu().numpy(), np.linalg.solve(Ac, f[:nc])) < 1e-10
+    # smoothers at level 0 with the shift applied by the kernel
+    for code, omega, key in ((_lib.SMOOTH_WJACOBI, 2. / 3., "_wj"), (_lib.SMOOTH_GSLEX, 1.0, "_gs"),
+                             (_lib.SMOOTH_GSLEX, 1.3, "_sor")):
+        v = xd.clone()
+        h.smooth(0, code, 3, shift, omega, v, fd)
+        assert crel(v.cpu().numpy(), multiband[tag + key]) < RTOL, key
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_banded_smoothers_through_solver(prod, multiband, tag):
+    """the reference's call: solver.gseidel(v0, f, shifted_matrix) with a complex scipy matrix"""
+    _, solver, _ = prod
+    H, n, shift, x, f = mb_case(multiband, tag)
+    As = (H - sp.eye(n) * shift).tocsc()
+    out = solver.wjacobi(x.copy(), f.copy(), As, nu=3)
+    assert out.shape == (n, 1) and np.iscomplexobj(out)
+    assert crel(out, multiband[tag + "_wj"]) < RTOL
+    assert crel(solver.gseidel(x.copy().reshape(n, 1), f.copy().reshape(n, 1), As, nu=3), multiband[tag + "_gs"]) < RTOL
+    assert crel(solver.sor(x.copy().reshape(n, 1), f.copy().reshape(n, 1), As, nu=3, omega=1.3),
+                multiband[tag + "_sor"]) < RTOL
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_banded_vcycles_match_reference(prod, multiband, tag):
+    import functools
+    sm, solver, _ = prod
+    H, n, shift, x, f = mb_case(multiband, tag)
+    for sname, smo in (("wj", None), ("gs", solver.gseidel), ("sor", functools.partial(solver.sor, omega=1.3))):
+        for low in (32, 8):
+            w = solver.vcycle(np.zeros((n, 1)), f.copy(), H, sm, shift=shift, lowest_level=low, smoother=smo)
+            assert w.shape == (n,)
+            assert crel(w, multiband["%s_vc_%s_%d" % (tag, sname, low)]) < 1e-10, (sname, low)
+    w = solver.vcycle(x.copy(), f.copy(), H, sm, nu1=2, nu2=3, shift=shift, lowest_level=16, smoother=solver.gseidel)
+    assert crel(w, multiband[tag + "_vc_gs_x0"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_banded_shift_iteration_matches_reference(prod, multiband, tag):
+    """the loop of ThesisProblem.py:84-104, verbatim, on the drop-in classes"""
+    sm, solver, _ = prod
+    H, n, shift, _, f = mb_case(multiband, tag)
+    v = f / np.linalg.norm(f)
+    w0 = np.zeros((n, 1))
+    lam = []
+    for _ in range(4):
+        w = solver.vcycle(w0, v, H, sm, shift=shift, lowest_level=2 ** 5, smoother=solver.gseidel)
+        v = w / np.linalg.norm(w)
+        lam.append(np.dot(v.conj().T, H.dot(v)))
+    assert np.max(np.abs(np.array(lam) - multiband[tag + "_it_lam"])) < 1e-9
+    assert crel(v, multiband[tag + "_it_v"]) < 1e-8
+
+
+def test_banded_real_operator_stays_real(prod, o, multiband):
+    """a real 1-D operator with more than three diagonals (here: the coarse operator of the k=0 well plus a
+    second-neighbour coupling) and real vectors comes back real, like numpy arithmetic would"""
+    sm, solver, _ = prod
+    osm, osolver, _ = o
+    n = 256
+    H = sp.csc_matrix(multiband["z0_H"].real) + 0.05 * sp.diags([np.ones(n - 2), np.ones(n - 2)], [-2, 2])
+    H = sp.csc_matrix(H)
+    f = rand(n, 5) - 0.5
+    shift = float(multiband["z0_shift"])
+    w = solver.vcycle(np.zeros(n), f.copy(), H, sm, shift=shift, lowest_level=16, smoother=solver.gseidel)
+    ref = osolver.vcycle(np.zeros(n), f.copy(), H, osm, shift=shift, lowest_level=16, smoother=osolver.gseidel)
+    assert w.dtype == np.float64 and w.shape == (n,)
+    assert crel(w, ref) < 1e-10
+
+
+@pytest.mark.parametrize("smoother", ["wj", "gs"])
+def test_banded_large_against_oracle(prod, o, multiband, smoother):
+    """4 bands x 2048 points = 8192 unknowns, built like PotWellSolver.makeMatrix does (tridiagonal blocks,
+    complex couplings), 9 levels down to 32"""
+    sm, solver, _ = prod
+    osm, osolver, _ = o
+    g = 2048
+    r = np.random.RandomState(11)
+
+    def tri(d, e):
+        return sp.diags([np.full(g - 1, e), np.full(g, d), np.full(g - 1, np.conj(e))], [-1, 0, 1], format="csc")
+    step = 2.0 / g
+    P = tri(6.85 * 2 / step ** 2 / np.pi ** 2, -6.85 / step ** 2 / np.pi ** 2)
+    Q = tri(2.1 * 2 / step ** 2 / np.pi ** 2, -2.1 / step ** 2 / np.pi ** 2)
+    S = tri(0.0, 0.3j / step)
+    Rm = sp.diags([np.full(g, -0.2 + 0.1j)], [0], format="csc")
+    V = sp.diags([np.where(np.abs(np.linspace(-1, 1, g)) > 0.5, 40.0, 0.0)], [0], format="csc")
+    Z = sp.csc_matrix((g, g))
+    H = sp.bmat([[P + Q + V, -S, Rm, Z], [-S.conj().T, P - Q + V, Z, Rm], [Rm.conj().T, Z, P - Q + V, S],
+                 [Z, Rm.conj().T, S.conj().T, P + Q + V]], format="csc")
+    n = 4 * g
+    f = (r.random_sample(n) - 0.5) + 1j * (r.random_sample(n) - 0.5)
+    shift = 3.0
+    smo, osmo = (None, None) if smoother == "wj" else (solver.gseidel, osolver.gseidel)
+    w = solver.vcycle(np.zeros(n), f.copy(), H, sm, shift=shift, lowest_level=32, smoother=smo)
+    ref = osolver.vcycle(np.zeros(n), f.copy(), H, osm, shift=shift, lowest_level=32, smoother=osmo)
+    assert crel(w, ref) < 1e-9
+
+
+def test_banded_refusals(prod, multiband, capsys):
+    from multigridcmt_b200 import _lib
+    sm, solver, _ = prod
+    H, n, shift, x, f = mb_case(multiband, "z7")
+    with pytest.raises(NotImplementedError):
+        solver.vcycle(np.zeros(n), f.copy(), H, sm, shift=shift, lowest_level=32, smoother=solver.rbgs)
+    assert solver.vcycle(np.zeros(n), f.copy(), H, sm, shift=shift, lowest_level=48) is None
+    assert "power of 2" in capsys.readouterr().out
+    # a singular coarsest operator is reported, not returned as garbage
+    Z = sp.csc_matrix((64, 64), dtype=complex)
+    with pytest.raises(_lib.MgcmtError):
+        solver.vcycle(np.zeros(64), np.ones(64, dtype=complex), Z + 0 * sp.eye(64, dtype=complex), sm, lowest_level=8)

@@ -150,3 +150,56 @@ def test_reference_arm_json_contract():
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# banded (multiband complex) operators: host-side storage and routing
+def test_banded_operator_round_trip(multiband):
+    import scipy.sparse as sp
+    from multigridcmt_b200.banded import BandedOperator
+    for tag, ndiag, real in (("z0", 3, True), ("z7", 9, False), ("x7", 13, False)):
+        H = sp.csc_matrix(multiband[tag + "_H"])
+        op = BandedOperator.from_sparse(H)
+        assert len(op.offsets) == ndiag and op.is_real == real and 0 in op.offsets
+        assert np.all(np.diff(op.offsets) > 0)
+        assert abs(op.tocsc() - H).max() == 0
+        assert np.array_equal(op.diagonal(), H.diagonal())
+        # entries that fall outside the matrix are stored as zeros
+        for k, off in enumerate(op.offsets):
+            i = np.arange(op.n)
+            assert not np.any(op.vals[k, (i + off < 0) | (i + off >= op.n)])
+
+
+def test_banded_operator_limits():
+    import scipy.sparse as sp
+    from multigridcmt_b200.banded import BandedOperator
+    from multigridcmt_b200.operators import UnsupportedOperator
+    dense = sp.csc_matrix(np.ones((128, 128)))
+    with pytest.raises(UnsupportedOperator):
+        BandedOperator.from_sparse(dense)
+    with pytest.raises(UnsupportedOperator):
+        BandedOperator.from_sparse(sp.csc_matrix(np.ones((4, 5))))
+    # a matrix without a stored main diagonal still gets offset 0
+    op = BandedOperator.from_sparse(sp.diags([np.ones(7)], [1], shape=(8, 8), format="csc"))
+    assert list(op.offsets) == [0, 1]
+
+
+def test_routing_picks_the_banded_path(multiband):
+    """real separable stencils -> fused path; complex / wide 1-D operators and complex vectors -> banded path"""
+    import scipy.sparse as sp
+    from multigridcmt_b200 import MGCMTSolver, MGCMTStencilMaker
+    from multigridcmt_b200.banded import BandedOperator
+    from multigridcmt_b200.operators import SeparableOperator, UnsupportedOperator
+    route = MGCMTSolver._route
+    L = MGCMTStencilMaker().laplacian(64)
+    x = np.zeros(64)
+    assert isinstance(route(L, "1d", x, x), SeparableOperator)
+    assert isinstance(route(L, "1d", x, x.astype(complex)), BandedOperator)
+    assert isinstance(route(sp.csc_matrix(multiband["z7_H"]), "1d", x, x), BandedOperator)
+    assert isinstance(route(sp.csc_matrix(multiband["z0_H"]), "1d", x, x), BandedOperator)   # complex dtype
+    penta = sp.diags([np.ones(62), np.ones(64), np.ones(62)], [-2, 0, 2], format="csc")
+    assert isinstance(route(penta, "1d", x, x), BandedOperator)
+    L2 = MGCMTStencilMaker().laplacian(8, dimension="2d")
+    with pytest.raises(UnsupportedOperator):
+        route(L2, "2d", np.zeros(64), np.zeros(64, dtype=complex))
+    assert MGCMTSolver._guess_dimension(sp.csc_matrix(multiband["z7_H"]), 256) == "1d"

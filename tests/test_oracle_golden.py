@@ -229,3 +229,60 @@ def test_closed_form_spectrum(o):
     H = (-1. / np.pi ** 2) * sm.laplacian(16, "2d")
     v = orc.well_eigenvector_2d(16, 1, 2)
     assert np.linalg.norm(H @ v - orc.well_eigenvalue_2d(16, 1, 2) * v) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------
+# multiband (complex, 4 coupled bands) Hamiltonians: ThesisProblem.py / PotWellSolver.makeMatrix
+MB_TAGS = ("z0", "z7", "x7")
+
+
+def _mb(multiband, tag):
+    import scipy.sparse as sp
+    H = sp.csc_matrix(multiband[tag + "_H"])
+    return H, H.shape[0], float(multiband[tag + "_shift"]), multiband[tag + "_x"], multiband[tag + "_f"]
+
+
+def _crel(a, b):
+    a = np.asarray(a).reshape(-1)
+    b = np.asarray(b).reshape(-1)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_multiband_smoothers_match_reference(o, multiband, tag):
+    import scipy.sparse as sp
+    _, s, _ = o
+    H, n, shift, x, f = _mb(multiband, tag)
+    As = (H - sp.eye(n) * shift).tocsc()
+    assert _crel(s.wjacobi(x.copy(), f.copy(), As, nu=3), multiband[tag + "_wj"]) < 1e-13
+    assert _crel(s.gseidel(x.copy(), f.copy(), As, nu=3), multiband[tag + "_gs"]) < 1e-13
+    assert _crel(s.sor(x.copy(), f.copy(), As, nu=3, omega=1.3), multiband[tag + "_sor"]) < 1e-13
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_multiband_vcycles_match_reference(o, multiband, tag):
+    import functools
+    sm, s, _ = o
+    H, n, shift, x, f = _mb(multiband, tag)
+    for sname, smo in (("wj", None), ("gs", s.gseidel), ("sor", functools.partial(s.sor, omega=1.3))):
+        for low in (32, 8):
+            w = s.vcycle(np.zeros((n, 1)), f.copy(), H, sm, shift=shift, lowest_level=low, smoother=smo)
+            assert _crel(w, multiband["%s_vc_%s_%d" % (tag, sname, low)]) < 1e-12, (sname, low)
+    w = s.vcycle(x.copy(), f.copy(), H, sm, nu1=2, nu2=3, shift=shift, lowest_level=16, smoother=s.gseidel)
+    assert _crel(w, multiband[tag + "_vc_gs_x0"]) < 1e-12
+
+
+@pytest.mark.parametrize("tag", MB_TAGS)
+def test_multiband_shift_iteration_matches_reference(o, multiband, tag):
+    """ThesisProblem.py:84-104: fixed-shift inverse iteration with V-cycles, Rayleigh quotient after each."""
+    sm, s, _ = o
+    H, n, shift, _, f = _mb(multiband, tag)
+    v = f / np.linalg.norm(f)
+    lam = []
+    for _ in range(4):
+        w = s.vcycle(np.zeros((n, 1)), v.copy(), H, sm, shift=shift, lowest_level=32, smoother=s.gseidel)
+        v = np.asarray(w).reshape(-1)
+        v = v / np.linalg.norm(v)
+        lam.append(np.dot(v.conj(), H.dot(v)))
+    assert np.max(np.abs(np.array(lam) - multiband[tag + "_it_lam"])) < 1e-11
+    assert _crel(v, multiband[tag + "_it_v"]) < 1e-10
