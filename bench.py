@@ -295,49 +295,22 @@ def run_ours(args):
 
     N = args.n or 4096
     lowest = args.lowest
-    smoother_code = _lib.SMOOTH_WJACOBI if args.smoother == "wjacobi" else _lib.SMOOTH_RBGS
-    omega = 2.0 / 3.0 if args.smoother == "wjacobi" else 1.0
     n = N * N
     H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
-    h = get_hierarchy(H, lowest)
     V_host, shifts = initial_block(N)
     k = len(MODES)
-    # The k eigenvectors of a step are independent until the Gram-Schmidt: each gets its own CUDA stream and its own
-    # hierarchy (level work vectors), so the latency-bound coarse levels of one cycle overlap the HBM-bound fine
-    # levels of another.
-    from multigridcmt_b200.hierarchy import Hierarchy
-    nstreams = max(1, min(args.streams, k))
-    hs = [h] + [Hierarchy(H, lowest) for _ in range(nstreams - 1)]
-    streams = [torch.cuda.Stream() for _ in range(nstreams)]
-    # replicas: with N ranks every rank runs the same independent block (data-parallel over problems);
-    # the path has no exchange step at this problem size.  (Slab decomposition of 16384^2: later round.)
-    blocks = [torch.from_numpy(V_host).cuda(), None]   # (k, n) vector-major blocks, resident in HBM
-    blocks[1] = torch.zeros_like(blocks[0])
-    cur = [0]                                          # blocks[cur] = V (input), blocks[1 - cur] = W (output)
-    rq = torch.zeros(k, 2, dtype=torch.float64, device="cuda")
-    ortho_mode = 2 if args.ortho == "gram" else 1
-
-    def step(serial=False):
-        nonlocal smoother_code, omega
-        V, W = blocks[cur[0]], blocks[1 - cur[0]]
-        main = torch.cuda.current_stream()
-        if not serial:
-            for st_ in streams:
-                st_.wait_stream(main)
-        for c in range(k):
-            hc = hs[c % nstreams]   # (each hierarchy has the coarse inverse of its own shift cached)
-            with torch.cuda.stream(main if serial else streams[c % nstreams]):
-                sp = _stream_ptr(torch)
-                # w0 = 0 as in the reference's drivers (2DPotGS.py:94): flagged, so the zero vector is not read
-                # cycle + Rayleigh quotient w^T H w / w^T w (its sums are taken inside the finest up leg); the
-                # normalisation w/||w|| of 2DPotGS.py:96 is what the orthonormalisation below does to every column anyway
-                _lib.check(lib.mgcmt_vcycle_rq(hc.handle, shifts[c], 4, 4, smoother_code, omega, _ptr(W[c]), _ptr(V[c]), 1,
-                                               _ptr(rq[c]), sp))
-        if not serial:
-            for st_ in streams:
-                main.wait_stream(st_)
-        _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(W), ortho_mode, _stream_ptr(torch)))
-        cur[0] = 1 - cur[0]                            # the orthonormalised block is the next step's input
+    # The timed object is the package's own device-resident outer loop (multigridcmt_b200/eigensolver.py): the k
+    # eigenvectors of a step are independent until the Gram-Schmidt, so each V-cycle gets its own CUDA stream and its
+    # own hierarchy (level work vectors) -- the latency-bound coarse levels of one cycle overlap the HBM-bound fine
+    # levels of another.  With N ranks and --replicas every rank runs the same independent block.
+    from multigridcmt_b200.eigensolver import ShiftMethod
+    loop = ShiftMethod(H, shifts, V_host, dimension="2d", lowest_level=lowest, nu1=4, nu2=4, smoother=args.smoother,
+                       ortho=("gram" if args.ortho == "gram" else "mgs"), streams=args.streams)
+    h = loop.hier[0]
+    nstreams = len(loop.streams)
+    rq = loop.rq
+    ortho_mode = loop.ortho
+    step = loop.step
 
     clocks = Clocks(local)
     if rank == 0:
@@ -349,7 +322,7 @@ def run_ours(args):
     # the Gram-matrix orthonormalisation must reproduce column-by-column MGS on this block (parity bar 1e-12)
     ortho_check = None
     if ortho_mode == 2:
-        A_ = blocks[1 - cur[0]].clone(); B_ = A_.clone()
+        A_ = loop.blocks[1 - loop.cur].clone(); B_ = A_.clone()
         _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(A_), 1, _stream_ptr(torch)))
         _lib.check(lib.mgcmt_gramschmidt(n, k, _ptr(B_), 2, _stream_ptr(torch)))
         ortho_check = float((A_ - B_).norm() / A_.norm())
@@ -393,8 +366,7 @@ def run_ours(args):
     # the other smoother of the path, same step (BASELINE config 3 names red-black Gauss-Seidel): a short side run
     other = None
     if world == 1 and args.smoother == "wjacobi":
-        keep = (smoother_code, omega)
-        smoother_code, omega = _lib.SMOOTH_RBGS, 1.0
+        loop.set_smoother("rbgs")
         for _ in range(3):
             step()
         torch.cuda.synchronize()
@@ -409,7 +381,7 @@ def run_ours(args):
         other = {"smoother": "rbgs (four-colour = red-black on the 5-point level, omega = 1)", "ms_per_step": ms_o,
                  "vcycles_per_s": k / (ms_o * 1e-3), "value": k * updates_per_cycle(N, lowest) / (ms_o * 1e-3),
                  "eigenvalues": lam_o}
-        smoother_code, omega = keep
+        loop.set_smoother(args.smoother)
     clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -632,6 +604,7 @@ def run_slab(args):
     e0.record()
     run(args.steps)
     e1.record()
+    host_issue_ms = (time.time() - t_begin) * 1e3 / args.steps   # CPU time to enqueue a step (no sync inside)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     t_end = time.time()
     ms = e0.elapsed_time(e1)
@@ -684,7 +657,7 @@ def run_slab(args):
                        "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": sv.nlev, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
                        "replicated_from": "%d^2" % (N >> sv.nlev), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
                        "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9)},
-            "vcycles_per_s": k * args.steps / (ms * 1e-3),
+            "vcycles_per_s": k * args.steps / (ms * 1e-3), "host_issue_ms_per_step": host_issue_ms,
             "eigenvalues": lam_h, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam_h, exact)],
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,
             "roofline": {"bound": "hbm", "achieved": 304.0 * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world, "peak": peak,

@@ -237,6 +237,36 @@ int mgcmt_band_coarse_solve(mgcmt_band_t *h, double shift, const double *d_f, do
 int mgcmt_band_vcycle(mgcmt_band_t *h, double shift, int nu1, int nu2, int smoother, double omega, double *d_v,
                       const double *d_f, void *stream);
 
+/* ---- slab block: the multi-GPU step driven natively ------------------------------------------------------------
+ * No counterpart in the reference (it has no parallelism).  multigridcmt_b200/slab.py defines the row-slab
+ * decomposition and drives it from Python over torch.distributed; these entry points issue
+ * the same kernels and exchanges from C++ with NCCL called directly, because at 8 GPUs the Python issue time of a step
+ * is as long as the step.  NCCL is looked up at run time in the library the process already loaded (PyTorch's):
+ * mgcmt_nccl_load(path or NULL); rank 0 makes an id (128 bytes) that the caller broadcasts; every rank creates its
+ * communicator from it.  One rank per GPU; all ranks must make the same calls in the same order. */
+typedef struct mgcmt_slabblock mgcmt_slabblock_t;
+int mgcmt_nccl_load(const char *path);
+int mgcmt_nccl_unique_id(void *out128);
+int mgcmt_nccl_comm_create(const void *id128, int world, int rank, void **out_comm);
+int mgcmt_nccl_comm_destroy(void *comm);
+/* k vectors of an n x n grid, rows [rank n/world, (rank+1) n/world) + 6 halo rows on both sides on this rank;
+ * levels 0..nlev_slab-1 stay decomposed, coarser ones are replicated after an all-gather.  Coefficient arrays as in
+ * mgcmt_hier_create (host, length n).  comm may be NULL when world == 1. */
+int mgcmt_slabblock_create(void *comm, int world, int rank, int n, int nlev_slab, int lowest_level, int k,
+                           const double *h_row_lo, const double *h_row_di, const double *h_row_up,
+                           const double *h_col_lo, const double *h_col_di, const double *h_col_up, double omega,
+                           void *stream, mgcmt_slabblock_t **out);
+int mgcmt_slabblock_destroy(mgcmt_slabblock_t *b);
+/* k V(4,4) weighted-Jacobi cycles in lock-step, zero start: (H - h_shifts[c]) w = f_c; h_f0[c] / h_v0[c] are device
+ * pointers to finest-level slab arrays ((n/world + 12) x n doubles; owned rows of f in, owned rows of w out, halo rows
+ * are scratch).  d_lam != NULL: d_lam[2c], d_lam[2c+1] = w_c^T H w_c, w_c^T w_c, summed over all ranks.
+ * (the drivers' loop body, 2DPotGS.py:93-103, for all k vectors) */
+int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *const *h_f0, double *const *h_v0,
+                          double *d_lam, void *stream);
+/* orthonormalise the k slab vectors d_block + c*stride (Gram-matrix form of MGCMTProcessor.gramschmidt: local packed
+ * Gram matrix of the owned rows, one all-reduce, Q = W R^-1 locally) */
+int mgcmt_slabblock_gram(mgcmt_slabblock_t *b, double *d_block, long long stride, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,361 @@
+// slab_block.cu -- native driver of the row-slab multi-GPU step (include/mgcmt_b200.h, "slab block").
+//
+// multigridcmt_b200/slab.py states the decomposition and drives it from Python over torch.distributed; that is the
+// testable reference of the host logic (gloo / single-process emulation), but at 8 GPUs a step is ~100 launches and
+// ~12 exchange phases in ~4 ms, and the Python issue time alone is that long.  This file issues the same sequence --
+// the same kernels through the same C entry points, in the same order -- from C++: k V(4,4) cycles advanced in
+// lock-step (each on its own stream, forked from / joined to the caller's stream around every phase), one NCCL group of
+// send/recv pairs per halo phase for all k vectors, in-place all-gather of the restricted residuals before the
+// replicated coarse part, all-reduce of the Rayleigh sums and of the packed Gram matrix.
+//
+// NCCL is reached through dlopen/dlsym on the library the process already has (the one PyTorch bundles), so this
+// shared object has no link-time dependency on it and loads on machines without NCCL.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mgcmt_b200.h"
+#include "kernels.h"
+
+using namespace mgcmt;
+
+namespace {
+
+// the slice of nccl.h this file uses (NCCL 2.x ABI: ncclUniqueId is 128 bytes, ncclFloat64 = 8, ncclSum = 0)
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+struct Nccl {
+  void *lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+} g_nccl;
+
+#define CU(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return set_error(MGCMT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+  } while (0)
+#define NC(expr)                                                                                      \
+  do {                                                                                                \
+    int r__ = (expr);                                                                                 \
+    if (r__ != 0)                                                                                     \
+      return set_error(MGCMT_ERR_CUDA, std::string(#expr) + ": NCCL error " + std::to_string(r__) +   \
+                                           (g_nccl.GetErrorString ? std::string(" (") + g_nccl.GetErrorString(r__) + ")" : "")); \
+  } while (0)
+#define RC(expr)                 \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != MGCMT_OK) return rc__; \
+  } while (0)
+
+int need_nccl() {
+  if (!g_nccl.lib) return set_error(MGCMT_ERR_STATE, "NCCL is not loaded: call mgcmt_nccl_load first");
+  return MGCMT_OK;
+}
+
+struct VecState {  // one vector of the block: its hierarchies, level buffers, stream
+  mgcmt_hier_t *slab = nullptr, *coarse = nullptr;
+  std::vector<double *> v, f, tmp;  // per slab level; entry 0 of v and f is the caller's array during a cycle
+  double *fg = nullptr, *vg = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+
+}  // namespace
+
+struct mgcmt_slabblock {
+  int world = 1, rank = 0, n = 0, own0 = 0, nlev = 0, k = 0;
+  double omega = 2.0 / 3.0;
+  ncclComm_t comm = nullptr;
+  std::vector<VecState> vec;
+  cudaEvent_t fork = nullptr;
+  double *scal = nullptr;  // 64 doubles
+};
+
+namespace {
+
+constexpr int kHalo = 6;  // multigridcmt_b200/slab.py: HALO
+
+size_t level_elems(const mgcmt_slabblock *b, int l) { return (size_t)((b->own0 >> l) + 2 * kHalo) * (size_t)(b->n >> l); }
+
+int fork_streams(mgcmt_slabblock *b, cudaStream_t main) {
+  CU(cudaEventRecord(b->fork, main));
+  for (VecState &s : b->vec) CU(cudaStreamWaitEvent(s.stream, b->fork, 0));
+  return MGCMT_OK;
+}
+
+int join_streams(mgcmt_slabblock *b, cudaStream_t main) {
+  for (VecState &s : b->vec) {
+    CU(cudaEventRecord(s.done, s.stream));
+    CU(cudaStreamWaitEvent(main, s.done, 0));
+  }
+  return MGCMT_OK;
+}
+
+// halo rows of level-l slab arrays: send the first / last kHalo owned rows to the neighbour above / below and receive
+// its rows into the halo; all arrays of one phase in one NCCL group
+struct HaloItem {
+  double *x;
+  int level;
+};
+int exchange(mgcmt_slabblock *b, const std::vector<HaloItem> &items, cudaStream_t main) {
+  if (b->world == 1) return MGCMT_OK;
+  NC(g_nccl.GroupStart());
+  for (const HaloItem &it : items) {
+    const size_t cols = (size_t)(b->n >> it.level), own = (size_t)(b->own0 >> it.level), cnt = kHalo * cols;
+    double *top_halo = it.x, *top_own = it.x + kHalo * cols, *bot_own = it.x + own * cols, *bot_halo = it.x + (own + kHalo) * cols;
+    if (b->rank > 0) {
+      NC(g_nccl.Send(top_own, cnt, kNcclFloat64, b->rank - 1, b->comm, main));
+      NC(g_nccl.Recv(top_halo, cnt, kNcclFloat64, b->rank - 1, b->comm, main));
+    }
+    if (b->rank + 1 < b->world) {
+      NC(g_nccl.Send(bot_own, cnt, kNcclFloat64, b->rank + 1, b->comm, main));
+      NC(g_nccl.Recv(bot_halo, cnt, kNcclFloat64, b->rank + 1, b->comm, main));
+    }
+  }
+  NC(g_nccl.GroupEnd());
+  return MGCMT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgcmt_nccl_load(const char *path) {
+  if (g_nccl.lib) return MGCMT_OK;
+  const char *name = (path && *path) ? path : "libnccl.so.2";
+  void *lib = dlopen(name, RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+  if (!lib) return set_error(MGCMT_ERR_STATE, std::string("cannot load NCCL (") + name + "): " + dlerror());
+#define SYM(field, sym)                                                                              \
+  do {                                                                                               \
+    *(void **)(&g_nccl.field) = dlsym(lib, sym);                                                     \
+    if (!g_nccl.field) return set_error(MGCMT_ERR_STATE, std::string("NCCL symbol missing: ") + sym); \
+  } while (0)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(AllGather, "ncclAllGather");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = lib;
+  return MGCMT_OK;
+}
+
+int mgcmt_nccl_unique_id(void *out128) {
+  RC(need_nccl());
+  if (!out128) return set_error(MGCMT_ERR_ARG, "null argument");
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(out128, id.internal, sizeof(id.internal));
+  return MGCMT_OK;
+}
+
+int mgcmt_nccl_comm_create(const void *id128, int world, int rank, void **out_comm) {
+  RC(need_nccl());
+  if (!id128 || !out_comm || world < 1 || rank < 0 || rank >= world) return set_error(MGCMT_ERR_ARG, "bad communicator arguments");
+  ncclUniqueId id;
+  memcpy(id.internal, id128, sizeof(id.internal));
+  ncclComm_t comm = nullptr;
+  NC(g_nccl.CommInitRank(&comm, world, id, rank));
+  *out_comm = comm;
+  return MGCMT_OK;
+}
+
+int mgcmt_nccl_comm_destroy(void *comm) {
+  if (!comm) return MGCMT_OK;
+  RC(need_nccl());
+  NC(g_nccl.CommDestroy((ncclComm_t)comm));
+  return MGCMT_OK;
+}
+
+int mgcmt_slabblock_destroy(mgcmt_slabblock_t *b) {
+  if (!b) return MGCMT_OK;
+  for (VecState &s : b->vec) {
+    if (s.slab) mgcmt_hier_destroy(s.slab);
+    if (s.coarse) mgcmt_hier_destroy(s.coarse);
+    for (size_t l = 1; l < s.v.size(); ++l) cudaFree(s.v[l]);
+    for (size_t l = 1; l < s.f.size(); ++l) cudaFree(s.f[l]);
+    for (double *p : s.tmp) cudaFree(p);
+    cudaFree(s.fg);
+    cudaFree(s.vg);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (b->fork) cudaEventDestroy(b->fork);
+  cudaFree(b->scal);
+  delete b;
+  return MGCMT_OK;
+}
+
+int mgcmt_slabblock_create(void *comm, int world, int rank, int n, int nlev_slab, int lowest_level, int k,
+                           const double *row_lo, const double *row_di, const double *row_up, const double *col_lo,
+                           const double *col_di, const double *col_up, double omega, void *stream,
+                           mgcmt_slabblock_t **out) {
+  if (!out) return set_error(MGCMT_ERR_ARG, "null argument");
+  if (world < 1 || rank < 0 || rank >= world || n % world) return set_error(MGCMT_ERR_ARG, "rows must divide evenly among the ranks");
+  if (world > 1 && !comm) return set_error(MGCMT_ERR_ARG, "a communicator is needed for more than one rank");
+  if (k < 1 || k > 16 || nlev_slab < 1) return set_error(MGCMT_ERR_ARG, "need 1 <= k <= 16 vectors and >= 1 slab level");
+  const int own0 = n / world;
+  if (own0 % (1 << nlev_slab) || (own0 >> (nlev_slab - 1)) < 2 * kHalo)
+    return set_error(MGCMT_ERR_ARG, "slab cuts must stay even, and slabs deeper than the halo, on every slab level");
+  mgcmt_slabblock *b = new mgcmt_slabblock();
+  b->world = world; b->rank = rank; b->n = n; b->own0 = own0; b->nlev = nlev_slab; b->k = k; b->omega = omega;
+  b->comm = (ncclComm_t)comm;
+  b->vec.resize(k);
+  auto bail = [&](int rc) {
+    std::string msg = mgcmt_last_error();
+    mgcmt_slabblock_destroy(b);
+    return set_error(rc, msg);
+  };
+#define CUB(expr)                                                                                     \
+  do {                                                                                                \
+    cudaError_t e__ = (expr);                                                                         \
+    if (e__ != cudaSuccess) {                                                                         \
+      set_error(MGCMT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                 \
+      return bail(MGCMT_ERR_CUDA);                                                                    \
+    }                                                                                                 \
+  } while (0)
+  CUB(cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming));
+  CUB(cudaMalloc(&b->scal, sizeof(double) * 64));
+  const size_t ng = (size_t)(n >> nlev_slab) * (size_t)(n >> nlev_slab);
+  for (VecState &s : b->vec) {
+    int rc = mgcmt_hier_create_slab(&s.slab, n, n, rank * own0, own0, nlev_slab, kHalo, row_lo, row_di, row_up, col_lo,
+                                    col_di, col_up, stream);
+    if (rc == MGCMT_OK)
+      rc = mgcmt_hier_create2(&s.coarse, n, n, 1, row_lo, row_di, row_up, col_lo, col_di, col_up, lowest_level, nlev_slab,
+                              stream);
+    if (rc != MGCMT_OK) return bail(rc);
+    s.v.assign(nlev_slab, nullptr);
+    s.f.assign(nlev_slab, nullptr);
+    s.tmp.assign(nlev_slab, nullptr);
+    for (int l = 0; l < nlev_slab; ++l) {
+      const size_t bytes = sizeof(double) * level_elems(b, l);
+      if (l > 0) {
+        CUB(cudaMalloc(&s.v[l], bytes));
+        CUB(cudaMalloc(&s.f[l], bytes));
+        CUB(cudaMemsetAsync(s.v[l], 0, bytes, (cudaStream_t)stream));
+        CUB(cudaMemsetAsync(s.f[l], 0, bytes, (cudaStream_t)stream));
+      }
+      CUB(cudaMalloc(&s.tmp[l], bytes));
+      CUB(cudaMemsetAsync(s.tmp[l], 0, bytes, (cudaStream_t)stream));
+    }
+    CUB(cudaMalloc(&s.fg, sizeof(double) * ng));
+    CUB(cudaMalloc(&s.vg, sizeof(double) * ng));
+    CUB(cudaMemsetAsync(s.fg, 0, sizeof(double) * ng, (cudaStream_t)stream));
+    CUB(cudaMemsetAsync(s.vg, 0, sizeof(double) * ng, (cudaStream_t)stream));
+    CUB(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  CUB(cudaStreamSynchronize((cudaStream_t)stream));
+#undef CUB
+  *out = b;
+  return MGCMT_OK;
+}
+
+int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *const *h_f0, double *const *h_v0,
+                          double *d_lam, void *stream) {
+  if (!b || !h_shifts || !h_f0 || !h_v0) return set_error(MGCMT_ERR_ARG, "null argument");
+  if (b->world > 1) RC(need_nccl());
+  cudaStream_t main = (cudaStream_t)stream;
+  const int k = b->k, nl = b->nlev;
+  for (int c = 0; c < k; ++c) {
+    if (!h_f0[c] || !h_v0[c] || h_f0[c] == h_v0[c]) return set_error(MGCMT_ERR_ARG, "need distinct non-null f and v arrays");
+    b->vec[c].f[0] = h_f0[c];
+    b->vec[c].v[0] = h_v0[c];
+  }
+  std::vector<HaloItem> items;
+  auto all_of = [&](std::vector<double *> VecState::*member, int l, bool append) {
+    if (!append) items.clear();
+    for (VecState &s : b->vec) items.push_back({(s.*member)[l], l});
+  };
+  // down: 4 sweeps + residual + restriction per level (one fused kernel per vector), halos of the new right-hand side
+  all_of(&VecState::f, 0, false);
+  RC(exchange(b, items, main));
+  for (int l = 0; l < nl; ++l) {
+    const bool last = (l + 1 == nl);
+    RC(fork_streams(b, main));
+    for (int c = 0; c < k; ++c) {
+      VecState &s = b->vec[c];
+      RC(mgcmt_fused_leg(s.slab, l, 2 /* down, zero start */, 4, h_shifts[c], b->omega, nullptr, s.f[l], s.tmp[l], nullptr,
+                         last ? s.fg : s.f[l + 1], s.stream));
+    }
+    RC(join_streams(b, main));
+    if (last) {
+      if (b->world > 1) {
+        const size_t cnt = (size_t)(b->own0 >> nl) * (size_t)(b->n >> nl);
+        NC(g_nccl.GroupStart());
+        for (VecState &s : b->vec) NC(g_nccl.AllGather(s.fg + (size_t)b->rank * cnt, s.fg, cnt, kNcclFloat64, b->comm, main));
+        NC(g_nccl.GroupEnd());
+      }
+    } else {
+      all_of(&VecState::f, l + 1, false);
+      RC(exchange(b, items, main));
+    }
+  }
+  // replicated coarse part: every rank runs the same small V-cycle on the gathered residual
+  RC(fork_streams(b, main));
+  for (int c = 0; c < k; ++c) {
+    VecState &s = b->vec[c];
+    RC(mgcmt_vcycle_from(s.coarse, nl, h_shifts[c], MGCMT_SMOOTH_WJACOBI, b->omega, s.vg, s.fg, s.stream));
+  }
+  RC(join_streams(b, main));
+  // up: halos of the smoothed iterate and of the coarse correction, then prolongation + correction + 4 sweeps
+  for (int l = nl - 1; l >= 0; --l) {
+    const bool last = (l + 1 == nl);
+    all_of(&VecState::tmp, l, false);
+    if (!last) all_of(&VecState::v, l + 1, true);
+    RC(exchange(b, items, main));
+    RC(fork_streams(b, main));
+    for (int c = 0; c < k; ++c) {
+      VecState &s = b->vec[c];
+      RC(mgcmt_fused_leg(s.slab, l, 3 /* up */, 4, h_shifts[c], b->omega, s.tmp[l], s.f[l], s.v[l], last ? s.vg : s.v[l + 1],
+                         nullptr, s.stream));
+    }
+    RC(join_streams(b, main));
+  }
+  if (d_lam) {
+    all_of(&VecState::v, 0, false);
+    RC(exchange(b, items, main));
+    RC(fork_streams(b, main));
+    for (int c = 0; c < k; ++c) RC(mgcmt_slab_rayleigh(b->vec[c].slab, 0, b->vec[c].v[0], d_lam + 2 * c, b->vec[c].stream));
+    RC(join_streams(b, main));
+    if (b->world > 1) NC(g_nccl.AllReduce(d_lam, d_lam, (size_t)2 * k, kNcclFloat64, kNcclSum, b->comm, main));
+  }
+  for (VecState &s : b->vec) s.f[0] = s.v[0] = nullptr;
+  return MGCMT_OK;
+}
+
+int mgcmt_slabblock_gram(mgcmt_slabblock_t *b, double *d_block, long long stride, void *stream) {
+  if (!b || !d_block) return set_error(MGCMT_ERR_ARG, "null argument");
+  if (b->world > 1) RC(need_nccl());
+  if (b->k > 6) return set_error(MGCMT_ERR_ARG, "Gram-matrix orthonormalisation takes k <= 6");
+  cudaStream_t main = (cudaStream_t)stream;
+  const long long n_own = (long long)b->own0 * b->n;
+  double *base = d_block + (size_t)kHalo * b->n;   // owned rows of vector 0; vector c is `stride` doubles further
+  RC(mgcmt_gram(n_own, b->k, base, stride, b->scal, stream));
+  if (b->world > 1)
+    NC(g_nccl.AllReduce(b->scal, b->scal, (size_t)(b->k * (b->k + 1) / 2), kNcclFloat64, kNcclSum, b->comm, main));
+  return mgcmt_cholqr_apply(n_own, b->k, base, stride, b->scal, stream);
+}
+
+}  // extern "C"

@@ -453,3 +453,101 @@ def vcycle_block(svs, shifts, f0s, v0s, lam=None, streams=None):
         for sv, sav in zip(svs, saved):
             for st, (f, v) in zip(sv.states, sav):
                 st.f[0], st.v[0] = f, v
+
+
+# ----------------------------------------------------------------------------------------------------
+# the same step issued natively (csrc/slab_block.cu): NCCL called from C++, no Python between the launches
+# ----------------------------------------------------------------------------------------------------
+def _nccl_library_path():
+    """the NCCL shared object this process already mapped (PyTorch's), else the bundled wheel, else the soname"""
+    import os
+    try:
+        with open("/proc/self/maps") as fh:
+            for line in fh:
+                if "libnccl" in line and ".so" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    try:
+        import nvidia.nccl
+        for base in list(getattr(nvidia.nccl, "__path__", [])):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+class NativeSlabBlock:
+    """k slab-decomposed V(4,4) cycles per call, driven from C++ (mgcmt_slabblock_*): the production form of
+    `vcycle_block` + `SlabVCycle.gramschmidt_gram`.  One rank per process; with world > 1 torch.distributed must be
+    initialised (it carries the 128-byte NCCL id from rank 0 to the others, nothing else).  Bit-for-bit the same
+    results as the Python-driven path (same kernels, same order): tools/check_native_slab.py."""
+
+    def __init__(self, op: SeparableOperator, world, rank, k, lowest_level=8, gather_cols=2048, omega=2. / 3.):
+        torch = _lib.require_cuda()
+        lib = _lib.load()
+        if op.nrows != op.ncols:
+            raise ValueError("slab decomposition is for square 2-D grids")
+        self.op, self.world, self.rank, self.k = op, int(world), int(rank), int(k)
+        self.N = op.ncols
+        self.nlev = plan_levels(self.N, world, gather_cols)
+        if self.nlev < 1:
+            raise ValueError("grid too small to decompose over %d ranks (use the single-GPU path)" % world)
+        self.own0 = self.N // world
+        self.begin0 = rank * self.own0
+        self.slab_size = (self.own0 + 2 * HALO) * self.N
+        self.comm = C.c_void_p()
+        self.handle = C.c_void_p()
+        if world > 1:
+            import torch.distributed as dist
+            _lib.check(lib.mgcmt_nccl_load(_nccl_library_path().encode()))
+            ident = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                _lib.check(lib.mgcmt_nccl_unique_id(C.c_void_p(ident.data_ptr())))
+            dev = ident.cuda() if dist.get_backend() == "nccl" else ident
+            dist.broadcast(dev, src=0)
+            ident = dev.cpu()
+            _lib.check(lib.mgcmt_nccl_comm_create(C.c_void_p(ident.data_ptr()), self.world, self.rank, C.byref(self.comm)))
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.mgcmt_slabblock_create(self.comm, self.world, self.rank, self.N, self.nlev, int(lowest_level), self.k,
+                                              hp(op.row[0]), hp(op.row[1]), hp(op.row[2]), hp(op.col[0]), hp(op.col[1]),
+                                              hp(op.col[2]), float(omega), stream, C.byref(self.handle)))
+        self._ptrs = (C.c_void_p * self.k)
+        self._shifts = (C.c_double * self.k)
+
+    def close(self):
+        lib = _lib.load()
+        if getattr(self, "handle", None):
+            lib.mgcmt_slabblock_destroy(self.handle)
+            self.handle = None
+        if getattr(self, "comm", None):
+            lib.mgcmt_nccl_comm_destroy(self.comm)
+            self.comm = None
+
+    def new_block(self):
+        """(k, slab_size) zero tensor: k finest-level slab vectors (owned rows + halos) of this rank"""
+        torch = _lib.require_cuda()
+        return torch.zeros(self.k, self.slab_size, dtype=torch.float64, device="cuda")
+
+    def owned(self, x):
+        """view of the owned rows of one finest-level slab vector"""
+        return x.view(self.own0 + 2 * HALO, self.N)[HALO:HALO + self.own0]
+
+    def cycle(self, shifts, F, W, lam=None):
+        """W[c] <- one V(4,4) cycle on (H - shifts[c]) w = F[c] from a zero start, for all k vectors; lam (k, 2)
+        receives the Rayleigh sums w^T H w, w^T w (all ranks).  Asynchronous on the current stream."""
+        torch = _lib.require_cuda()
+        es = F.shape[1] * 8
+        f0 = self._ptrs(*[F.data_ptr() + c * es for c in range(self.k)])
+        v0 = self._ptrs(*[W.data_ptr() + c * es for c in range(self.k)])
+        _lib.check(_lib.load().mgcmt_slabblock_cycle(self.handle, self._shifts(*[float(s) for s in shifts]), f0, v0,
+                                                     C.c_void_p(lam.data_ptr()) if lam is not None else None,
+                                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def gram(self, W):
+        torch = _lib.require_cuda()
+        _lib.check(_lib.load().mgcmt_slabblock_gram(self.handle, C.c_void_p(W.data_ptr()), W.shape[1],
+                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))

@@ -919,3 +919,112 @@ def test_banded_refusals(prod, multiband, capsys):
     Z = sp.csc_matrix((64, 64), dtype=complex)
     with pytest.raises(_lib.MgcmtError):
         solver.vcycle(np.zeros(64), np.ones(64, dtype=complex), Z + 0 * sp.eye(64, dtype=complex), sm, lowest_level=8)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the device-resident outer loop (eigensolver.ShiftMethod) == the drivers' loop on the reference classes
+@pytest.mark.parametrize("ortho,streams", [("mgs", None), ("mgs", 1), ("gram", 2)])
+def test_shift_method_object_matches_reference_golden(prod, golden, ortho, streams):
+    from multigridcmt_b200.eigensolver import ShiftMethod
+    sm, _, _ = prod
+    N, N0, iters, lowest = [int(x) for x in golden["sh_meta"]]
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
+    loop = ShiftMethod(H, golden["sh_shifts"], golden["sh_V0"].T.copy(), dimension="2d", lowest_level=lowest,
+                       ortho=ortho, streams=streams)
+    lam = loop.iterate(iters)
+    assert np.allclose(lam, golden["sh_lambda"], rtol=1e-10, atol=0)
+    assert np.allclose(loop.last_rayleigh(), golden["sh_lambda"][-1], rtol=1e-10, atol=0)
+    V = loop.vectors()
+    tol = 1e-8 if ortho == "mgs" else 1e-7
+    assert rel(V[:, 0], golden["sh_V"][:, 0]) < tol
+    assert rel(V[:, 3], golden["sh_V"][:, 3]) < tol
+    assert np.max(np.abs(V.T @ V - np.eye(4))) < 1e-12
+    Hd = H.toarray() if hasattr(H, "toarray") else H.tocsc().toarray()
+    assert np.allclose(loop.eigenvalues(), [V[:, c] @ (Hd @ V[:, c]) for c in range(4)], rtol=1e-12)
+    rn = loop.residual_norms()
+    assert np.allclose(rn, [np.linalg.norm(Hd @ V[:, c] - (V[:, c] @ (Hd @ V[:, c])) * V[:, c]) for c in range(4)],
+                       rtol=1e-6, atol=1e-13)
+
+
+def test_shift_method_object_1d_and_start_block(o):
+    """1-D well, closed-form start block (replaces the drivers' eigsh on the coarse grid), Gauss-Seidel smoother;
+    against the same loop on the oracle"""
+    from multigridcmt_b200 import MGCMTStencilMaker
+    from multigridcmt_b200.eigensolver import ShiftMethod, well_eigenvalue_1d, well_start_block
+    osm, osolver, oproc = o
+    N, modes = 256, (1, 2, 3)
+    V0, shifts = well_start_block(N, modes, N0=16, dimension="1d")
+    assert V0.shape == (3, N) and np.allclose(np.linalg.norm(V0, axis=1), 1.0)
+    assert np.allclose(shifts, [well_eigenvalue_1d(16, k) for k in modes])
+    H = (-1. / np.pi ** 2) * MGCMTStencilMaker().laplacian(N)
+    loop = ShiftMethod(H, shifts, V0, dimension="1d", lowest_level=16, smoother="gseidel")
+    lam = loop.iterate(3)
+    V = V0.T.copy()
+    ref = np.zeros((3, 3))
+    for it in range(3):
+        for c in range(3):
+            w = osolver.vcycle(np.zeros(N), V[:, c].copy(), H, osm, shift=shifts[c], lowest_level=16,
+                               smoother=osolver.gseidel)
+            V[:, c] = w / np.linalg.norm(w)
+            ref[it, c] = V[:, c] @ (H @ V[:, c])
+        V = oproc.gramschmidt(V)
+    assert np.allclose(lam, ref, rtol=1e-10, atol=0)
+    assert rel(loop.vectors(), V) < 1e-8
+    assert np.all(np.abs(lam[-1] - [well_eigenvalue_1d(N, k) for k in modes]) < 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# natively driven slab block (csrc/slab_block.cu), one rank: same numbers as the Python-driven slab path and as the
+# undecomposed V-cycle (the NCCL exchanges themselves are checked on 2+ GPUs by tools/check_native_slab.py)
+def test_native_slab_block_single_rank(T, prod):
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    from multigridcmt_b200.slab import HALO, LocalComm, NativeSlabBlock, SlabVCycle, vcycle_block
+    sm, solver, proc = prod
+    N, k = 512, 4
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    shifts = [1.7, 4.3, 4.4, 7.0]
+    nb = NativeSlabBlock(H, 1, 0, k, lowest_level=8, gather_cols=128)
+    assert nb.nlev == 2 and nb.slab_size == (N + 2 * HALO) * N
+    F, W = nb.new_block(), nb.new_block()
+    lam = T.zeros(k, 2, dtype=T.float64, device="cuda")
+    f_host = [rand(N * N, 40 + c) - 0.5 for c in range(k)]
+    for c in range(k):
+        nb.owned(F[c]).copy_(dev(T, f_host[c]).view(N, N))
+    nb.cycle(shifts, F, W, lam)
+    T.cuda.synchronize()
+    # (a) undecomposed cycle through the hierarchy
+    h = get_hierarchy(H, 8)
+    for c in range(k):
+        v = T.zeros(N * N, dtype=T.float64, device="cuda")
+        h.vcycle(shifts[c], 4, 4, _lib.SMOOTH_WJACOBI, 2. / 3., v, dev(T, f_host[c]), v0_is_zero=True)
+        w = nb.owned(W[c]).reshape(-1)
+        assert rel(w.cpu().numpy(), v.cpu().numpy()) < 1e-13
+        out2 = T.zeros(2, dtype=T.float64, device="cuda")
+        h.rayleigh(0, v, out2)
+        assert np.allclose(lam[c].cpu().numpy(), out2.cpu().numpy(), rtol=1e-12)
+    # (b) the Python-driven slab path, same kernels in the same order: identical bits
+    svs = [SlabVCycle(H, 1, LocalComm(1), [0], lowest_level=8, gather_cols=128) for _ in range(k)]
+    F2, W2 = svs[0].new_block(k)[0], svs[0].new_block(k)[0]
+    F2.copy_(F)
+    for c in range(k):     # F's halo rows were refreshed by the cycle; start from the same owned rows only
+        F2[c].zero_()
+        svs[0].states[0].owned(F2[c], 0).copy_(dev(T, f_host[c]).view(N, N))
+    lam2 = T.zeros(k, 2, dtype=T.float64, device="cuda")
+    vcycle_block(svs, shifts, [[F2[c]] for c in range(k)], [[W2[c]] for c in range(k)], lam=[lam2])
+    T.cuda.synchronize()
+    for c in range(k):
+        assert T.equal(nb.owned(W[c]), svs[0].states[0].owned(W2[c], 0))
+    assert T.equal(lam, lam2)
+    # (c) orthonormalisation of the block
+    ref = W.clone()
+    nb.gram(W)
+    svs[0].gramschmidt_gram([ref])
+    T.cuda.synchronize()
+    for c in range(k):
+        assert T.equal(nb.owned(W[c]), nb.owned(ref[c]))
+    Q = T.stack([nb.owned(W[c]).reshape(-1) for c in range(k)])
+    assert float((Q @ Q.t() - T.eye(k, dtype=T.float64, device="cuda")).abs().max()) < 1e-12
+    for sv in svs:
+        sv.close()
+    nb.close()
