@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--replicas", action="store_true", help="multi-GPU: independent replicas instead of row slabs")
     ap.add_argument("--gather-cols", type=int, default=512, help="slab path: levels at most this wide are replicated")
+    ap.add_argument("--slab-driver", choices=["native", "python"], default="native",
+                    help="slab path: step issued from C++ with NCCL called directly (csrc/slab_block.cu), or from Python over torch.distributed")
     return ap.parse_args()
 
 
@@ -286,6 +288,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from multigridcmt_b200 import MGCMTProcessor, MGCMTSolver, MGCMTStencilMaker, _lib
@@ -533,6 +537,8 @@ def run_slab(args):
     import torch.distributed as dist
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: stdout carries ONE JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from multigridcmt_b200 import MGCMTStencilMaker, _lib
     from multigridcmt_b200.slab import HALO, SlabVCycle, TorchDistComm
@@ -542,47 +548,70 @@ def run_slab(args):
     k = len(MODES)
     sm = MGCMTStencilMaker()
     H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
-    comm = TorchDistComm()
-    # one solver state (level buffers) per CUDA stream: the 4 independent V-cycles of a step overlap each other's
-    # halo exchanges and replicated coarse parts
-    nstreams = max(1, min(args.streams, k))
-    svs = [SlabVCycle(H, world, comm, [rank], lowest_level=lowest, gather_cols=args.gather_cols) for _ in range(nstreams)]
-    streams = [torch.cuda.Stream() for _ in range(nstreams)]
-    sv = svs[0]
-    st = sv.states[0]
-    own, begin = st.own0, st.begin0
+    native = (args.slab_driver == "native" and args.ortho == "gram")
     P = interp1(N)
     shifts = [ev1(N0, a) + ev1(N0, b) for a, b in MODES]
-    Vb, Wb = sv.new_block(k)[0], sv.new_block(k)[0]       # (k, slab_size) blocks in slab layout
-    V = [[Vb[c]] for c in range(k)]                       # V[c][0] = this rank's slab array of vector c
-    W = [[Wb[c]] for c in range(k)]
-    bd = {"V": Vb, "W": Wb}
+    lam = torch.zeros(k, 2, dtype=torch.float64, device="cuda")
+    svs = []
+    if native:
+        # the whole step is two C calls: k lock-step cycles (+ Rayleigh sums) and the Gram-form orthonormalisation
+        from multigridcmt_b200.slab import NativeSlabBlock
+        nb = NativeSlabBlock(H, world, rank, k, lowest_level=lowest, gather_cols=args.gather_cols)
+        own, begin, nlev_slab, lockstep = nb.own0, nb.begin0, nb.nlev, True
+        owned = nb.owned
+        bd = {"V": nb.new_block(), "W": nb.new_block()}
+
+        def step():
+            nb.cycle(shifts, bd["V"], bd["W"], lam)
+            nb.gram(bd["W"])
+            bd["V"], bd["W"] = bd["W"], bd["V"]
+
+        def one_cycle_all():      # e2e: the k cycles of a step without the orthonormalisation
+            nb.cycle(shifts, bd["V"], bd["W"], None)
+    else:
+        comm = TorchDistComm()
+        # one solver state (level buffers) per CUDA stream: the 4 independent V-cycles of a step overlap each other's
+        # halo exchanges and replicated coarse parts
+        nstreams = max(1, min(args.streams, k))
+        svs = [SlabVCycle(H, world, comm, [rank], lowest_level=lowest, gather_cols=args.gather_cols) for _ in range(nstreams)]
+        streams = [torch.cuda.Stream() for _ in range(nstreams)]
+        sv = svs[0]
+        st = sv.states[0]
+        own, begin, nlev_slab = st.own0, st.begin0, sv.nlev
+        owned = lambda x: st.owned(x, 0)
+        bd = {"V": sv.new_block(k)[0], "W": sv.new_block(k)[0]}       # (k, slab_size) blocks in slab layout
+        from multigridcmt_b200.slab import vcycle_block
+        lockstep = (nstreams == k)
+
+        def cycles(with_lam):
+            V = [[bd["V"][c]] for c in range(k)]
+            W = [[bd["W"][c]] for c in range(k)]
+            if lockstep:
+                # the k cycles advance level by level together: every halo-exchange phase is one NCCL group for all k
+                vcycle_block(svs, shifts, V, W, lam=[lam] if with_lam else None, streams=streams)
+            else:
+                for c in range(k):
+                    svc = svs[c % nstreams]
+                    svc.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
+                    if with_lam:
+                        svc.rayleigh(W[c], sync=False)
+                        lam[c].copy_(svc.states[0].scal[:2])
+            return W
+
+        def step():
+            W = cycles(True)
+            if args.ortho == "gram":
+                sv.gramschmidt_gram([bd["W"]])
+            else:
+                sv.gramschmidt(W)
+            bd["V"], bd["W"] = bd["W"], bd["V"]
+
+        def one_cycle_all():
+            cycles(False)
     for c, (a, b) in enumerate(MODES):
         ya, yb = P @ vec1(N0, a), P @ vec1(N0, b)
         blk = np.outer(ya[begin:begin + own], yb) / (np.linalg.norm(ya) * np.linalg.norm(yb))
-        st.owned(V[c][0], 0).copy_(torch.from_numpy(blk).cuda())
-    lam = torch.zeros(k, 2, dtype=torch.float64, device="cuda")
-
-    from multigridcmt_b200.slab import vcycle_block
-    lockstep = (nstreams == k)
-
-    def step():
-        if lockstep:
-            # the k cycles advance level by level together: every halo-exchange phase is one NCCL group for all k
-            vcycle_block(svs, shifts, V, W, lam=[lam], streams=streams)
-        else:
-            for c in range(k):
-                svc = svs[c % nstreams]
-                svc.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
-                svc.rayleigh(W[c], sync=False)
-                lam[c].copy_(svc.states[0].scal[:2])
-        if args.ortho == "gram":
-            sv.gramschmidt_gram([bd["W"]])
-        else:
-            sv.gramschmidt(W)
-        bd["V"], bd["W"] = bd["W"], bd["V"]
-        for c in range(k):
-            V[c], W[c] = W[c], V[c]
+        owned(bd["V"][c]).copy_(torch.from_numpy(blk).cuda())
 
     clocks = Clocks(local)
     if rank == 0:
@@ -621,15 +650,17 @@ def run_slab(args):
     # e2e: owned rows of f come from pinned host memory, the owned rows of the result go back, every cycle
     e2e = None
     if args.e2e_steps > 0:
-        hostf = torch.empty(own * N, dtype=torch.float64).pin_memory()
-        hostv = torch.empty(own * N, dtype=torch.float64).pin_memory()
-        hostf.copy_(st.owned(V[0][0], 0).reshape(-1))
+        hostf = torch.empty(k, own * N, dtype=torch.float64).pin_memory()
+        hostv = torch.empty(k, own * N, dtype=torch.float64).pin_memory()
+        for c in range(k):
+            hostf[c].copy_(owned(bd["V"][c]).reshape(-1))
         def e2e_step():
             for c in range(k):
-                st.owned(V[c][0], 0).reshape(-1).copy_(hostf, non_blocking=True)
-                sv.vcycle(shifts[c], v0_is_zero=True, f0=V[c], v0=W[c])
-                hostv.copy_(st.owned(W[c][0], 0).reshape(-1), non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                owned(bd["V"][c]).copy_(hostf[c].view(own, N), non_blocking=True)
+            one_cycle_all()
+            for c in range(k):
+                hostv[c].view(own, N).copy_(owned(bd["W"][c]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         e2e_step()
         torch.cuda.synchronize(); dist.barrier()
         t0 = time.perf_counter()
@@ -640,7 +671,7 @@ def run_slab(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": ups_step * args.e2e_steps / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": k * own * N * 8 * world, "d2h_bytes_per_step": k * own * N * 8 * world,
-               "steps": args.e2e_steps, "call": "SlabVCycle.vcycle on owned rows copied from / to pinned host memory"}
+               "steps": args.e2e_steps, "call": "slab block cycle (k V-cycles) on owned rows copied from / to pinned host memory"}
     if rank == 0:
         peaks = {}
         try:
@@ -654,8 +685,9 @@ def run_slab(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "2D infinite well %d^2 slab-decomposed over %d GPUs (rows), lowest 4 eigenpairs, shift method: "
                                    "4 x V(4,4) + Rayleigh quotient + MGS per step" % (N, world),
-                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": sv.nlev, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
-                       "replicated_from": "%d^2" % (N >> sv.nlev), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
+                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": nlev_slab, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
+                       "driver": ("native: step issued from C++, NCCL called directly (csrc/slab_block.cu)" if native else "python: torch.distributed"),
+                       "replicated_from": "%d^2" % (N >> nlev_slab), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
                        "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9)},
             "vcycles_per_s": k * args.steps / (ms * 1e-3), "host_issue_ms_per_step": host_issue_ms,
             "eigenvalues": lam_h, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam_h, exact)],
@@ -669,6 +701,8 @@ def run_slab(args):
         print(json.dumps(line))
     for s_ in svs:
         s_.close()
+    if native:
+        nb.close()
     dist.destroy_process_group()
 
 
