@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--replicas", action="store_true", help="multi-GPU: independent replicas instead of row slabs")
     ap.add_argument("--gather-cols", type=int, default=512, help="slab path: levels at most this wide are replicated")
+    ap.add_argument("--slab-stagger", type=int, default=1,
+                    help="native slab driver: run the block as two halves half a phase apart (exchange of one overlaps kernels of the other)")
     ap.add_argument("--slab-driver", choices=["native", "python"], default="native",
                     help="slab path: step issued from C++ with NCCL called directly (csrc/slab_block.cu), or from Python over torch.distributed")
     return ap.parse_args()
@@ -107,6 +109,22 @@ def updates_per_cycle(N, lowest):
 # ---------------------------------------------------------------------------------------------------
 # clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ---------------------------------------------------------------------------------------------------
+class StdoutToStderr:
+    """fd-level redirect of stdout into stderr (C libraries that printf: stdout must carry ONE JSON line)"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 class Clocks:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -288,9 +306,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with StdoutToStderr():     # NCCL printf()s its version banner to stdout at the first communicator init
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
 
     from multigridcmt_b200 import MGCMTProcessor, MGCMTSolver, MGCMTStencilMaker, _lib
     from multigridcmt_b200.hierarchy import _ptr, _stream_ptr, get_hierarchy
@@ -537,9 +555,9 @@ def run_slab(args):
     import torch.distributed as dist
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: stdout carries ONE JSON line
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    with StdoutToStderr():         # NCCL printf()s its version banner to stdout at the first communicator init
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
     from multigridcmt_b200 import MGCMTStencilMaker, _lib
     from multigridcmt_b200.slab import HALO, SlabVCycle, TorchDistComm
     lib = _lib.load()
@@ -556,7 +574,9 @@ def run_slab(args):
     if native:
         # the whole step is two C calls: k lock-step cycles (+ Rayleigh sums) and the Gram-form orthonormalisation
         from multigridcmt_b200.slab import NativeSlabBlock
-        nb = NativeSlabBlock(H, world, rank, k, lowest_level=lowest, gather_cols=args.gather_cols)
+        with StdoutToStderr():
+            nb = NativeSlabBlock(H, world, rank, k, lowest_level=lowest, gather_cols=args.gather_cols,
+                                 stagger=bool(args.slab_stagger))
         own, begin, nlev_slab, lockstep = nb.own0, nb.begin0, nb.nlev, True
         owned = nb.owned
         bd = {"V": nb.new_block(), "W": nb.new_block()}
@@ -686,7 +706,9 @@ def run_slab(args):
             "config": {"workload": "2D infinite well %d^2 slab-decomposed over %d GPUs (rows), lowest 4 eigenpairs, shift method: "
                                    "4 x V(4,4) + Rayleigh quotient + MGS per step" % (N, world),
                        "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": nlev_slab, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
-                       "driver": ("native: step issued from C++, NCCL called directly (csrc/slab_block.cu)" if native else "python: torch.distributed"),
+                       "driver": (("native: step issued from C++, NCCL called directly (csrc/slab_block.cu)"
+                                   + ("; two halves half a phase apart on two communicators" if args.slab_stagger else "; lock-step")) if native
+                                  else "python: torch.distributed"),
                        "replicated_from": "%d^2" % (N >> nlev_slab), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
                        "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9)},
             "vcycles_per_s": k * args.steps / (ms * 1e-3), "host_issue_ms_per_step": host_issue_ms,

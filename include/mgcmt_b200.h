@@ -251,8 +251,10 @@ int mgcmt_nccl_comm_create(const void *id128, int world, int rank, void **out_co
 int mgcmt_nccl_comm_destroy(void *comm);
 /* k vectors of an n x n grid, rows [rank n/world, (rank+1) n/world) + 6 halo rows on both sides on this rank;
  * levels 0..nlev_slab-1 stay decomposed, coarser ones are replicated after an all-gather.  Coefficient arrays as in
- * mgcmt_hier_create (host, length n).  comm may be NULL when world == 1. */
-int mgcmt_slabblock_create(void *comm, int world, int rank, int n, int nlev_slab, int lowest_level, int k,
+ * mgcmt_hier_create (host, length n).  comm may be NULL when world == 1.  comm2: a second communicator over the same
+ * ranks (or NULL): with it the vectors run as two halves half a phase apart, one half's halo exchange overlapping the
+ * other half's kernels. */
+int mgcmt_slabblock_create(void *comm, void *comm2, int world, int rank, int n, int nlev_slab, int lowest_level, int k,
                            const double *h_row_lo, const double *h_row_di, const double *h_row_up,
                            const double *h_col_lo, const double *h_col_di, const double *h_col_up, double omega,
                            void *stream, mgcmt_slabblock_t **out);

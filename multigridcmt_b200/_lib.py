@@ -80,7 +80,7 @@ SIGNATURES = {
     "mgcmt_nccl_unique_id": (_I, [_P]),
     "mgcmt_nccl_comm_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
     "mgcmt_nccl_comm_destroy": (_I, [_P]),
-    "mgcmt_slabblock_create": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _D, _P, C.POINTER(_P)]),
+    "mgcmt_slabblock_create": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _D, _P, C.POINTER(_P)]),
     "mgcmt_slabblock_destroy": (_I, [_P]),
     "mgcmt_slabblock_cycle": (_I, [_P, _P, _P, _P, _P, _P]),
     "mgcmt_slabblock_gram": (_I, [_P, _P, _LL, _P]),

@@ -3,10 +3,11 @@
 // multigridcmt_b200/slab.py states the decomposition and drives it from Python over torch.distributed; that is the
 // testable reference of the host logic (gloo / single-process emulation), but at 8 GPUs a step is ~100 launches and
 // ~12 exchange phases in ~4 ms, and the Python issue time alone is that long.  This file issues the same sequence --
-// the same kernels through the same C entry points, in the same order -- from C++: k V(4,4) cycles advanced in
-// lock-step (each on its own stream, forked from / joined to the caller's stream around every phase), one NCCL group of
-// send/recv pairs per halo phase for all k vectors, in-place all-gather of the restricted residuals before the
-// replicated coarse part, all-reduce of the Rayleigh sums and of the packed Gram matrix.
+// the same kernels through the same C entry points on the same data -- from C++: k V(4,4) cycles advanced phase by
+// phase (each vector on its own stream), one NCCL group of send/recv pairs per halo phase, in-place all-gather of the
+// restricted residuals before the replicated coarse part, all-reduce of the Rayleigh sums and of the packed Gram
+// matrix.  The vectors form two halves, each with its own communicator, that run half a phase apart so that one half's
+// exchange overlaps the other half's kernels.
 //
 // NCCL is reached through dlopen/dlsym on the library the process already has (the one PyTorch bundles), so this
 // shared object has no link-time dependency on it and loads on machines without NCCL.
@@ -77,10 +78,20 @@ struct VecState {  // one vector of the block: its hierarchies, level buffers, s
 
 }  // namespace
 
+// The k vectors are split into two halves that advance through the phases of a cycle half a phase apart: while one half
+// exchanges halos (NCCL, its own communicator and stream) the other runs its kernels, so the exchange latency of the
+// many short phases is hidden instead of idling the GPU.
+struct Half {
+  int begin = 0, end = 0;        // vectors [begin, end)
+  ncclComm_t comm = nullptr;
+  cudaStream_t gs = nullptr;     // the half's ordering stream: NCCL calls, fork / join of its vectors' streams
+  cudaEvent_t fork = nullptr, comp_done = nullptr;
+};
+
 struct mgcmt_slabblock {
   int world = 1, rank = 0, n = 0, own0 = 0, nlev = 0, k = 0;
   double omega = 2.0 / 3.0;
-  ncclComm_t comm = nullptr;
+  Half half[2];
   std::vector<VecState> vec;
   cudaEvent_t fork = nullptr;
   double *scal = nullptr;  // 64 doubles
@@ -92,42 +103,98 @@ constexpr int kHalo = 6;  // multigridcmt_b200/slab.py: HALO
 
 size_t level_elems(const mgcmt_slabblock *b, int l) { return (size_t)((b->own0 >> l) + 2 * kHalo) * (size_t)(b->n >> l); }
 
-int fork_streams(mgcmt_slabblock *b, cudaStream_t main) {
-  CU(cudaEventRecord(b->fork, main));
-  for (VecState &s : b->vec) CU(cudaStreamWaitEvent(s.stream, b->fork, 0));
+int fork_streams(mgcmt_slabblock *b, Half &h) {
+  CU(cudaEventRecord(h.fork, h.gs));
+  for (int c = h.begin; c < h.end; ++c) CU(cudaStreamWaitEvent(b->vec[c].stream, h.fork, 0));
   return MGCMT_OK;
 }
 
-int join_streams(mgcmt_slabblock *b, cudaStream_t main) {
-  for (VecState &s : b->vec) {
-    CU(cudaEventRecord(s.done, s.stream));
-    CU(cudaStreamWaitEvent(main, s.done, 0));
+int join_streams(mgcmt_slabblock *b, Half &h) {
+  for (int c = h.begin; c < h.end; ++c) {
+    CU(cudaEventRecord(b->vec[c].done, b->vec[c].stream));
+    CU(cudaStreamWaitEvent(h.gs, b->vec[c].done, 0));
   }
   return MGCMT_OK;
 }
 
 // halo rows of level-l slab arrays: send the first / last kHalo owned rows to the neighbour above / below and receive
-// its rows into the halo; all arrays of one phase in one NCCL group
+// its rows into the halo; all arrays of one phase of one half in one NCCL group
 struct HaloItem {
   double *x;
   int level;
 };
-int exchange(mgcmt_slabblock *b, const std::vector<HaloItem> &items, cudaStream_t main) {
-  if (b->world == 1) return MGCMT_OK;
+int exchange(mgcmt_slabblock *b, Half &h, const std::vector<HaloItem> &items) {
+  if (b->world == 1 || items.empty()) return MGCMT_OK;
   NC(g_nccl.GroupStart());
   for (const HaloItem &it : items) {
     const size_t cols = (size_t)(b->n >> it.level), own = (size_t)(b->own0 >> it.level), cnt = kHalo * cols;
     double *top_halo = it.x, *top_own = it.x + kHalo * cols, *bot_own = it.x + own * cols, *bot_halo = it.x + (own + kHalo) * cols;
     if (b->rank > 0) {
-      NC(g_nccl.Send(top_own, cnt, kNcclFloat64, b->rank - 1, b->comm, main));
-      NC(g_nccl.Recv(top_halo, cnt, kNcclFloat64, b->rank - 1, b->comm, main));
+      NC(g_nccl.Send(top_own, cnt, kNcclFloat64, b->rank - 1, h.comm, h.gs));
+      NC(g_nccl.Recv(top_halo, cnt, kNcclFloat64, b->rank - 1, h.comm, h.gs));
     }
     if (b->rank + 1 < b->world) {
-      NC(g_nccl.Send(bot_own, cnt, kNcclFloat64, b->rank + 1, b->comm, main));
-      NC(g_nccl.Recv(bot_halo, cnt, kNcclFloat64, b->rank + 1, b->comm, main));
+      NC(g_nccl.Send(bot_own, cnt, kNcclFloat64, b->rank + 1, h.comm, h.gs));
+      NC(g_nccl.Recv(bot_halo, cnt, kNcclFloat64, b->rank + 1, h.comm, h.gs));
     }
   }
   NC(g_nccl.GroupEnd());
+  return MGCMT_OK;
+}
+
+// Stage i of a cycle for one half.  comm(i) precedes comp(i):
+//   i < nl        comm: halos of f[i]                               comp: down leg of level i
+//   i == nl       comm: all-gather of the restricted residual       comp: replicated coarse cycle
+//   nl < i <= 2nl comm: halos of tmp[l] (and v[l+1]), l = 2nl - i   comp: up leg of level l
+//   i == 2nl + 1  comm: halos of the result v[0]                    comp: Rayleigh sums            (only with d_lam)
+int comm_stage(mgcmt_slabblock *b, Half &h, int i) {
+  const int nl = b->nlev;
+  std::vector<HaloItem> items;
+  auto add = [&](std::vector<double *> VecState::*member, int l) {
+    for (int c = h.begin; c < h.end; ++c) items.push_back({(b->vec[c].*member)[l], l});
+  };
+  if (i < nl) {
+    add(&VecState::f, i);
+  } else if (i == nl) {
+    if (b->world == 1) return MGCMT_OK;
+    const size_t cnt = (size_t)(b->own0 >> nl) * (size_t)(b->n >> nl);
+    NC(g_nccl.GroupStart());
+    for (int c = h.begin; c < h.end; ++c) {
+      VecState &s = b->vec[c];
+      NC(g_nccl.AllGather(s.fg + (size_t)b->rank * cnt, s.fg, cnt, kNcclFloat64, h.comm, h.gs));
+    }
+    NC(g_nccl.GroupEnd());
+    return MGCMT_OK;
+  } else if (i <= 2 * nl) {
+    const int l = 2 * nl - i;
+    add(&VecState::tmp, l);
+    if (l + 1 < nl) add(&VecState::v, l + 1);
+  } else {
+    add(&VecState::v, 0);
+  }
+  return exchange(b, h, items);
+}
+
+int comp_stage(mgcmt_slabblock *b, Half &h, int i, const double *shifts, double *d_lam) {
+  const int nl = b->nlev;
+  RC(fork_streams(b, h));
+  for (int c = h.begin; c < h.end; ++c) {
+    VecState &s = b->vec[c];
+    if (i < nl) {
+      RC(mgcmt_fused_leg(s.slab, i, 2 /* down, zero start */, 4, shifts[c], b->omega, nullptr, s.f[i], s.tmp[i], nullptr,
+                         (i + 1 == nl) ? s.fg : s.f[i + 1], s.stream));
+    } else if (i == nl) {
+      RC(mgcmt_vcycle_from(s.coarse, nl, shifts[c], MGCMT_SMOOTH_WJACOBI, b->omega, s.vg, s.fg, s.stream));
+    } else if (i <= 2 * nl) {
+      const int l = 2 * nl - i;
+      RC(mgcmt_fused_leg(s.slab, l, 3 /* up */, 4, shifts[c], b->omega, s.tmp[l], s.f[l], s.v[l],
+                         (l + 1 == nl) ? s.vg : s.v[l + 1], nullptr, s.stream));
+    } else {
+      RC(mgcmt_slab_rayleigh(s.slab, 0, s.v[0], d_lam + 2 * c, s.stream));
+    }
+  }
+  RC(join_streams(b, h));
+  CU(cudaEventRecord(h.comp_done, h.gs));
   return MGCMT_OK;
 }
 
@@ -201,13 +268,18 @@ int mgcmt_slabblock_destroy(mgcmt_slabblock_t *b) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
   }
+  for (Half &h : b->half) {
+    if (h.gs) cudaStreamDestroy(h.gs);
+    if (h.fork) cudaEventDestroy(h.fork);
+    if (h.comp_done) cudaEventDestroy(h.comp_done);
+  }
   if (b->fork) cudaEventDestroy(b->fork);
   cudaFree(b->scal);
   delete b;
   return MGCMT_OK;
 }
 
-int mgcmt_slabblock_create(void *comm, int world, int rank, int n, int nlev_slab, int lowest_level, int k,
+int mgcmt_slabblock_create(void *comm, void *comm2, int world, int rank, int n, int nlev_slab, int lowest_level, int k,
                            const double *row_lo, const double *row_di, const double *row_up, const double *col_lo,
                            const double *col_di, const double *col_up, double omega, void *stream,
                            mgcmt_slabblock_t **out) {
@@ -220,7 +292,14 @@ int mgcmt_slabblock_create(void *comm, int world, int rank, int n, int nlev_slab
     return set_error(MGCMT_ERR_ARG, "slab cuts must stay even, and slabs deeper than the halo, on every slab level");
   mgcmt_slabblock *b = new mgcmt_slabblock();
   b->world = world; b->rank = rank; b->n = n; b->own0 = own0; b->nlev = nlev_slab; b->k = k; b->omega = omega;
-  b->comm = (ncclComm_t)comm;
+  // two staggered halves when there is a communicator for each (or none is needed)
+  const bool two = k >= 2 && (world == 1 || comm2 != nullptr);
+  b->half[0].begin = 0;
+  b->half[0].end = two ? (k + 1) / 2 : k;
+  b->half[0].comm = (ncclComm_t)comm;
+  b->half[1].begin = b->half[0].end;
+  b->half[1].end = k;
+  b->half[1].comm = (ncclComm_t)comm2;
   b->vec.resize(k);
   auto bail = [&](int rc) {
     std::string msg = mgcmt_last_error();
@@ -236,6 +315,11 @@ int mgcmt_slabblock_create(void *comm, int world, int rank, int n, int nlev_slab
     }                                                                                                 \
   } while (0)
   CUB(cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming));
+  for (Half &h : b->half) {
+    CUB(cudaStreamCreateWithFlags(&h.gs, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&h.fork, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&h.comp_done, cudaEventDisableTiming));
+  }
   CUB(cudaMalloc(&b->scal, sizeof(double) * 64));
   const size_t ng = (size_t)(n >> nlev_slab) * (size_t)(n >> nlev_slab);
   for (VecState &s : b->vec) {
@@ -283,64 +367,34 @@ int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *
     b->vec[c].f[0] = h_f0[c];
     b->vec[c].v[0] = h_v0[c];
   }
-  std::vector<HaloItem> items;
-  auto all_of = [&](std::vector<double *> VecState::*member, int l, bool append) {
-    if (!append) items.clear();
-    for (VecState &s : b->vec) items.push_back({(s.*member)[l], l});
-  };
-  // down: 4 sweeps + residual + restriction per level (one fused kernel per vector), halos of the new right-hand side
-  all_of(&VecState::f, 0, false);
-  RC(exchange(b, items, main));
-  for (int l = 0; l < nl; ++l) {
-    const bool last = (l + 1 == nl);
-    RC(fork_streams(b, main));
-    for (int c = 0; c < k; ++c) {
-      VecState &s = b->vec[c];
-      RC(mgcmt_fused_leg(s.slab, l, 2 /* down, zero start */, 4, h_shifts[c], b->omega, nullptr, s.f[l], s.tmp[l], nullptr,
-                         last ? s.fg : s.f[l + 1], s.stream));
-    }
-    RC(join_streams(b, main));
-    if (last) {
-      if (b->world > 1) {
-        const size_t cnt = (size_t)(b->own0 >> nl) * (size_t)(b->n >> nl);
-        NC(g_nccl.GroupStart());
-        for (VecState &s : b->vec) NC(g_nccl.AllGather(s.fg + (size_t)b->rank * cnt, s.fg, cnt, kNcclFloat64, b->comm, main));
-        NC(g_nccl.GroupEnd());
-      }
-    } else {
-      all_of(&VecState::f, l + 1, false);
-      RC(exchange(b, items, main));
+  Half &A = b->half[0], &B = b->half[1];
+  const bool two = B.end > B.begin;
+  const int nstage = 2 * nl + 1 + (d_lam ? 1 : 0);
+  // both halves start after everything already on the caller's stream
+  CU(cudaEventRecord(b->fork, main));
+  CU(cudaStreamWaitEvent(A.gs, b->fork, 0));
+  if (two) CU(cudaStreamWaitEvent(B.gs, b->fork, 0));
+  RC(comm_stage(b, A, 0));
+  if (two) RC(comm_stage(b, B, 0));
+  for (int i = 0; i < nstage; ++i) {
+    // A computes stage i (after B's stage i-1 kernels), then exchanges for stage i+1 while B computes stage i, ...
+    if (two && i > 0) CU(cudaStreamWaitEvent(A.gs, B.comp_done, 0));
+    RC(comp_stage(b, A, i, h_shifts, d_lam));
+    if (i + 1 < nstage) RC(comm_stage(b, A, i + 1));
+    if (two) {
+      CU(cudaStreamWaitEvent(B.gs, A.comp_done, 0));
+      RC(comp_stage(b, B, i, h_shifts, d_lam));
+      if (i + 1 < nstage) RC(comm_stage(b, B, i + 1));
     }
   }
-  // replicated coarse part: every rank runs the same small V-cycle on the gathered residual
-  RC(fork_streams(b, main));
-  for (int c = 0; c < k; ++c) {
-    VecState &s = b->vec[c];
-    RC(mgcmt_vcycle_from(s.coarse, nl, h_shifts[c], MGCMT_SMOOTH_WJACOBI, b->omega, s.vg, s.fg, s.stream));
+  // back to the caller's stream
+  CU(cudaEventRecord(A.fork, A.gs));
+  CU(cudaStreamWaitEvent(main, A.fork, 0));
+  if (two) {
+    CU(cudaEventRecord(B.fork, B.gs));
+    CU(cudaStreamWaitEvent(main, B.fork, 0));
   }
-  RC(join_streams(b, main));
-  // up: halos of the smoothed iterate and of the coarse correction, then prolongation + correction + 4 sweeps
-  for (int l = nl - 1; l >= 0; --l) {
-    const bool last = (l + 1 == nl);
-    all_of(&VecState::tmp, l, false);
-    if (!last) all_of(&VecState::v, l + 1, true);
-    RC(exchange(b, items, main));
-    RC(fork_streams(b, main));
-    for (int c = 0; c < k; ++c) {
-      VecState &s = b->vec[c];
-      RC(mgcmt_fused_leg(s.slab, l, 3 /* up */, 4, h_shifts[c], b->omega, s.tmp[l], s.f[l], s.v[l], last ? s.vg : s.v[l + 1],
-                         nullptr, s.stream));
-    }
-    RC(join_streams(b, main));
-  }
-  if (d_lam) {
-    all_of(&VecState::v, 0, false);
-    RC(exchange(b, items, main));
-    RC(fork_streams(b, main));
-    for (int c = 0; c < k; ++c) RC(mgcmt_slab_rayleigh(b->vec[c].slab, 0, b->vec[c].v[0], d_lam + 2 * c, b->vec[c].stream));
-    RC(join_streams(b, main));
-    if (b->world > 1) NC(g_nccl.AllReduce(d_lam, d_lam, (size_t)2 * k, kNcclFloat64, kNcclSum, b->comm, main));
-  }
+  if (d_lam && b->world > 1) NC(g_nccl.AllReduce(d_lam, d_lam, (size_t)2 * k, kNcclFloat64, kNcclSum, A.comm, main));
   for (VecState &s : b->vec) s.f[0] = s.v[0] = nullptr;
   return MGCMT_OK;
 }
@@ -354,7 +408,7 @@ int mgcmt_slabblock_gram(mgcmt_slabblock_t *b, double *d_block, long long stride
   double *base = d_block + (size_t)kHalo * b->n;   // owned rows of vector 0; vector c is `stride` doubles further
   RC(mgcmt_gram(n_own, b->k, base, stride, b->scal, stream));
   if (b->world > 1)
-    NC(g_nccl.AllReduce(b->scal, b->scal, (size_t)(b->k * (b->k + 1) / 2), kNcclFloat64, kNcclSum, b->comm, main));
+    NC(g_nccl.AllReduce(b->scal, b->scal, (size_t)(b->k * (b->k + 1) / 2), kNcclFloat64, kNcclSum, b->half[0].comm, main));
   return mgcmt_cholqr_apply(n_own, b->k, base, stride, b->scal, stream);
 }
 

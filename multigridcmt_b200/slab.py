@@ -485,7 +485,8 @@ class NativeSlabBlock:
     initialised (it carries the 128-byte NCCL id from rank 0 to the others, nothing else).  Bit-for-bit the same
     results as the Python-driven path (same kernels, same order): tools/check_native_slab.py."""
 
-    def __init__(self, op: SeparableOperator, world, rank, k, lowest_level=8, gather_cols=2048, omega=2. / 3.):
+    def __init__(self, op: SeparableOperator, world, rank, k, lowest_level=8, gather_cols=2048, omega=2. / 3.,
+                 stagger=True):
         torch = _lib.require_cuda()
         lib = _lib.load()
         if op.nrows != op.ncols:
@@ -498,22 +499,24 @@ class NativeSlabBlock:
         self.own0 = self.N // world
         self.begin0 = rank * self.own0
         self.slab_size = (self.own0 + 2 * HALO) * self.N
-        self.comm = C.c_void_p()
+        self.comm, self.comm2 = C.c_void_p(), C.c_void_p()
         self.handle = C.c_void_p()
         if world > 1:
             import torch.distributed as dist
             _lib.check(lib.mgcmt_nccl_load(_nccl_library_path().encode()))
-            ident = torch.zeros(128, dtype=torch.uint8)
-            if rank == 0:
-                _lib.check(lib.mgcmt_nccl_unique_id(C.c_void_p(ident.data_ptr())))
-            dev = ident.cuda() if dist.get_backend() == "nccl" else ident
-            dist.broadcast(dev, src=0)
-            ident = dev.cpu()
-            _lib.check(lib.mgcmt_nccl_comm_create(C.c_void_p(ident.data_ptr()), self.world, self.rank, C.byref(self.comm)))
+            # two communicators: the block runs as two halves half a phase apart (stagger=False: one, lock-step)
+            for comm in ([self.comm, self.comm2] if stagger and self.k >= 2 else [self.comm]):
+                ident = torch.zeros(128, dtype=torch.uint8)
+                if rank == 0:
+                    _lib.check(lib.mgcmt_nccl_unique_id(C.c_void_p(ident.data_ptr())))
+                dev = ident.cuda() if dist.get_backend() == "nccl" else ident
+                dist.broadcast(dev, src=0)
+                ident = dev.cpu()
+                _lib.check(lib.mgcmt_nccl_comm_create(C.c_void_p(ident.data_ptr()), self.world, self.rank, C.byref(comm)))
         hp = lambda a: a.ctypes.data_as(C.c_void_p)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(lib.mgcmt_slabblock_create(self.comm, self.world, self.rank, self.N, self.nlev, int(lowest_level), self.k,
-                                              hp(op.row[0]), hp(op.row[1]), hp(op.row[2]), hp(op.col[0]), hp(op.col[1]),
+        _lib.check(lib.mgcmt_slabblock_create(self.comm, self.comm2, self.world, self.rank, self.N, self.nlev, int(lowest_level),
+                                              self.k, hp(op.row[0]), hp(op.row[1]), hp(op.row[2]), hp(op.col[0]), hp(op.col[1]),
                                               hp(op.col[2]), float(omega), stream, C.byref(self.handle)))
         self._ptrs = (C.c_void_p * self.k)
         self._shifts = (C.c_double * self.k)
@@ -523,9 +526,10 @@ class NativeSlabBlock:
         if getattr(self, "handle", None):
             lib.mgcmt_slabblock_destroy(self.handle)
             self.handle = None
-        if getattr(self, "comm", None):
-            lib.mgcmt_nccl_comm_destroy(self.comm)
-            self.comm = None
+        for name in ("comm", "comm2"):
+            if getattr(self, name, None):
+                lib.mgcmt_nccl_comm_destroy(getattr(self, name))
+                setattr(self, name, None)
 
     def new_block(self):
         """(k, slab_size) zero tensor: k finest-level slab vectors (owned rows + halos) of this rank"""

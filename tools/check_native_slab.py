@@ -26,6 +26,7 @@ def main():
     H = (-1.0 / np.pi ** 2) * MGCMTStencilMaker().laplacian(N, "2d", matrix_free=True)
     shifts = [1.7665, 4.3863, 4.3864, 7.0062]
     nb = NativeSlabBlock(H, world, rank, k, lowest_level=8, gather_cols=gather)
+    nb1 = NativeSlabBlock(H, world, rank, k, lowest_level=8, gather_cols=gather, stagger=False)
     comm = TorchDistComm()
     svs = [SlabVCycle(H, world, comm, [rank], lowest_level=8, gather_cols=gather) for _ in range(k)]
     streams = [torch.cuda.Stream() for _ in range(k)]
@@ -41,17 +42,26 @@ def main():
         nb.cycle(shifts, F1, W1, lam1)
         nb.gram(W1)
 
+    F3, W3 = nb.new_block(), nb.new_block()
+    for c in range(k):
+        nb.owned(F3[c]).copy_(own[c])
+    lam3 = torch.zeros_like(lam1)
+
+    def native_lockstep():
+        nb1.cycle(shifts, F3, W3, lam3)
+        nb1.gram(W3)
+
     def python():
         vcycle_block(svs, shifts, [[F2[c]] for c in range(k)], [[W2[c]] for c in range(k)], lam=[lam2], streams=streams)
         svs[0].gramschmidt_gram([W2])
 
-    native(); python()
+    native(); python(); native_lockstep()
     torch.cuda.synchronize(); dist.barrier()
-    same_w = all(torch.equal(nb.owned(W1[c]), nb.owned(W2[c])) for c in range(k))
-    same_lam = torch.equal(lam1, lam2)
+    same_w = all(torch.equal(nb.owned(W1[c]), nb.owned(W2[c])) and torch.equal(nb.owned(W1[c]), nb.owned(W3[c])) for c in range(k))
+    same_lam = torch.equal(lam1, lam2) and torch.equal(lam1, lam3)
     res = {"rank": rank, "world": world, "N": N, "slab_levels": nb.nlev, "identical_vectors": same_w, "identical_rayleigh": same_lam,
            "lam": (lam1[:, 0] / lam1[:, 1]).cpu().tolist()}
-    for name, fn in (("native", native), ("python", python)):
+    for name, fn in (("native", native), ("native_lockstep", native_lockstep), ("python", python)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -69,7 +79,7 @@ def main():
     ok = same_w and same_lam
     for sv in svs:
         sv.close()
-    nb.close()
+    nb.close(); nb1.close()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
