@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--replicas", action="store_true", help="multi-GPU: independent replicas instead of row slabs")
     ap.add_argument("--gather-cols", type=int, default=512, help="slab path: levels at most this wide are replicated")
-    ap.add_argument("--slab-stagger", type=int, default=1,
+    ap.add_argument("--slab-stagger", type=int, default=0,
                     help="native slab driver: run the block as two halves half a phase apart (exchange of one overlaps kernels of the other)")
     ap.add_argument("--slab-driver", choices=["native", "python"], default="native",
                     help="slab path: step issued from C++ with NCCL called directly (csrc/slab_block.cu), or from Python over torch.distributed")

@@ -445,6 +445,8 @@ static int build_hier(mgcmt_hier_t **out, int nrows_glob, int ncols, int coarsen
     L.dev.five = (l == 0 || !coarsen_rows) ? 1 : 0;
     L.dev.crow_shift = 0;
     L.dev.nrows_coarse = 0;
+    L.dev.rq_lo = slab ? halo : 0;
+    L.dev.rq_hi = slab ? halo + own : L.dev.nrows;
     if (slab) {
       if (l + 1 < nlev) {  // coarse level is a slab piece too
         L.dev.crow_shift = halo / 2;
@@ -798,6 +800,32 @@ int mgcmt_vcycle_from(mgcmt_hier_t *h, int level, double shift, int smoother, do
   // the V-cycle restricted to levels level..coarsest, zero initial guess, 4/4 sweeps: what MGCMTSolver.vcycle
   // does at every coarse level (MGCMTSolver.py:316-320)
   return vcycle_level(h, level, shift, 4, 4, smoother, omega, d_v, d_f, true, (cudaStream_t)stream);
+}
+
+int mgcmt_slab_up_rq(mgcmt_hier_t *h, double shift, double omega, const double *d_vin, const double *d_f, double *d_vout,
+                     const double *d_ecoarse, double *d_out2, void *stream) {
+  int rc = check_level(h, 0);
+  if (rc) return rc;
+  if (!h->slab) return fail(MGCMT_ERR_STATE, "not a slab hierarchy");
+  if (!d_out2) return fail(MGCMT_ERR_ARG, "null output");
+  if (d_vin == d_vout) return fail(MGCMT_ERR_ARG, "fused legs are out of place");
+  NEED_ALIGNED(d_vin, d_f, d_vout, d_ecoarse);
+  Level &L = h->lev[0];
+  cudaStream_t s = (cudaStream_t)stream;
+  const int slots = fused_rq_slots(L.dev);
+  if (slots <= 0) return fail(MGCMT_ERR_STATE, "the fused Rayleigh stage is not available for this level");
+  if (slots > h->rq_slots) {
+    cudaFree(h->rq_partials);
+    h->rq_partials = nullptr;
+    CU(cudaMalloc(&h->rq_partials, sizeof(double) * 2 * slots));
+    h->rq_slots = slots;
+  }
+  // halo rows 5 and own+6 of the output are exact (dependency cone of prolongation + 4 sweeps = 5 rows, 6 halo rows),
+  // so (A w) on the first and last owned row is too: the sums over the owned rows need no second exchange
+  CU(launch_fused_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, d_vin, d_f, d_vout, d_ecoarse, h->rq_partials, s));
+  CU(launch_finish(2, slots, h->rq_partials, d_out2, s));
+  CU(launch_rq_unshift(d_out2, shift, s));
+  return MGCMT_OK;
 }
 
 int mgcmt_slab_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream) {

@@ -15,6 +15,7 @@ struct LevelDev {
   int five;        // 1: Ma = Mb = I (finest level: 5-point stencil)
   int crow_shift;    // row-slab decomposition: coarse local row = (fine local row >> 1) + crow_shift (0 when not
   int nrows_coarse;  // decomposed); rows of the coarse array the transfers address (0 => nrows / 2)
+  int rq_lo, rq_hi;  // local rows [rq_lo, rq_hi) whose w^T A w, w^T w the fused Rayleigh stage sums (slab piece: the owned rows)
   const double *ka_lo, *ka_di, *ka_up, *ma_lo, *ma_di, *ma_up;  // length nrows_glob
   const double *kb_lo, *kb_di, *kb_up, *mb_lo, *mb_di, *mb_up;  // length ncols
 };

@@ -390,7 +390,7 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
           const double acc = st[k].a1[q] + (FIVE ? cr_ka_up * S[q] : (cr_ma_up * T[q] + cr_ka_up * S[q]));
           const double ff = ffv[q];
           out[q] = is_res ? (ff - acc) : (st[k].xc[q] + w[q] * (ff - acc));
-          if (RQ && is_res && rho >= r0 && rho < r1 && colout[q]) {  // each useful point exactly once
+          if (RQ && is_res && rho >= r0 && rho < r1 && rho >= L.rq_lo && rho < L.rq_hi && colout[q]) {  // each useful (owned) point exactly once
             rq_num += st[k].xc[q] * acc;
             rq_den += st[k].xc[q] * st[k].xc[q];
           }

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -95,6 +96,9 @@ struct mgcmt_slabblock {
   std::vector<VecState> vec;
   cudaEvent_t fork = nullptr;
   double *scal = nullptr;  // 64 doubles
+  bool fused_rq = true;            // Rayleigh sums inside the finest up leg (MGCMT_SLAB_FUSED_RQ=0: separate stage)
+  bool profile = false;            // time every stage of the next cycles with CUDA events (lock-step form only)
+  std::vector<cudaEvent_t> prof;   // 2 * nstage + 1 events of the last profiled cycle
 };
 
 namespace {
@@ -146,7 +150,8 @@ int exchange(mgcmt_slabblock *b, Half &h, const std::vector<HaloItem> &items) {
 //   i < nl        comm: halos of f[i]                               comp: down leg of level i
 //   i == nl       comm: all-gather of the restricted residual       comp: replicated coarse cycle
 //   nl < i <= 2nl comm: halos of tmp[l] (and v[l+1]), l = 2nl - i   comp: up leg of level l
-//   i == 2nl + 1  comm: halos of the result v[0]                    comp: Rayleigh sums            (only with d_lam)
+//   i == 2nl + 1  comm: halos of the result v[0]                    comp: Rayleigh sums   (only with d_lam when the
+//                                                                         sums are not taken inside the last up leg)
 int comm_stage(mgcmt_slabblock *b, Half &h, int i) {
   const int nl = b->nlev;
   std::vector<HaloItem> items;
@@ -187,8 +192,11 @@ int comp_stage(mgcmt_slabblock *b, Half &h, int i, const double *shifts, double 
       RC(mgcmt_vcycle_from(s.coarse, nl, shifts[c], MGCMT_SMOOTH_WJACOBI, b->omega, s.vg, s.fg, s.stream));
     } else if (i <= 2 * nl) {
       const int l = 2 * nl - i;
-      RC(mgcmt_fused_leg(s.slab, l, 3 /* up */, 4, shifts[c], b->omega, s.tmp[l], s.f[l], s.v[l],
-                         (l + 1 == nl) ? s.vg : s.v[l + 1], nullptr, s.stream));
+      const double *e = (l + 1 == nl) ? s.vg : s.v[l + 1];
+      if (l == 0 && d_lam && b->fused_rq)   // the Rayleigh sums of the result are taken inside the last up leg
+        RC(mgcmt_slab_up_rq(s.slab, shifts[c], b->omega, s.tmp[0], s.f[0], s.v[0], e, d_lam + 2 * c, s.stream));
+      else
+        RC(mgcmt_fused_leg(s.slab, l, 3 /* up */, 4, shifts[c], b->omega, s.tmp[l], s.f[l], s.v[l], e, nullptr, s.stream));
     } else {
       RC(mgcmt_slab_rayleigh(s.slab, 0, s.v[0], d_lam + 2 * c, s.stream));
     }
@@ -268,6 +276,7 @@ int mgcmt_slabblock_destroy(mgcmt_slabblock_t *b) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
   }
+  for (cudaEvent_t e : b->prof) cudaEventDestroy(e);
   for (Half &h : b->half) {
     if (h.gs) cudaStreamDestroy(h.gs);
     if (h.fork) cudaEventDestroy(h.fork);
@@ -301,6 +310,7 @@ int mgcmt_slabblock_create(void *comm, void *comm2, int world, int rank, int n, 
   b->half[1].end = k;
   b->half[1].comm = (ncclComm_t)comm2;
   b->vec.resize(k);
+  if (const char *e = getenv("MGCMT_SLAB_FUSED_RQ")) b->fused_rq = (e[0] != '0');
   auto bail = [&](int rc) {
     std::string msg = mgcmt_last_error();
     mgcmt_slabblock_destroy(b);
@@ -369,18 +379,30 @@ int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *
   }
   Half &A = b->half[0], &B = b->half[1];
   const bool two = B.end > B.begin;
-  const int nstage = 2 * nl + 1 + (d_lam ? 1 : 0);
+  const int nstage = 2 * nl + 1 + ((d_lam && !b->fused_rq) ? 1 : 0);
   // both halves start after everything already on the caller's stream
   CU(cudaEventRecord(b->fork, main));
   CU(cudaStreamWaitEvent(A.gs, b->fork, 0));
   if (two) CU(cudaStreamWaitEvent(B.gs, b->fork, 0));
+  const bool prof = b->profile && !two;
+  if (prof) {
+    while ((int)b->prof.size() < 2 * nstage + 1) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      b->prof.push_back(e);
+    }
+    CU(cudaEventRecord(b->prof[0], A.gs));
+  }
   RC(comm_stage(b, A, 0));
+  if (prof) CU(cudaEventRecord(b->prof[1], A.gs));
   if (two) RC(comm_stage(b, B, 0));
   for (int i = 0; i < nstage; ++i) {
     // A computes stage i (after B's stage i-1 kernels), then exchanges for stage i+1 while B computes stage i, ...
     if (two && i > 0) CU(cudaStreamWaitEvent(A.gs, B.comp_done, 0));
     RC(comp_stage(b, A, i, h_shifts, d_lam));
+    if (prof) CU(cudaEventRecord(b->prof[2 * i + 2], A.gs));
     if (i + 1 < nstage) RC(comm_stage(b, A, i + 1));
+    if (prof && i + 1 < nstage) CU(cudaEventRecord(b->prof[2 * i + 3], A.gs));
     if (two) {
       CU(cudaStreamWaitEvent(B.gs, A.comp_done, 0));
       RC(comp_stage(b, B, i, h_shifts, d_lam));
@@ -396,6 +418,28 @@ int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *
   }
   if (d_lam && b->world > 1) NC(g_nccl.AllReduce(d_lam, d_lam, (size_t)2 * k, kNcclFloat64, kNcclSum, A.comm, main));
   for (VecState &s : b->vec) s.f[0] = s.v[0] = nullptr;
+  return MGCMT_OK;
+}
+
+int mgcmt_slabblock_profile(mgcmt_slabblock_t *b, int on) {
+  if (!b) return set_error(MGCMT_ERR_ARG, "null argument");
+  b->profile = on != 0;
+  return MGCMT_OK;
+}
+
+int mgcmt_slabblock_profile_read(mgcmt_slabblock_t *b, int with_lam, double *ms_comm, double *ms_comp, int *nstage_out) {
+  if (!b || !ms_comm || !ms_comp || !nstage_out) return set_error(MGCMT_ERR_ARG, "null argument");
+  const int nstage = 2 * b->nlev + 1 + ((with_lam && !b->fused_rq) ? 1 : 0);
+  if ((int)b->prof.size() < 2 * nstage + 1) return set_error(MGCMT_ERR_STATE, "no profiled cycle (lock-step form, profile on)");
+  CU(cudaDeviceSynchronize());
+  for (int i = 0; i < nstage; ++i) {
+    float a = 0.f, c = 0.f;
+    CU(cudaEventElapsedTime(&a, b->prof[2 * i], b->prof[2 * i + 1]));
+    CU(cudaEventElapsedTime(&c, b->prof[2 * i + 1], b->prof[2 * i + 2]));
+    ms_comm[i] = a;
+    ms_comp[i] = c;
+  }
+  *nstage_out = nstage;
   return MGCMT_OK;
 }
 

@@ -486,7 +486,7 @@ class NativeSlabBlock:
     results as the Python-driven path (same kernels, same order): tools/check_native_slab.py."""
 
     def __init__(self, op: SeparableOperator, world, rank, k, lowest_level=8, gather_cols=2048, omega=2. / 3.,
-                 stagger=True):
+                 stagger=False):
         torch = _lib.require_cuda()
         lib = _lib.load()
         if op.nrows != op.ncols:
@@ -550,6 +550,18 @@ class NativeSlabBlock:
         _lib.check(_lib.load().mgcmt_slabblock_cycle(self.handle, self._shifts(*[float(s) for s in shifts]), f0, v0,
                                                      C.c_void_p(lam.data_ptr()) if lam is not None else None,
                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def profile(self, on=True):
+        _lib.check(_lib.load().mgcmt_slabblock_profile(self.handle, 1 if on else 0))
+
+    def profile_read(self, with_lam=True):
+        """per-stage milliseconds of the last profiled cycle: list of (stage name, comm ms, compute ms)"""
+        n = 2 * self.nlev + 2
+        comm, comp, ns = (C.c_double * n)(), (C.c_double * n)(), C.c_int()
+        _lib.check(_lib.load().mgcmt_slabblock_profile_read(self.handle, 1 if with_lam else 0, comm, comp, C.byref(ns)))
+        names = (["down L%d" % l for l in range(self.nlev)] + ["coarse (replicated)"]
+                 + ["up L%d" % l for l in range(self.nlev - 1, -1, -1)] + ["rayleigh (separate pass)"])
+        return [(names[i], comm[i], comp[i]) for i in range(ns.value)]
 
     def gram(self, W):
         torch = _lib.require_cuda()

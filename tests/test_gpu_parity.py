@@ -1015,7 +1015,8 @@ def test_native_slab_block_single_rank(T, prod):
     T.cuda.synchronize()
     for c in range(k):
         assert T.equal(nb.owned(W[c]), svs[0].states[0].owned(W2[c], 0))
-    assert T.equal(lam, lam2)
+    # the native driver takes the Rayleigh sums inside the last up leg, the Python one in a separate pass
+    assert np.allclose(lam.cpu().numpy(), lam2.cpu().numpy(), rtol=1e-12, atol=0)
     # (c) orthonormalisation of the block
     ref = W.clone()
     nb.gram(W)
