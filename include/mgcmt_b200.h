@@ -178,7 +178,8 @@ int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, 
 /* runtime switches, for tests and A/B timing: "fused" (1/0), "fused_min_cols" (smallest level width
  * that uses the fused legs), "tile_max_cols" (levels at most this wide use the tile legs),
  * "tail_max_cols" (levels at most this wide are collapsed into the single-CTA tail kernel; 0 = off),
- * "fused_c5" (2|4 columns per lane on the 5-point level) */
+ * "fused_c5" (2|4 columns per lane on the 5-point level), "band_gs_scan" (1/0: scan form of the in-chunk
+ * recurrence of the banded Gauss-Seidel sweep), "band_gs_split" (1/0: old-value part of that sweep in its own launch) */
 int mgcmt_set_option(const char *name, int value);
 
 /* ---- reductions / vector post-processing (MGCMTProcessor.py, Rayleigh quotients in the drivers) --

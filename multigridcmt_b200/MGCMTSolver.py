@@ -356,11 +356,11 @@ class MGCMTSolver:
         M = np.asarray(M)
         return M.shape == (n, n) and np.array_equal(M, np.eye(n))
 
-    def _rq_hierarchy(self, A, M, n, lowest):
+    def _rq_hierarchy(self, A, M, n, lowest, dimension="1d"):
         if not self._is_identity(M, n):
             raise NotImplementedError("the device RQ path needs M = identity on the finest level (as in RQMin.py:17); "
                                       "coarse mass matrices R*M*P are built from it")
-        op = recognise(A, "1d")
+        op = recognise(A, dimension)
         return get_hierarchy(op, lowest)
 
     def _rqmin_level(self, h, level, x, nu):
@@ -423,7 +423,12 @@ class MGCMTSolver:
         if is_device_tensor(v0):
             x = x.clone()
         n = x.numel()
-        h = self._rq_hierarchy(A, M, n, min(n, 4096))
+        dimension = self._guess_dimension(A, n)
+        if dimension == "2d":
+            op = recognise(A, "2d")
+            h = self._rq_hierarchy(op, M, n, self._any_lowest(op), "2d")
+        else:
+            h = self._rq_hierarchy(A, M, n, min(n, 4096))
         x, rho = self._rqmin_level(h, 0, x, nu)
         if shape is None:
             return x, rho
@@ -441,13 +446,28 @@ class MGCMTSolver:
             k, rho = self._rqmin_level(h, level, k, nu2)
         return k, rho
 
-    def vcycle_rqmg(self, x, A, M, nu1=4, nu2=4, nmin=2):
-        # MGCMTSolver.py:99-122
+    def vcycle_rqmg(self, x, A, M, nu1=4, nu2=4, nmin=2, dimension="1d"):
+        # MGCMTSolver.py:99-122.  dimension="2d" is an extension: the reference's RQMG is
+        # 1-D only (its transfer operators are built without `dimension=`, D6); the 2-D form uses the same recursion with
+        # the 2-D restriction / interpolation and stops coarsening when the VECTOR length is <= nmin, like the original.
         shape = np.shape(x) if not is_device_tensor(x) else None
         k = to_device(x)
         if is_device_tensor(x):
             k = k.clone()
         n = k.numel()
+        if dimension == "2d":
+            N = int(round(np.sqrt(n)))
+            if N * N != n or N < 2 or N & (N - 1):
+                print("New gridsize isn't a power of 2 !")
+                return None
+            low = N
+            while low > 2 and low * low > max(int(nmin), 4):
+                low //= 2
+            h = self._rq_hierarchy(A, M, n, low, "2d")
+            k, rho = self._rqmg_level(h, 0, k, nu1, nu2, max(int(nmin), low * low))
+            if shape is None:
+                return k, rho
+            return to_host(k).reshape(shape), rho
         if n < 2 or n & (n - 1):
             print("New gridsize isn't a power of 2 !")
             return None

@@ -730,6 +730,8 @@ int mgcmt_set_option(const char *name, int value) {
     mgcmt::g_fused_c5 = value;
     return MGCMT_OK;
   }
+  if (!strcmp(name, "band_gs_scan")) { mgcmt::g_band_gs_scan = value ? 1 : 0; return MGCMT_OK; }
+  if (!strcmp(name, "band_gs_split")) { mgcmt::g_band_gs_split = value ? 1 : 0; return MGCMT_OK; }
   return fail(MGCMT_ERR_ARG, std::string("unknown option ") + name);
 }
 

@@ -141,7 +141,7 @@ __global__ void band_galerkin_kernel(BandDev F, int nc, int ndiag_c, const int *
 // finished unknown per step.  v_in may alias v_out and y (in-place Gauss-Seidel).
 __global__ void __launch_bounds__(32) band_lower_solve_kernel(BandDev L, double shift, double wl, double cf, double cd,
                                                               double cu, double oscale, const cplx *vin, const cplx *f,
-                                                              cplx *y, const cplx *g, cplx *vout) {
+                                                              cplx *y, const cplx *g, cplx *vout, int scan) {
   __shared__ cplx coef[32][33];  // coef[r][lane]: wl * A[c0+lane, c0+r] for r < lane
   const int lane = threadIdx.x;
   const unsigned full = 0xffffffffu;
@@ -174,14 +174,147 @@ __global__ void __launch_bounds__(32) band_lower_solve_kernel(BandDev L, double 
     }
     __syncwarp(full);
     cplx mine = make_double2(0.0, 0.0);
+    // Usual case (every level of the multiband hierarchies except the few coarsest): inside the chunk a row couples
+    // only to its predecessor, so the block is the first-order recurrence x_l = p_l + q_l x_{l-1} -- solved by a
+    // 5-step inclusive scan over the affine maps instead of 32 dependent steps.
+    const unsigned pred = lane > 0 ? (1u << (lane - 1)) : 0u;
+    if (scan && __all_sync(full, (mask & ~pred) == 0u)) {
+      cplx p = cmul(t, dinv);
+      cplx q = make_double2(0.0, 0.0);
+      if (mask) q = cscale(-1.0, cmul(coef[lane - 1][lane], dinv));
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        cplx pp, qq;
+        pp.x = __shfl_up_sync(full, p.x, s);
+        pp.y = __shfl_up_sync(full, p.y, s);
+        qq.x = __shfl_up_sync(full, q.x, s);
+        qq.y = __shfl_up_sync(full, q.y, s);
+        if (lane >= s) {
+          p = cadd(p, cmul(q, pp));
+          q = cmul(q, qq);
+        }
+      }
+      mine = p;
+    } else {
 #pragma unroll 4
-    for (int r = 0; r < 32; ++r) {
-      const cplx cand = cmul(t, dinv);
-      cplx xr;
-      xr.x = __shfl_sync(full, cand.x, r);
-      xr.y = __shfl_sync(full, cand.y, r);
-      if (lane == r) mine = cand;
-      if ((mask >> r) & 1u) cfms(t, coef[r][lane], xr);
+      for (int r = 0; r < 32; ++r) {
+        const cplx cand = cmul(t, dinv);
+        cplx xr;
+        xr.x = __shfl_sync(full, cand.x, r);
+        xr.y = __shfl_sync(full, cand.y, r);
+        if (lane == r) mine = cand;
+        if ((mask >> r) & 1u) cfms(t, coef[r][lane], xr);
+      }
+    }
+    if (valid) {
+      y[i] = mine;
+      cplx o = cscale(oscale, mine);
+      if (g) o = cadd(o, g[i]);
+      vout[i] = o;
+    }
+    __syncwarp(full);
+    __threadfence_block();
+  }
+}
+
+// ---- the same sweep in two launches (default): everything that only needs OLD values first, fully parallel ...
+//   rhs_i = cf f_i + cd d_i v_i - cu sum_{off > 0} A_s[i, i+off] v[i+off]
+__global__ void band_upper_rhs_kernel(BandDev L, double shift, double cf, double cd, double cu, const cplx *vin,
+                                      const cplx *f, cplx *rhs) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.n; i += gridDim.x * blockDim.x) {
+    cplx t = make_double2(0.0, 0.0);
+    if (cf != 0.0) t = cscale(cf, f[i]);
+    if (cd != 0.0) {
+      cplx d = L.vals[(size_t)L.idiag * L.n + i];
+      d.x -= shift;
+      t = cadd(t, cscale(cd, cmul(d, vin[i])));
+    }
+    if (cu != 0.0)
+      for (int k = L.idiag + 1; k < L.ndiag; ++k) {   // offsets ascend: the diagonals after the main one are the upper ones
+        const int j = i + L.offs[k];
+        if (j >= L.n) break;
+        cfms(t, cscale(cu, L.vals[(size_t)k * L.n + i]), vin[j]);
+      }
+    rhs[i] = t;
+  }
+}
+
+// ... then the forward substitution proper (one warp): (D + wl strict_lower(A_s)) y = rhs, v_out = oscale y + g.  Only
+// the lower diagonals are touched here; their offsets sit in shared memory and their loads are issued four at a time.
+__global__ void __launch_bounds__(32) band_lower_solve2_kernel(BandDev L, double shift, double wl, double oscale,
+                                                               const cplx *rhs, cplx *y, const cplx *g, cplx *vout, int scan) {
+  __shared__ cplx coef[32][33];
+  __shared__ int s_off[kBandMaxDiags];
+  const int lane = threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  const int nlow = L.idiag;   // offsets ascend: diagonals 0 .. idiag-1 are the lower ones
+  for (int k = lane; k < nlow; k += 32) s_off[k] = L.offs[k];
+  __syncwarp(full);
+  for (int c0 = 0; c0 < L.n; c0 += 32) {
+    const int i = c0 + lane;
+    const bool valid = i < L.n;
+    cplx t = make_double2(0.0, 0.0), dinv = make_double2(1.0, 0.0);
+    unsigned mask = 0u;
+    if (valid) {
+      cplx d = L.vals[(size_t)L.idiag * L.n + i];
+      d.x -= shift;
+      dinv = crecip(d);
+      t = rhs[i];
+    }
+    for (int base = 0; base < nlow; base += 4) {
+      cplx a[4], xv[4];
+      int jj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = base + u;
+        int j = -1;
+        if (valid && k < nlow) j = i + s_off[k];
+        if (j < 0) j = -1;
+        jj[u] = j;
+        a[u] = (j >= 0) ? L.vals[(size_t)k * L.n + i] : make_double2(0.0, 0.0);
+        xv[u] = (j >= 0 && j < c0) ? y[j] : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (jj[u] < 0) continue;
+        if (jj[u] < c0) {
+          cfms(t, cscale(wl, a[u]), xv[u]);
+        } else {
+          coef[jj[u] - c0][lane] = cscale(wl, a[u]);
+          mask |= 1u << (jj[u] - c0);
+        }
+      }
+    }
+    __syncwarp(full);
+    cplx mine = make_double2(0.0, 0.0);
+    const unsigned pred = lane > 0 ? (1u << (lane - 1)) : 0u;
+    if (scan && __all_sync(full, (mask & ~pred) == 0u)) {
+      cplx p = cmul(t, dinv);
+      cplx q = make_double2(0.0, 0.0);
+      if (mask) q = cscale(-1.0, cmul(coef[lane - 1][lane], dinv));
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        cplx pp, qq;
+        pp.x = __shfl_up_sync(full, p.x, s);
+        pp.y = __shfl_up_sync(full, p.y, s);
+        qq.x = __shfl_up_sync(full, q.x, s);
+        qq.y = __shfl_up_sync(full, q.y, s);
+        if (lane >= s) {
+          p = cadd(p, cmul(q, pp));
+          q = cmul(q, qq);
+        }
+      }
+      mine = p;
+    } else {
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const cplx cand = cmul(t, dinv);
+        cplx xr;
+        xr.x = __shfl_sync(full, cand.x, r);
+        xr.y = __shfl_sync(full, cand.y, r);
+        if (lane == r) mine = cand;
+        if ((mask >> r) & 1u) cfms(t, coef[r][lane], xr);
+      }
     }
     if (valid) {
       y[i] = mine;
@@ -281,6 +414,11 @@ __global__ void band_gemv_kernel(int n, const cplx *aug, const cplx *f, cplx *y)
   if (lane == 0) y[warp] = acc;
 }
 
+}  // namespace
+int g_band_gs_scan = 1;   // mgcmt_set_option("band_gs_scan", 0|1): scan form of the in-chunk recurrence (A/B, tests)
+int g_band_gs_split = 1;  // mgcmt_set_option("band_gs_split", 0|1): old-value part of the sweep in its own parallel launch
+namespace {
+
 int blocks_for(long long n) {
   long long b = (n + 255) / 256;
   if (b > 148 * 8) b = 148 * 8;
@@ -325,9 +463,17 @@ cudaError_t launch_band_galerkin(const BandDev &F, int nc, int ndiag_c, const in
 
 cudaError_t launch_band_lower_solve(const BandDev &L, double shift, double wl, double cf, double cd, double cu,
                                     double oscale, const double *vin, const double *f, double *y, const double *g,
-                                    double *vout, cudaStream_t s) {
+                                    double *vout, double *rhs_scratch, cudaStream_t s) {
+  if (g_band_gs_split && rhs_scratch) {
+    band_upper_rhs_kernel<<<blocks_for(L.n), 256, 0, s>>>(L, shift, cf, cd, cu, (const cplx *)vin, (const cplx *)f,
+                                                          (cplx *)rhs_scratch);
+    band_lower_solve2_kernel<<<1, 32, 0, s>>>(L, shift, wl, oscale, (const cplx *)rhs_scratch, (cplx *)y, (const cplx *)g,
+                                              (cplx *)vout, g_band_gs_scan);
+    count_launch(2);
+    return cudaGetLastError();
+  }
   band_lower_solve_kernel<<<1, 32, 0, s>>>(L, shift, wl, cf, cd, cu, oscale, (const cplx *)vin, (const cplx *)f, (cplx *)y,
-                                           (const cplx *)g, (cplx *)vout);
+                                           (const cplx *)g, (cplx *)vout, g_band_gs_scan);
   count_launch();
   return cudaGetLastError();
 }

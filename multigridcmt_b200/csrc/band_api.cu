@@ -112,13 +112,13 @@ int band_smooth(mgcmt_band *h, int level, int smoother, int nu, double shift, do
   }
   if (smoother == MGCMT_SMOOTH_GSLEX) {
     if (omega == 1.0) {
-      for (int i = 0; i < nu; ++i) CU(launch_band_lower_solve(L.dev, shift, 1.0, 1.0, 0.0, 1.0, 1.0, v, f, v, nullptr, v, s));
+      for (int i = 0; i < nu; ++i) CU(launch_band_lower_solve(L.dev, shift, 1.0, 1.0, 0.0, 1.0, 1.0, v, f, v, nullptr, v, L.tmp, s));
       return MGCMT_OK;
     }
     // sor, quirk Q6: v <- (D - wL)^-1 ((1-w) D + w U) v + w (D - L)^-1 f
-    CU(launch_band_lower_solve(L.dev, shift, 1.0, 1.0, 0.0, 0.0, omega, v, f, L.y, nullptr, L.g, s));
+    CU(launch_band_lower_solve(L.dev, shift, 1.0, 1.0, 0.0, 0.0, omega, v, f, L.y, nullptr, L.g, L.tmp, s));
     for (int i = 0; i < nu; ++i)
-      CU(launch_band_lower_solve(L.dev, shift, omega, 0.0, 1.0 - omega, omega, 1.0, v, f, L.y, L.g, v, s));
+      CU(launch_band_lower_solve(L.dev, shift, omega, 0.0, 1.0 - omega, omega, 1.0, v, f, L.y, L.g, v, L.tmp, s));
     return MGCMT_OK;
   }
   return set_error(MGCMT_ERR_ARG, "banded operators take the wjacobi, gseidel and sor smoothers (red-black needs a radius-1 stencil)");

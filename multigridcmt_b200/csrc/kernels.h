@@ -114,6 +114,7 @@ cudaError_t launch_scale_to(long long n, const double *x, const double *sumsq, d
 // band.cu: general banded complex128 operators (1-D multiband Hamiltonians); vectors are complex interleaved
 constexpr int kBandMaxCoarse = 512;  // largest coarsest level the dense complex solve takes
 constexpr int kBandMaxDiags = 96;
+extern int g_band_gs_scan, g_band_gs_split;
 cudaError_t launch_band_apply(const BandDev &L, double shift, const double *x, double *y, cudaStream_t s);
 cudaError_t launch_band_jacobi(const BandDev &L, double shift, double omega, const double *vin, const double *f,
                                double *vout, cudaStream_t s);
@@ -124,7 +125,7 @@ cudaError_t launch_band_galerkin(const BandDev &F, int nc, int ndiag_c, const in
                                  cudaStream_t s);
 cudaError_t launch_band_lower_solve(const BandDev &L, double shift, double wl, double cf, double cd, double cu,
                                     double oscale, const double *vin, const double *f, double *y, const double *g,
-                                    double *vout, cudaStream_t s);
+                                    double *vout, double *rhs_scratch, cudaStream_t s);
 cudaError_t launch_band_inverse(const BandDev &L, double shift, double *aug, int *status, cudaStream_t s);
 cudaError_t launch_band_gemv(int n, const double *aug, const double *f, double *y, cudaStream_t s);
 

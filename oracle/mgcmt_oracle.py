@@ -375,17 +375,19 @@ class Solver:
             g = np.array(2 * (A.dot(x) - rho * M.dot(x)))
         return x, rho
 
-    def vcycle_rqmg(self, x, A, M, nu1=4, nu2=4, nmin=2):
-        # MGCMTSolver.py:99-122 (1-D transfer operators only, D6)
+    def vcycle_rqmg(self, x, A, M, nu1=4, nu2=4, nmin=2, dimension="1d"):
+        # MGCMTSolver.py:99-122 (1-D transfer operators only, D6).  dimension="2d" is NOT in the reference: the same
+        # recursion with the 2-D transfer operators (CPU twin of the product's extension; parity unpinned for 2-D).
         k = np.array(x)
         n = len(k)
         k, rho = self.rqmin(A, k, M, nu=nu1)
-        if n > nmin:
-            P = self.stencil_maker.interpolation(n // 2, n)
-            R = self.stencil_maker.restriction(n, n // 2)
+        g = n if dimension == "1d" else int(round(math.sqrt(n)))
+        if n > nmin and g > 2:
+            P = self.stencil_maker.interpolation(g // 2, g, dimension=dimension)
+            R = self.stencil_maker.restriction(g, g // 2, dimension=dimension)
             Ac = R * A * P
             Mc = R * M * P
-            c, rho = self.vcycle_rqmg(R * k, Ac, Mc, nu1=nu1, nu2=nu2, nmin=nmin)
+            c, rho = self.vcycle_rqmg(R * k, Ac, Mc, nu1=nu1, nu2=nu2, nmin=nmin, dimension=dimension)
             k = k + P * c
             k, rho = self.rqmin(A, k, M, nu=nu2)
         return k, rho

@@ -522,6 +522,28 @@ def test_rq_family_matches_reference_golden(prod, golden, o):
     assert out.shape == (64, 2) and rel(out[:, 0], want[:, 0]) < 1e-6
 
 
+def test_rq_family_2d_extension(prod, o):
+    """rqmin on a 2-D operator, and vcycle_rqmg(dimension="2d") -- an extension (the reference's RQMG is 1-D only,
+    SURVEY.md 8(f) row 4): against the oracle's twin of the same recursion, and converging to the closed-form value"""
+    sm, s, _ = prod
+    N = 32
+    H = sp.csr_matrix((-1. / np.pi ** 2) * sm.laplacian(N, "2d"))
+    M = sp.eye(N * N, format="csr")
+    x0 = np.random.RandomState(3).random_sample(N * N)
+    x, rho = s.rqmin(H, x0.copy(), M, nu=4)
+    ox, orho = o[1].rqmin(H, x0.copy(), M, nu=4)
+    assert x.shape == (N * N,) and rel(x, ox) < 1e-9 and abs(rho - orho) < 1e-10 * abs(orho)
+    x, ox = x0.copy(), x0.copy()
+    for it in range(5):
+        x, rho = s.vcycle_rqmg(x, H, M, nmin=64, dimension="2d")
+        ox, orho = o[1].vcycle_rqmg(ox, H, M, nmin=64, dimension="2d")
+        if it < 2:
+            assert rel(x, ox) < 1e-7 and abs(rho - orho) < 1e-9 * abs(orho)
+    assert abs(rho - orho) < 1e-8 * abs(orho)
+    assert abs(rho - orc.well_eigenvalue_2d(N, 1, 1)) < 1e-5
+    assert s.vcycle_rqmg(np.ones(48 * 48), H, M, dimension="2d") is None
+
+
 def test_vcycle_rq_fused_stage(T, prod):
     """mgcmt_vcycle_rq: same iterate as mgcmt_vcycle, Rayleigh sums == a separate pass (fused stage at 512^2, fallback at 32^2)"""
     import ctypes as C
