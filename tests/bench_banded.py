@@ -1,6 +1,7 @@
 """Time the banded complex V-cycle (multiband Hamiltonians, ThesisProblem.py sizes and larger) on the GPU,
-with the numpy/scipy oracle on the host beside it.  Not part of bench.py's headline: a side measurement for DESIGN.md.
-usage: python tools/bench_banded.py [gridpoints_per_band ...]"""
+with the numpy/scipy oracle on the host beside it as checker and CPU reference.  Not part of bench.py's headline: a side
+measurement for DESIGN.md.  Lives under tests/ because it uses oracle/ (test infrastructure); not collected by pytest.
+usage: python tests/bench_banded.py [gridpoints_per_band ...]"""
 import json
 import os
 import sys
