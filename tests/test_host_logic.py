@@ -203,3 +203,86 @@ def test_routing_picks_the_banded_path(multiband):
     with pytest.raises(UnsupportedOperator):
         route(L2, "2d", np.zeros(64), np.zeros(64, dtype=complex))
     assert MGCMTSolver._guess_dimension(sp.csc_matrix(multiband["z7_H"]), 256) == "1d"
+
+
+# ---------------------------------------------------------------------------------------------------
+# numpy twins of the banded device formulas (csrc/band.cu), pinned to the REAL reference's outputs on CPU:
+# a change of the formulas has to pass here before it goes to the GPU
+def _galerkin_twin(op):
+    """band_galerkin_kernel + the coarse-offset rule of mgcmt_band_create, restated with numpy"""
+    from multigridcmt_b200.banded import BandedOperator
+    n, offs = op.n, [int(o) for o in op.offsets]
+    m = n // 2
+    cs = sorted({D for d in offs for D in range((d - 1) // 2, (d + 2) // 2 + 1) if -m < D < m})
+    vals = np.zeros((len(cs), m), dtype=complex)
+    for kc, D in enumerate(cs):
+        for J in range(m):
+            K = J + D
+            if not 0 <= K < m:
+                continue
+            acc = 0.0
+            for a in range(3):
+                ia = 2 * J + a
+                if ia >= n:
+                    continue
+                for b in range(3):
+                    ib = 2 * K + b
+                    d = 2 * D + b - a
+                    if ib >= n or d not in offs:
+                        continue
+                    acc += (0.5 if a == 1 else 0.25) * (1.0 if b == 1 else 0.5) * op.vals[offs.index(d), ia]
+            vals[kc, J] = acc
+    return BandedOperator(m, cs, vals)
+
+
+@pytest.mark.parametrize("tag", ["z0", "z7", "x7"])
+def test_banded_galerkin_formula_matches_reference_rap(multiband, tag):
+    import scipy.sparse as sp
+    from multigridcmt_b200.banded import BandedOperator
+    op = BandedOperator.from_sparse(sp.csc_matrix(multiband[tag + "_H"]))
+    coarse = _galerkin_twin(op)
+    ref = multiband[tag + "_RAP"]
+    assert np.max(np.abs(coarse.tocsc().toarray() - ref)) <= 1e-14 * np.max(np.abs(ref))
+    assert len(coarse.offsets) == (3 if tag == "z0" else 15)
+    # and once more down: the diagonal count of the 4-band operators stays at 15
+    if tag != "z0":
+        assert len(_galerkin_twin(coarse).offsets) == 15
+
+
+@pytest.mark.parametrize("tag", ["z7", "x7"])
+def test_banded_substitution_parameters_match_reference(multiband, tag):
+    """(wl, cf, cd, cu, oscale) of band_lower_solve: gseidel = (1,1,0,1,1); sor = (1,1,0,0,w) then (w,0,1-w,w,1) + g"""
+    H = multiband[tag + "_H"]
+    n = H.shape[0]
+    As = H - np.eye(n) * float(multiband[tag + "_shift"])
+    x, f = multiband[tag + "_x"], multiband[tag + "_f"]
+    D, Lo, Up = np.diag(np.diag(As)), np.tril(As, -1), np.triu(As, 1)
+
+    def lower_solve(wl, cf, cd, cu, oscale, vin, g):
+        y = np.linalg.solve(D + wl * Lo, cf * f + cd * (D @ vin) - cu * (Up @ vin))
+        return oscale * y + (0 if g is None else g)
+    v = x.copy()
+    for _ in range(3):
+        v = lower_solve(1, 1, 0, 1, 1, v, None)
+    assert np.linalg.norm(v - multiband[tag + "_gs"]) < 1e-13 * np.linalg.norm(v)
+    w = 1.3
+    g = lower_solve(1, 1, 0, 0, w, x, None)
+    v = x.copy()
+    for _ in range(3):
+        v = lower_solve(w, 0, 1 - w, w, 1, v, g)
+    assert np.linalg.norm(v - multiband[tag + "_sor"]) < 1e-13 * np.linalg.norm(v)
+    # the scan form of the in-chunk recurrence x_l = p_l + q_l x_{l-1} (Hillis-Steele over affine maps)
+    rng = np.random.RandomState(0)
+    p = rng.random_sample(32) + 1j * rng.random_sample(32)
+    q = 0.5 * (rng.random_sample(32) + 1j * rng.random_sample(32))
+    q[0] = 0
+    seq = np.zeros(32, dtype=complex)
+    for l in range(32):
+        seq[l] = p[l] + (q[l] * seq[l - 1] if l else 0)
+    P, Q, s = p.copy(), q.copy(), 1
+    while s < 32:
+        Pn, Qn = P.copy(), Q.copy()
+        Pn[s:] = P[s:] + Q[s:] * P[:-s]
+        Qn[s:] = Q[s:] * Q[:-s]
+        P, Q, s = Pn, Qn, 2 * s
+    assert np.max(np.abs(P - seq)) < 1e-14
