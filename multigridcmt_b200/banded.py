@@ -17,7 +17,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
-from .operators import UnsupportedOperator
+from .operators import UnsupportedOperator, data_fingerprint
 
 MAX_DIAGS = 96          # kBandMaxDiags in csrc/kernels.h
 MAX_COARSEST = 512      # kBandMaxCoarse
@@ -174,10 +174,7 @@ def recognise_banded(A):
     """BandedOperator.from_sparse with a small identity cache (drivers pass the same matrix every call)."""
     if isinstance(A, BandedOperator):
         return A
-    data = getattr(A, "data", None)
-    fp = (id(A), A.shape, getattr(A, "nnz", None),
-          data.ctypes.data if isinstance(data, np.ndarray) else None,
-          complex(data[:8].sum()) if isinstance(data, np.ndarray) and data.size else 0.0)
+    fp = (id(A), A.shape, getattr(A, "nnz", None)) + data_fingerprint(A)
     hit = _RECOGNISED.get(id(A))
     if hit is not None and hit[0] == fp:
         return hit[1]

@@ -521,6 +521,12 @@ class NativeSlabBlock:
         self._ptrs = (C.c_void_p * self.k)
         self._shifts = (C.c_double * self.k)
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self):
         lib = _lib.load()
         if getattr(self, "handle", None):

@@ -286,3 +286,23 @@ def test_banded_substitution_parameters_match_reference(multiband, tag):
         Qn[s:] = Q[s:] * Q[:-s]
         P, Q, s = Pn, Qn, 2 * s
     assert np.max(np.abs(P - seq)) < 1e-14
+
+
+def test_recognition_cache_notices_in_place_edits():
+    """drivers reuse one matrix object; editing its values in place (e.g. adding a potential) must not hit a stale entry"""
+    import scipy.sparse as sp
+    from multigridcmt_b200 import MGCMTStencilMaker
+    from multigridcmt_b200.banded import recognise_banded
+    from multigridcmt_b200.operators import recognise
+    L = sp.csc_matrix(MGCMTStencilMaker().laplacian(64))
+    a = recognise(L, "1d")
+    assert recognise(L, "1d") is a
+    L.data[-1] *= 2.0                      # far from the first few entries
+    b = recognise(L, "1d")
+    assert b is not a and b.col[1][-1] == 2.0 * a.col[1][-1]
+    C = sp.csc_matrix(np.diag(np.arange(1, 9) + 0j) + np.diag(np.ones(6), 2))
+    c = recognise_banded(C)
+    assert recognise_banded(C) is c
+    C.data[-1] += 1j
+    d = recognise_banded(C)
+    assert d is not c and not d.is_real
