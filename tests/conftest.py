@@ -31,3 +31,14 @@ def multiband():
     """Outputs of the REAL reference on its own 4-band Hamiltonians (oracle/make_golden_multiband.py)."""
     import numpy as np
     return np.load(MULTIBAND)
+
+
+CONFIG0 = os.path.join(ROOT, "tests", "golden", "config0_golden.npz")
+
+
+@pytest.fixture(scope="session")
+def config0():
+    """BASELINE config 0 (1-D well, 1024 points, Gauss-Seidel V-cycles) run by the REAL reference
+    (oracle/make_golden_config0.py)."""
+    import numpy as np
+    return np.load(CONFIG0)

@@ -1051,3 +1051,30 @@ def test_native_slab_block_single_rank(T, prod):
     for sv in svs:
         sv.close()
     nb.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 0 at its own size, against the REAL reference (oracle/make_golden_config0.py): 1-D well, 1024 points,
+# shift method with Gauss-Seidel V-cycles + Gram-Schmidt, through the drop-in classes
+def test_config0_matches_reference_golden(prod, config0):
+    import functools
+    sm, s, p = prod
+    n, n0, low, iters, k = [int(x) for x in config0["meta"]]
+    H = (-1. / np.pi ** 2) * sm.laplacian(n)
+    V = config0["V0"].copy()
+    lam = np.zeros((iters, k))
+    for it in range(iters):
+        for j in range(k):
+            w = s.vcycle(np.zeros((n, 1)), V[:, j].copy(), H, sm, shift=config0["shifts"][j], lowest_level=low,
+                         smoother=s.gseidel)
+            V[:, j] = w / np.linalg.norm(w)
+            lam[it, j] = np.dot(V[:, j], H.dot(V[:, j]))
+        V = p.gramschmidt(V)
+    assert np.max(np.abs(lam - config0["lam"])) < 1e-9
+    assert rel(V, config0["V"]) < 1e-8
+    f = config0["f"]
+    w = s.vcycle(np.zeros((n, 1)), f.copy(), H, sm, shift=config0["shifts"][0], lowest_level=low)
+    assert rel(w, config0["vc_wj"]) < 1e-9
+    w = s.vcycle(np.zeros((n, 1)), f.copy(), H, sm, shift=config0["shifts"][0], lowest_level=low,
+                 smoother=functools.partial(s.sor, omega=1.2))
+    assert rel(w, config0["vc_sor"]) < 1e-9

@@ -286,3 +286,31 @@ def test_multiband_shift_iteration_matches_reference(o, multiband, tag):
         lam.append(np.dot(v.conj(), H.dot(v)))
     assert np.max(np.abs(np.array(lam) - multiband[tag + "_it_lam"])) < 1e-11
     assert _crel(v, multiband[tag + "_it_v"]) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE config 0 at its own size: 1-D well, 1024 points, shift method with Gauss-Seidel V-cycles
+def test_config0_shift_loop_matches_reference(o, config0):
+    import functools
+    sm, s, p = o
+    n, n0, low, iters, k = [int(x) for x in config0["meta"]]
+    H = (-1. / np.pi ** 2) * sm.laplacian(n)
+    V = config0["V0"].copy()
+    lam = np.zeros((iters, k))
+    for it in range(iters):
+        for j in range(k):
+            w = s.vcycle(np.zeros((n, 1)), V[:, j].copy(), H, sm, shift=config0["shifts"][j], lowest_level=low,
+                         smoother=s.gseidel)
+            V[:, j] = w / np.linalg.norm(w)
+            lam[it, j] = V[:, j] @ (H @ V[:, j])
+        V = p.gramschmidt(V)
+    assert np.max(np.abs(lam - config0["lam"])) < 1e-12
+    assert np.linalg.norm(V - config0["V"]) < 1e-12 * np.linalg.norm(config0["V"])
+    f = config0["f"]
+    w = s.vcycle(np.zeros((n, 1)), f.copy(), H, sm, shift=config0["shifts"][0], lowest_level=low)
+    assert np.linalg.norm(w - config0["vc_wj"]) < 1e-13 * np.linalg.norm(w)
+    w = s.vcycle(np.zeros((n, 1)), f.copy(), H, sm, shift=config0["shifts"][0], lowest_level=low,
+                 smoother=functools.partial(s.sor, omega=1.2))
+    assert np.linalg.norm(w - config0["vc_sor"]) < 1e-13 * np.linalg.norm(w)
+    # and the loop does what the driver wants: the lowest eigenvalues of the 1024-point well
+    assert np.all(np.abs(lam[-1] - [orc.well_eigenvalue_1d(n, j + 1) for j in range(k)]) < 1e-4)
