@@ -238,14 +238,16 @@ def cpu_sample(n_cpu, lowest, repeats=1):
 def run_reference(args):
     """The reference arm: the CPU implementation of the path on the host cores.  The reference itself is Python 2 and
     cannot be installed or run on this box, so this is the C/OpenMP port of its arithmetic (kind "port") with all host
-    threads, on the bench workload (4096^2): each step = the 4 V(4,4)-cycles of one shift-method iteration."""
+    threads, on the bench workload of the same --gpus (4096^2; 16384^2 for N > 1): each step = the 4 V(4,4)-cycles of one
+    shift-method iteration, as many steps as fit the time budget."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
-    N = args.n or 4096
+    multi = (int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus > 1) and not args.replicas
+    N = args.n or (16384 if multi else 4096)      # the same workload as our arm at this --gpus (16384^2 when slab-decomposed)
     lowest = args.lowest
     h = c_oracle.WellHierarchy(N, lowest)
     P = interp1(N)
@@ -280,7 +282,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": warm, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "2D infinite well %d^2, lowest 4 eigenpairs, shift method: 4 x V(4,4) per step (CPU port of the "
                                "reference's arithmetic; the Python-2 reference itself cannot run here)" % N,
                    "smoother": "wjacobi", "lowest_level": lowest},
