@@ -306,3 +306,61 @@ def test_recognition_cache_notices_in_place_edits():
     C.data[-1] += 1j
     d = recognise_banded(C)
     assert d is not c and not d.is_real
+
+
+# ---------------------------------------------------------------------------------------------------
+# property tests of the host-side bookkeeping (hypothesis)
+def test_banded_round_trip_random_matrices():
+    import scipy.sparse as sp
+    from hypothesis import given, settings, strategies as st
+    from multigridcmt_b200.banded import BandedOperator
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(2, 40), st.lists(st.integers(-39, 39), min_size=1, max_size=6), st.integers(0, 2 ** 31 - 1), st.booleans())
+    def check(n, offs, seed, cplx):
+        rng = np.random.RandomState(seed)
+        offs = sorted({o for o in offs if -n < o < n})
+        if not offs:
+            offs = [0]
+        diags = []
+        for o in offs:
+            d = rng.random_sample(n - abs(o)) - 0.5
+            if cplx:
+                d = d + 1j * (rng.random_sample(n - abs(o)) - 0.5)
+            d[rng.random_sample(d.size) < 0.2] = 0       # explicit zeros must not matter
+            diags.append(d)
+        A = sp.diags(diags, offs, shape=(n, n), format="csc")
+        op = BandedOperator.from_sparse(A)
+        assert abs(op.tocsc() - A).max() == 0
+        assert 0 in op.offsets and np.all(np.diff(op.offsets) > 0)
+        assert op.is_real == (not np.any(A.toarray().imag))
+        x = rng.random_sample(n) + 1j * rng.random_sample(n)
+        y = np.zeros(n, dtype=complex)
+        for k, o in enumerate(op.offsets):              # the row-indexed storage the kernels use
+            for i in range(n):
+                if 0 <= i + o < n:
+                    y[i] += op.vals[k, i] * x[i + o]
+        assert np.allclose(y, A @ x, rtol=1e-13, atol=1e-13)
+    check()
+
+
+def test_plan_levels_invariants():
+    from hypothesis import given, settings, strategies as st
+    from multigridcmt_b200.slab import HALO, plan_levels
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(6, 15), st.sampled_from([1, 2, 4, 8]), st.sampled_from([128, 512, 2048]))
+    def check(logn, world, gather):
+        n = 1 << logn
+        if n % world:
+            return
+        nlev = plan_levels(n, world, gather)
+        own = n // world
+        for l in range(nlev):
+            assert (n >> l) > gather                       # only levels wider than gather_cols stay decomposed
+            assert (own >> l) >= 64 and (own >> l) >= 2 * HALO
+            assert own % (1 << (l + 1)) == 0               # cuts stay on even rows of every slab level
+        # maximal: the next level would break one of the rules
+        l = nlev
+        assert not ((n >> l) > gather and (own >> l) >= 64 and own % (1 << (l + 1)) == 0)
+    check()
