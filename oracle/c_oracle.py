@@ -60,6 +60,8 @@ def load():
         lib.orc_destroy.argtypes = [C.c_void_p]
         lib.orc_vcycle.restype = C.c_int
         lib.orc_vcycle.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
+        lib.orc_vcycle_smoother.restype = C.c_int
+        lib.orc_vcycle_smoother.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
         _lib = lib
     return _lib
 
@@ -78,10 +80,14 @@ class WellHierarchy:
         self._keep = (lo, di, up)
         self.h = load().orc_create(n, _p(lo), _p(di), _p(up), _p(lo), _p(di), _p(up), int(lowest))
 
-    def vcycle(self, v0, f, shift, nu1=4, nu2=4, omega=2.0 / 3.0):
+    def vcycle(self, v0, f, shift, nu1=4, nu2=4, omega=None, smoother="wjacobi"):
+        """smoother: "wjacobi" (omega default 2/3) or "rbgs" (four-colour Gauss-Seidel / SOR, omega default 1)"""
         v = np.ascontiguousarray(v0, dtype=np.float64).copy().reshape(-1)
         f = np.ascontiguousarray(f, dtype=np.float64).reshape(-1)
-        rc = load().orc_vcycle(self.h, float(shift), float(omega), int(nu1), int(nu2), _p(v), _p(f))
+        code = {"wjacobi": 0, "rbgs": 1}[smoother]
+        if omega is None:
+            omega = 2.0 / 3.0 if code == 0 else 1.0
+        rc = load().orc_vcycle_smoother(self.h, code, float(shift), float(omega), int(nu1), int(nu2), _p(v), _p(f))
         if rc:
             raise RuntimeError("C oracle: singular coarsest operator")
         return v

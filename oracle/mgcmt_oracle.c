@@ -171,6 +171,25 @@ static void jacobi(const level_t *L, double shift, double omega, int nu, double 
   if (a != v) memcpy(v, a, sizeof(double) * (size_t)n * n);
 }
 
+/* Red-black (four-colour) Gauss-Seidel / SOR, the CPU twin of the product's rbgs (NOT in the reference: its gseidelrb is
+ * dead code, MGCMTSolver.py:248-279; the ordering is the one oracle/mgcmt_oracle.py: Solver.rbgs defines): colours
+ * (i%2, j%2) in the order (0,0), (1,1), (0,1), (1,0); within a colour every unknown is relaxed with the latest values of
+ * the other colours -- points of one colour never neighbour each other, so a colour is one parallel pass, in place. */
+static void rbgs(const level_t *L, double shift, double omega, int nu, double *v, const double *f) {
+  const int n = L->n;
+  static const int col[4][2] = {{0, 0}, {1, 1}, {0, 1}, {1, 0}};
+  for (int it = 0; it < nu; ++it)
+    for (int c = 0; c < 4; ++c) {
+      const int pa = col[c][0], pb = col[c][1];
+#pragma omp parallel for schedule(static)
+      for (int i = pa; i < n; i += 2)
+        for (int j = pb; j < n; j += 2) {
+          const double d = (L->ma[1][i] * L->kb[1][j] + L->ka[1][i] * L->mb[1][j]) - shift;
+          v[(size_t)i * n + j] += omega * (f[(size_t)i * n + j] - apply_pt(L, shift, v, i, j)) / d;
+        }
+    }
+}
+
 static void residual_restrict(const level_t *L, double shift, const double *v, const double *f, double *r, double *rc) {
   const int n = L->n, nc = n / 2;
   double *zero = dalloc(n);
@@ -270,7 +289,12 @@ static void coarse_solve(level_t *L, const double *f, double *v) {
   }
 }
 
-static int cycle(hier_t *h, int l, double shift, double omega, int nu1, int nu2, double *v, const double *f) {
+static void smooth(const level_t *L, int smoother, double shift, double omega, int nu, double *v, const double *f, double *tmp) {
+  if (smoother == 1) rbgs(L, shift, omega, nu, v, f);
+  else jacobi(L, shift, omega, nu, v, f, tmp);
+}
+
+static int cycle(hier_t *h, int l, int smoother, double shift, double omega, int nu1, int nu2, double *v, const double *f) {
   level_t *L = &h->lev[l];
   if (l == h->nlev - 1) {
     if (!L->lu_valid || L->lu_shift != shift)
@@ -279,15 +303,20 @@ static int cycle(hier_t *h, int l, double shift, double omega, int nu1, int nu2,
     return 0;
   }
   level_t *C = &h->lev[l + 1];
-  jacobi(L, shift, omega, nu1, v, f, L->t);
+  smooth(L, smoother, shift, omega, nu1, v, f, L->t);
   residual_restrict(L, shift, v, f, L->t, C->f);
   memset(C->v, 0, sizeof(double) * (size_t)C->n * C->n);
-  if (cycle(h, l + 1, shift, omega, 4, 4, C->v, C->f)) return 1;   /* coarse levels always 4/4 (MGCMTSolver.py:320) */
+  if (cycle(h, l + 1, smoother, shift, omega, 4, 4, C->v, C->f)) return 1;   /* coarse levels always 4/4 (MGCMTSolver.py:320) */
   prolong_add(L, C->v, v);
-  jacobi(L, shift, omega, nu2, v, f, L->t);
+  smooth(L, smoother, shift, omega, nu2, v, f, L->t);
   return 0;
 }
 
 int orc_vcycle(hier_t *h, double shift, double omega, int nu1, int nu2, double *v, const double *f) {
-  return cycle(h, 0, shift, omega, nu1, nu2, v, f);
+  return cycle(h, 0, 0, shift, omega, nu1, nu2, v, f);
+}
+
+/* smoother: 0 = weighted Jacobi (MGCMTSolver.py:182-208), 1 = red-black Gauss-Seidel / SOR (see rbgs above) */
+int orc_vcycle_smoother(hier_t *h, int smoother, double shift, double omega, int nu1, int nu2, double *v, const double *f) {
+  return cycle(h, 0, smoother, shift, omega, nu1, nu2, v, f);
 }

@@ -16,3 +16,17 @@ def test_c_oracle_matches_numpy_oracle(N, low, shift, nu):
     want = osv.vcycle(v0.copy(), f.copy(), H, osm, nu1=nu[0], nu2=nu[1], shift=shift, lowest_level=low, dimension="2d")
     got = c_oracle.WellHierarchy(N, low).vcycle(v0, f, shift, nu1=nu[0], nu2=nu[1])
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-11
+
+
+@pytest.mark.parametrize("N,low,shift,omega", [(32, 8, 0.0, 1.0), (64, 8, 4.38639582, 1.0), (64, 8, 1.76659015, 1.15)])
+def test_c_oracle_rbgs_matches_numpy_oracle(N, low, shift, omega):
+    """the red-black (four-colour) smoother: C twin == numpy twin (Solver.rbgs), whole V-cycles"""
+    import functools
+    osm, osv = orc.StencilMaker(), orc.Solver()
+    H = (-1. / np.pi ** 2) * osm.laplacian(N, "2d")
+    rs = np.random.RandomState(100 + N)
+    f = rs.random_sample(N * N)
+    want = osv.vcycle(np.zeros(N * N), f.copy(), H, osm, shift=shift, lowest_level=low, dimension="2d",
+                      smoother=functools.partial(osv.rbgs, omega=omega))
+    got = c_oracle.WellHierarchy(N, low).vcycle(np.zeros(N * N), f, shift, smoother="rbgs", omega=omega)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-11
