@@ -397,6 +397,19 @@ def test_vcycle_matches_c_oracle_at_large_sizes(prod, N, low, shift):
     assert rel(got, want) < 1e-10, rel(got, want)
 
 
+def test_rbgs_vcycle_matches_c_oracle_at_1024(prod):
+    """BASELINE config 3's smoother at a size scipy cannot reach in seconds: red-black (four-colour) Gauss-Seidel
+    V-cycle against the C twin (tests/test_c_oracle.py holds that twin to the numpy one)"""
+    import c_oracle
+    sm, s, _ = prod
+    N, low, shift = 1024, 8, 1.76659015
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    f = np.random.RandomState(5).random_sample(N * N)
+    got = s.vcycle(np.zeros(N * N), f.copy(), H, sm, shift=shift, lowest_level=low, dimension="2d", smoother=s.rbgs)
+    want = c_oracle.WellHierarchy(N, low).vcycle(np.zeros(N * N), f, shift, smoother="rbgs")
+    assert rel(got, want) < 1e-9, rel(got, want)
+
+
 def test_vcycle_api_conventions(prod, capsys, T):
     sm, s, _ = prod
     L = sm.laplacian(2)
