@@ -307,7 +307,7 @@ int fused_up(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu2,
   const int first = left > maxpass ? maxpass : left;
   if (l == 0) prof_mark(s);
   // finest level, Rayleigh quotient requested and this pass is the last one: the up leg also leaves the partial sums
-  const int slots = (l == 0 && h->rq_out && !gs && first == 4 && left == 4 && !use_tile(h, l)) ? fused_rq_slots(L.dev) : 0;
+  const int slots = (l == 0 && h->rq_out && first == 4 && left == 4 && !use_tile(h, l)) ? fused_rq_slots(L.dev, gs ? 1 : 0) : 0;
   if (slots > 0) {
     if (slots > h->rq_slots) {
       cudaFree(h->rq_partials);
@@ -315,7 +315,8 @@ int fused_up(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu2,
       CU(cudaMalloc(&h->rq_partials, sizeof(double) * 2 * slots));
       h->rq_slots = slots;
     }
-    CU(launch_fused_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, a, f, b, e, h->rq_partials, s));
+    if (gs) CU(launch_fused_gs_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, a, f, b, e, h->rq_partials, s));
+    else CU(launch_fused_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, a, f, b, e, h->rq_partials, s));
     CU(launch_finish(2, slots, h->rq_partials, h->rq_out, s));
     h->rq_done = true;
   } else {
@@ -447,6 +448,22 @@ static int build_hier(mgcmt_hier_t **out, int nrows_glob, int ncols, int coarsen
     L.dev.nrows_coarse = 0;
     L.dev.rq_lo = slab ? halo : 0;
     L.dev.rq_hi = slab ? halo + own : L.dev.nrows;
+    L.dev.uni = 0;
+    L.dev.uni_c = L.dev.uni_d = 0.0;
+    if (l == 0 && coarsen_rows && nr >= 2 && nc >= 2) {
+      // constant 5-point stencil (the infinite well, 2DPot.py:25-26)?  Then the legs of this level run in fused_uni.cu
+      const double c = h_col_lo[1];
+      bool uni = true;
+      for (int i = 0; i < nr && uni; ++i)
+        uni = h_row_di[i] == h_row_di[0] && (i == 0 || h_row_lo[i] == c) && (i + 1 == nr || h_row_up[i] == c);
+      for (int j = 0; j < nc && uni; ++j)
+        uni = h_col_di[j] == h_col_di[0] && (j == 0 || h_col_lo[j] == c) && (j + 1 == nc || h_col_up[j] == c);
+      if (uni && c != 0.0) {
+        L.dev.uni = 1;
+        L.dev.uni_c = c;
+        L.dev.uni_d = h_row_di[0] + h_col_di[0];
+      }
+    }
     if (slab) {
       if (l + 1 < nlev) {  // coarse level is a slab piece too
         L.dev.crow_shift = halo / 2;
@@ -720,6 +737,13 @@ int mgcmt_set_option(const char *name, int value) {
   if (!strcmp(name, "fused_min_cols")) { g_opt_fused_min_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tile_max_cols")) { g_opt_tile_max_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tail_max_cols")) { g_opt_tail_max_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "fused_uni")) { mgcmt::g_fused_uni = value ? 1 : 0; return MGCMT_OK; }
+  if (!strcmp(name, "uni_wfreg")) { mgcmt::g_uni_wfreg = value ? 1 : 0; return MGCMT_OK; }
+  if (!strcmp(name, "uni_minctas")) {
+    if (value != 0 && value != 2 && value != 3) return fail(MGCMT_ERR_ARG, "uni_minctas must be 0 (default), 2 or 3");
+    mgcmt::g_uni_minctas = value;
+    return MGCMT_OK;
+  }
   if (!strcmp(name, "fused_c9")) {
     if (value != 0 && value != 2 && value != 4) return fail(MGCMT_ERR_ARG, "fused_c9 must be 0 (auto), 2 or 4");
     mgcmt::g_fused_c9 = value;

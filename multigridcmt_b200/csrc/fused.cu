@@ -495,31 +495,38 @@ static size_t fused_smem_bytes(bool prolong, int rows_per_chunk, int nstage) {
   return b;
 }
 
+// ctas_per_sm: resident CTAs per SM of the instantiation that will run (occupancy query); the chunk height is chosen
+// so that the grid fills whole waves (leg_rows_per_chunk, fused_uni.cu) -- a grid a few CTAs over a wave used to cost
+// the 9-point levels a second pass of 24 CTAs
 template <int NU, int C>
-static void fused_geometry(const LevelDev &L, int *gx, int *rpc_out) {
+static void fused_geometry(const LevelDev &L, int ctas_per_sm, int nstage, int *gx, int *rpc_out) {
   constexpr int USEFUL = 32 * C - 2 * ((NU + 3) & ~1);
   const int strips = (L.ncols + USEFUL - 1) / USEFUL;
   *gx = (strips + kWarps - 1) / kWarps;
-  int rpc = 128;
-  while (rpc > 16 && (long long)*gx * ((L.nrows + rpc - 1) / rpc) < 264) rpc >>= 1;  // ~90 % of 148 SMs x 2 CTAs
-  if (rpc > L.nrows) rpc = L.nrows;  // nrows is a power of two >= 2 here (even chunks)
-  *rpc_out = rpc;
+  *rpc_out = leg_rows_per_chunk(L.nrows, *gx, ctas_per_sm * num_sms(), nstage, 128);
 }
 
 template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS>
 static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega, const double *v_in,
                                   const double *f, double *v_out, const double *e_coarse, double *r_coarse,
-                                  cudaStream_t s) {
-  int gx, rpc;
-  fused_geometry<NU, C>(L, &gx, &rpc);
-  const size_t smem = fused_smem_bytes<C>(PROLONG, rpc, NU + (RESTRICT ? 1 : 0));
+                                  cudaStream_t s, int *slots_out = nullptr) {
   auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C, GS>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);
+  static int occ = 0;  // per instantiation: resident CTAs per SM with a 128-row chunk's shared memory
+  if (!occ) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, fused_smem_bytes<C>(PROLONG, 128, NSTAGE));
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
   }
+  int gx, rpc;
+  fused_geometry<NU, C>(L, occ, NSTAGE, &gx, &rpc);
+  if (slots_out) {
+    *slots_out = gx * ((L.nrows + rpc - 1) / rpc) * kWarps;
+    return cudaSuccess;
+  }
+  const size_t smem = fused_smem_bytes<C>(PROLONG, rpc, NSTAGE);
   dim3 grid(gx, (L.nrows + rpc - 1) / rpc);
   kern<<<grid, kWarps * 32, smem, s>>>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, rpc);
   count_launch();
@@ -529,7 +536,7 @@ static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega,
 template <bool FIVE, int NU, int C, int GS = 0>
 static cudaError_t dispatch_mode(const LevelDev &L, int mode, double shift, double omega, const double *v_in,
                                  const double *f, double *v_out, const double *e_coarse, double *r_coarse,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, int *slots_out = nullptr) {
   switch (mode) {
     case FUSED_SMOOTH:
       if (NU == 0) return cudaErrorInvalidValue;
@@ -542,7 +549,7 @@ static cudaError_t dispatch_mode(const LevelDev &L, int mode, double shift, doub
       return launch_fused_t<FIVE, NU, true, false, false, C, GS>(L, shift, omega, v_in, f, v_out, e_coarse, nullptr, s);
     case FUSED_UP_RQ:  // only the Jacobi NU = 4 up leg of the finest level carries the Rayleigh-quotient stage
       if constexpr (GS == 0 && NU == 4 && FIVE && C == 4)
-        return launch_fused_t<true, 4, true, true, false, 4, 0>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+        return launch_fused_t<true, 4, true, true, false, 4, 0>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out);
       else
         return cudaErrorInvalidValue;
   }
@@ -554,6 +561,11 @@ cudaError_t launch_fused_gs_leg(const LevelDev &L, int mode, int sweeps, double 
                                 const double *v_in, const double *f, double *v_out, const double *e_coarse,
                                 double *r_coarse, cudaStream_t s) {
   if (L.nrows < 2) return cudaErrorInvalidValue;
+  if (uni5_available(L)) return launch_uni5_leg(L, 1, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  if (sweeps == 0) {  // no smoothing (nu1 = 0 or nu2 = 0): the colour order does not matter, the Jacobi leg's transfer is the same
+    return L.five ? dispatch_mode<true, 0, 2>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s)
+                  : dispatch_mode<false, 0, 2>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  }
   if (L.five) {
     switch (sweeps) {
       case 1: return dispatch_mode<true, 2, 2, 1>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
@@ -574,11 +586,13 @@ int g_fused_c5 = MGCMT_FUSED_C5;  // columns per lane on the 5-point level (2 or
 
 // number of per-warp partial-sum slots a FUSED_UP_RQ launch on this level writes (2 * slots doubles), or 0 if that
 // mode is not available for the level
-int fused_rq_slots(const LevelDev &L) {
-  if (!L.five || g_fused_c5 != 4 || L.nrows < 2) return 0;
-  int gx, rpc;
-  fused_geometry<4, 4>(L, &gx, &rpc);
-  return gx * ((L.nrows + rpc - 1) / rpc) * kWarps;
+int fused_rq_slots(const LevelDev &L, int gs) {
+  if (uni5_available(L)) return uni5_rq_slots(L, gs);
+  if (gs || !L.five || g_fused_c5 != 4 || L.nrows < 2) return 0;
+  int slots = 0;
+  if (dispatch_mode<true, 4, 4>(L, FUSED_UP_RQ, 0.0, 1.0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &slots) != cudaSuccess)
+    return 0;
+  return slots;
 }
 
 int g_fused_c9 = 0;  // columns per lane on 9-point levels: 2, 4, or 0 = 4 on levels >= 4096 wide (enough strips to
@@ -588,6 +602,7 @@ cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, 
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,
                              double *r_coarse, cudaStream_t s) {
   if (L.nrows < 2) return cudaErrorInvalidValue;  // 2-D levels only
+  if (uni5_available(L)) return launch_uni5_leg(L, 0, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
 #define NU_CASE(NUV)                                                                                         \
   case NUV:                                                                                                  \
     if (L.five && g_fused_c5 == 4)                                                                           \

@@ -1,0 +1,537 @@
+// fused_uni.cu -- the V-cycle legs of fused.cu for levels whose operator is a CONSTANT 5-point stencil
+// (the infinite well of 2DPot*.py on its finest grid: H = (-1/pi^2) laplacian(N, "2d"), MGCMTStencilMaker.py:15-25).
+//
+//   down leg:  v_out = S^NU(v_in; f),   r_coarse = R (f - A_s v_out)        (MGCMTSolver.py:313-315)
+//   up leg:    v_out = S^NU(v_in + P e_coarse; f)  [+ w^T A_s w, w^T w]     (MGCMTSolver.py:323-326, 2DPotGS.py:103)
+//
+// One HBM pass per leg as in fused.cu (rows streamed through a cp.async ring, the sweeps pipelined along the row
+// direction, strips overlapped by HALO columns and recomputed), rebuilt around what ncu showed limits that kernel --
+// not fp64 and not HBM but the shared-memory / shuffle path (MIO) and the in-order issue behind it:
+//
+//  * arithmetic: 5 instead of ~10 fp64 instructions per update, using what is constant:
+//      A_s x (i,j) = c (x(i-1,j) + x(i+1,j) + x(i,j-1) + x(i,j+1)) + d x(i,j),        d = ka_di + kb_di - shift
+//      sweep:      out = (1 - omega) x + w f - beta S4,     w = omega / d,  beta = w c,  S4 = sum of the 4 neighbours
+//      residual:   w r = - omega x + w f - beta S4          (the 1/w goes into the full-weighting constants)
+//      Rayleigh:   w A_s x = omega x + beta S4              (the residual stage with f = 0; 1/w applied to the warp sum)
+//    Per stage and column the state is the centre row `xc` and `pre` = everything of the open row known one step before
+//    it is finalised; when the lower neighbour row arrives the finalised value is ONE fma, out = fma(-beta, x, pre).
+//  * a step runs in two phases: phase A is the chain of NSTAGE dependent fmas (plus the shuffle-free part of the new
+//    `pre`) and fires the two shuffles per stage; phase B consumes the shuffled neighbours.  A warp issues in order, so
+//    this keeps NSTAGE shuffle round trips off the critical path of a step.
+//  * global <-> shared: lane l copies the 16-byte granules l and 32+l of the strip row (every cp.async instruction
+//    covers 512 contiguous bytes = whole 32-byte sectors; the per-lane column pairs of fused.cu touch half of every
+//    sector per instruction, which doubles the L2 -> SM sectors and the shared-memory write wavefronts), the granules
+//    are XOR-swizzled in shared memory (bit 0 ^= bit 3) so that both the copies and the consumers' LDS.128 of their own
+//    4 columns are bank-conflict free, and one __syncwarp per step makes the copies visible across lanes.  Results leave
+//    with one 32-byte store per lane (HALO is a multiple of 4 columns).
+//  * w f: Jacobi legs carry it from stage to stage in registers (WFREG: no shared-memory round trip per stage);
+//    Gauss-Seidel legs (9 stages) park it in the f ring slot, de-interleaved by column parity so that a colour stage
+//    reads one granule.
+// Dirichlet zeros: beta = 0 in columns outside the grid (per-lane constant) keeps them zero; rows outside the grid
+// are only met in the first / last few steps of the first / last chunk, which run a masked copy of the step (SLOW).
+// Weighted Jacobi and the red-black Gauss-Seidel/SOR colour stages (GS = 1: two stages per sweep) share the code; a
+// colour stage only generates the arithmetic of its colour (row parity is compile-time through the unrolled step,
+// column parity through the first column of every lane being a multiple of 4).
+//
+// Results differ from fused.cu / the oracle only in the association of the sums (tested at 1e-12).
+#include <type_traits>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgcmt {
+
+namespace {
+
+constexpr int kC = 4;        // columns per lane
+constexpr int kWarpsU = 4;   // warps per CTA (independent strips)
+constexpr int kERingU = 4;   // coarse-row ring (PROLONG)
+__host__ __device__ constexpr int uni_halo(int nu) { return (nu + 2 + 3) & ~3; }   // >= nu + 2, multiple of 4
+__host__ __device__ constexpr int uni_vring(int nstage) { return nstage > 5 ? 4 : 6; }
+__host__ __device__ constexpr int uni_fring(int nstage, bool wfreg) {
+  return wfreg ? uni_vring(nstage) : uni_vring(nstage) + (nstage > 0 ? nstage - 1 : 0);
+}
+
+__device__ __forceinline__ void ucpa16(void *smem, const void *gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ucpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ucpa_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_stream4(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+struct UStage {
+  double xc[kC], pre[kC];
+};
+
+}  // namespace
+
+// NU: Jacobi sweeps (GS = 0) or colour stages (GS = 1, two per sweep).  PROLONG && RESTRICT = up leg + Rayleigh sums.
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, bool WFREG, int MINCTAS>
+__global__ void __launch_bounds__(kWarpsU * 32, MINCTAS)
+uni5_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v_in,
+                const double *__restrict__ f, double *__restrict__ v_out,
+                const double *__restrict__ e_coarse, double *__restrict__ r_coarse, int rows_per_chunk) {
+  constexpr int C = kC;
+  constexpr int HALO = uni_halo(NU);
+  constexpr int WCOLS = 32 * C;
+  constexpr int USEFUL = WCOLS - 2 * HALO;
+  constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);
+  constexpr int NS1 = NSTAGE > 0 ? NSTAGE : 1;
+  constexpr int kVR = uni_vring(NSTAGE);
+  constexpr int kFR = uni_fring(NSTAGE, WFREG);
+  constexpr int AHEAD = kVR - 1;  // rows in flight ahead of the one being consumed
+  constexpr bool RQ = PROLONG && RESTRICT;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // per warp: v ring [kVR][64 granules], f ring [kFR][64], e ring [kERingU][32]; a granule is 16 bytes
+  constexpr int WARP_GRAN = (ZEROV ? 0 : kVR * 64) + kFR * 64 + (PROLONG ? kERingU * 32 : 0);
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  double2 *ring_v = reinterpret_cast<double2 *>(smem_raw) + warp * WARP_GRAN;
+  double2 *ring_f = ring_v + (ZEROV ? 0 : kVR * 64);
+  double2 *ring_e = ring_f + kFR * 64;
+
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(r0 + rows_per_chunk, L.nrows);
+  const int t_first = r0 - NU - (RESTRICT ? 1 : 0);
+  const int t_last = r1 - 1 + NU + (RESTRICT ? 2 : 0);  // last input row that matters = last time step
+  const int t_begin = (t_first - (PROLONG ? 2 : 0)) & ~1;
+  const int nrc = L.nrows_coarse ? L.nrows_coarse : L.nrows / 2, ncc = L.ncols / 2;
+  const int cs = L.crow_shift;
+  const unsigned nglob = (unsigned)L.nrows_glob;
+
+  const int rq_slot = (blockIdx.y * gridDim.x + blockIdx.x) * kWarpsU + warp;
+  const int rq_nslots = gridDim.x * gridDim.y * kWarpsU;
+  const int strip = blockIdx.x * kWarpsU + warp;
+  const int u0 = strip * USEFUL;  // first useful fine column of this strip (a multiple of 4)
+  if (u0 >= L.ncols) {            // surplus warp (the kernel has no CTA-wide barrier)
+    if (RQ && lane == 0) { r_coarse[rq_slot] = 0.0; r_coarse[rq_nslots + rq_slot] = 0.0; }
+    return;
+  }
+  const int u1 = min(u0 + USEFUL, L.ncols);
+  const int cstart = u0 - HALO;         // first column of the strip
+  const int c0 = cstart + C * lane;     // first of this lane's 4 columns (a multiple of 4)
+
+  const double diag = L.uni_d - shift;
+  const double w = omega / diag;
+  const double a_smooth = 1.0 - omega, a_res = -omega;
+  // c0 and ncols are multiples of 4: a lane's 4 columns are inside / outside the grid (and useful or not) together
+  const bool quadin = (c0 >= 0 && c0 < L.ncols);
+  const bool quadout = (c0 >= u0 && c0 < u1);
+  const double nb = quadin ? -(w * L.uni_c) : 0.0;   // -beta inside the grid, 0 outside
+  const double hm = quadin ? 0.5 : 0.0;              // interpolation weight of even columns: 0 outside the grid
+  const double q4 = 0.25 / w, q2 = 0.5 / w;          // full weighting with the 1/w of the scaled residual folded in
+  const bool st32 = ((reinterpret_cast<uintptr_t>(v_out) & 31) == 0);
+
+  // loader: granules lane and 32 + lane of the strip row; swizzled position G ^ ((G >> 3) & 1)
+  int ldpos[2];
+  bool ldin[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int G = 32 * g + lane;
+    ldpos[g] = G ^ ((G >> 3) & 1);
+    const int j = cstart + 2 * G;
+    ldin[g] = (j >= 0 && j < L.ncols);
+  }
+  // consumer: granules 2 lane, 2 lane + 1 (columns c0 .. c0+3)
+  const int pa = (2 * lane) ^ ((lane >> 2) & 1), pb = (2 * lane + 1) ^ ((lane >> 2) & 1);
+
+  // ---- asynchronous row fetch ---------------------------------------------------------------------
+  auto issue = [&](int t, int vslot, int fslot) {
+    // rows outside the slab array or outside the global grid are zero-filled
+    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last && (unsigned)(t + L.row0) < nglob;
+    const size_t rowoff = (size_t)(rowin ? t : 0) * L.ncols;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const bool ok = rowin && ldin[g];
+      const size_t off = ok ? rowoff + cstart + 2 * (32 * g + lane) : 0;
+      if (!ZEROV) ucpa16(ring_v + vslot * 64 + ldpos[g], v_in + off, ok);
+      if (NSTAGE > 0) ucpa16(ring_f + fslot * 64 + ldpos[g], f + off, ok);
+    }
+    if (PROLONG && (t & 1) == 0) {
+      // coarse row I = t/2 is first needed by fine row t (even); this lane's coarse columns c0/2, c0/2 + 1
+      const int I = (t >> 1) + cs;
+      const int Gc = ((t + L.row0) >> 1);  // global coarse row
+      const int J = c0 >> 1;
+      const bool ok = I >= 0 && I < nrc && t <= t_last && Gc >= 0 && Gc < (L.nrows_glob >> 1) && J >= 0 && J < ncc;
+      ucpa16(ring_e + (I & (kERingU - 1)) * 32 + lane, e_coarse + (ok ? (size_t)I * ncc + J : 0), ok);
+    }
+    ucpa_commit();
+  };
+
+  UStage st[NS1];
+  double wfq[NS1][C];  // WFREG: w f of the row each stage opens in the current step
+#pragma unroll
+  for (int k = 0; k < NS1; ++k)
+#pragma unroll
+    for (int q = 0; q < C; ++q) st[k].xc[q] = st[k].pre[q] = wfq[k][q] = 0.0;
+
+  double eprev[C], ecur[C];  // column-interpolated coarse rows I-1 and I (PROLONG)
+#pragma unroll
+  for (int q = 0; q < C; ++q) eprev[q] = ecur[q] = 0.0;
+  double rq_num = 0.0, rq_den = 0.0;
+  double racc[2] = {0.0, 0.0};  // running full-weighting row sums (RESTRICT)
+
+  int vs = 0, fs = 0;  // ring slots of the current input row t
+  auto step = [&](int t, auto odd_tag, auto slow_tag) {
+    constexpr bool ODD = decltype(odd_tag)::value;
+    constexpr bool SLOW = decltype(slow_tag)::value;
+    ucpa_wait<AHEAD - 1>();  // row t has landed (this lane's copies) ...
+    __syncwarp();            // ... and every lane's; all lanes are done reading the slots refilled below
+    {
+      int vnew = vs + AHEAD; vnew -= (vnew >= kVR) ? kVR : 0;
+      int fnew = fs + AHEAD; fnew -= (fnew >= kFR) ? kFR : 0;
+      issue(t + AHEAD, vnew, fnew);
+    }
+
+    // ---- the input row t ---------------------------------------------------------------------------
+    double x[C];
+    if (ZEROV) {
+#pragma unroll
+      for (int q = 0; q < C; ++q) x[q] = 0.0;
+    } else {
+      const double2 xa = ring_v[vs * 64 + pa], xb = ring_v[vs * 64 + pb];
+      x[0] = xa.x; x[1] = xa.y; x[2] = xb.x; x[3] = xb.y;
+    }
+    if (NSTAGE > 0) {
+      double2 fa = ring_f[fs * 64 + pa], fb = ring_f[fs * 64 + pb];
+      wfq[0][0] = w * fa.x; wfq[0][1] = w * fa.y; wfq[0][2] = w * fb.x; wfq[0][3] = w * fb.y;
+      if (!WFREG && NSTAGE > 1) {
+        // later stages read w f from the slot, de-interleaved by column parity: a colour stage needs one granule
+        ring_f[fs * 64 + pa] = make_double2(wfq[0][0], wfq[0][2]);
+        ring_f[fs * 64 + pb] = make_double2(wfq[0][1], wfq[0][3]);
+      }
+    }
+    if (!WFREG) {
+      // w f of the rows the later stages open, all loads up front (row t - k, parked by stage 0 k steps ago)
+#pragma unroll
+      for (int k = 1; k < NSTAGE; ++k) {
+        const bool is_res = RESTRICT && (k == NSTAGE - 1);
+        if (RQ && is_res) continue;
+        int sl = fs - k;
+        sl += (sl < 0) ? kFR : 0;
+        const bool gs_stage = (GS != 0) && !is_res;
+        // columns this stage opens in row n = t - k: parity (colour + row parity); row parity of n = ODD ^ (k & 1)
+        const int cpar = ODD ? 1 : 0;  // colour (k & 1) ^ parity of row t - k
+        if (!gs_stage || cpar == 0) { const double2 g0 = ring_f[sl * 64 + pa]; wfq[k][0] = g0.x; wfq[k][2] = g0.y; }
+        if (!gs_stage || cpar == 1) { const double2 g1 = ring_f[sl * 64 + pb]; wfq[k][1] = g1.x; wfq[k][3] = g1.y; }
+      }
+    }
+    if (PROLONG) {
+      if (!ODD) {
+        // new coarse row I = t/2: interpolate along columns.  fine col c0+2g (even) = 1/2 (E[J-1] + E[J]),
+        // fine col c0+2g+1 = E[J], J = c0/2 + g.  Lane 0 has no left neighbour: its first column is the
+        // outermost halo column of the strip and HALO >= NSTAGE + 1, so that error never reaches a useful column.
+        const double2 e2 = ring_e[(((t >> 1) + cs) & (kERingU - 1)) * 32 + lane];
+        const double eleft = __shfl_up_sync(0xffffffffu, e2.y, 1);
+#pragma unroll
+        for (int q = 0; q < C; ++q) eprev[q] = ecur[q];
+        ecur[0] = hm * (eleft + e2.x);  // hm = 0 outside the grid: the first column past the grid stays zero
+        ecur[1] = e2.x;
+        ecur[2] = hm * (e2.x + e2.y);
+        ecur[3] = e2.y;
+#pragma unroll
+        for (int q = 0; q < C; ++q) x[q] += 0.5 * (eprev[q] + ecur[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < C; ++q) x[q] += ecur[q];
+      }
+      if (SLOW) {  // the interpolated correction is the only input that is not already zero outside the grid
+        const bool rin = (unsigned)(t + L.row0) < nglob;
+#pragma unroll
+        for (int q = 0; q < C; ++q) x[q] = rin ? x[q] : 0.0;
+      }
+    }
+
+    // ---- phase A: row n = t - k of stage k's input arrives, row n - 1 is finalised (one fma per point) ----
+    double xl[NS1], xr[NS1];  // shuffled edge neighbours of the row every stage opened
+    double res[C];            // the last stage's output if it is the residual
+#pragma unroll
+    for (int k = 0; k < NSTAGE; ++k) {
+      const int rho = t - k - 1;
+      const bool is_res = RESTRICT && (k == NSTAGE - 1);
+      const bool gs_stage = (GS != 0) && !is_res;
+      const int colour = k & 1;
+      const int prho = (ODD ? 1 : 0) ^ ((k + 1) & 1);  // parity of rho (t_begin, row0 even; c0 a multiple of 4)
+      auto in_colour = [&](int prow, int pcol) { return !gs_stage || (((prow + pcol) & 1) == colour); };
+      const double ak = is_res ? a_res : a_smooth;
+
+      double out[C];
+#pragma unroll
+      for (int q = 0; q < C; ++q) out[q] = in_colour(prho, q & 1) ? fma(nb, x[q], st[k].pre[q]) : st[k].xc[q];
+      if (SLOW) {
+        const bool rin = (unsigned)(rho + L.row0) < nglob;
+#pragma unroll
+        for (int q = 0; q < C; ++q) out[q] = rin ? out[q] : 0.0;
+      }
+      if (RQ && is_res) {
+        if (rho >= r0 && rho < r1 && rho >= L.rq_lo && rho < L.rq_hi && quadout) {  // each useful (owned) point once
+#pragma unroll
+          for (int q = 0; q < C; ++q) {
+            rq_num = fma(st[k].xc[q], out[q], rq_num);
+            rq_den = fma(st[k].xc[q], st[k].xc[q], rq_den);
+          }
+        }
+      }
+      // open row n: the part that needs no shuffle (old centre row = upper neighbour, a x, w f)
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        if (in_colour(prho ^ 1, q & 1)) {
+          const double base = (RQ && is_res) ? ak * x[q] : fma(ak, x[q], wfq[k][q]);
+          st[k].pre[q] = fma(nb, st[k].xc[q], base);
+        }
+      }
+      xl[k] = __shfl_up_sync(0xffffffffu, x[C - 1], 1);
+      xr[k] = __shfl_down_sync(0xffffffffu, x[0], 1);
+#pragma unroll
+      for (int q = 0; q < C; ++q) { st[k].xc[q] = x[q]; x[q] = out[q]; }
+
+      if (!is_res && k == NU - 1 && rho >= r0 && rho < r1 && quadout) {
+        // x = row rho of the last sweep: the smoothed iterate
+        double *dst = v_out + (size_t)rho * L.ncols + c0;
+        if (st32) st_stream4(dst, x[0], x[1], x[2], x[3]);
+        else { st_stream2(dst, make_double2(x[0], x[1])); st_stream2(dst + 2, make_double2(x[2], x[3])); }
+      }
+      if (is_res) {
+#pragma unroll
+        for (int q = 0; q < C; ++q) res[q] = x[q];
+      }
+    }
+    double rnext = 0.0;
+    if (RESTRICT && !RQ) rnext = __shfl_down_sync(0xffffffffu, res[0], 1);
+
+    // ---- phase B: the horizontal neighbours of the opened rows ------------------------------------------
+#pragma unroll
+    for (int k = 0; k < NSTAGE; ++k) {
+      const bool is_res = RESTRICT && (k == NSTAGE - 1);
+      const bool gs_stage = (GS != 0) && !is_res;
+      const int colour = k & 1;
+      const int pn = (ODD ? 1 : 0) ^ (k & 1);  // parity of the opened row n = t - k
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        if (!gs_stage || (((pn + q) & 1) == colour)) {
+          const double xm = (q == 0) ? xl[k] : st[k].xc[q - 1];
+          const double xp = (q == C - 1) ? xr[k] : st[k].xc[q + 1];
+          st[k].pre[q] = fma(nb, xm + xp, st[k].pre[q]);
+        }
+      }
+    }
+    if (RESTRICT && !RQ) {
+      // res = w * residual row rho (zero outside the grid), rho = t - NU - 1: full weighting, columns first
+      //   coarse J = c0/2 + g  <-  1/4 r[2J] + 1/2 r[2J+1] + 1/4 r[2J+2]
+      const int rho = t - NU - 1;
+      constexpr bool RHO_ODD = (ODD != ((NU + 1) % 2 != 0));
+      double crr[2];
+      crr[0] = fma(q4, res[0] + res[2], q2 * res[1]);
+      crr[1] = fma(q4, res[2] + rnext, q2 * res[3]);
+      if (!RHO_ODD) {
+        const int I = (rho >> 1) - 1 + cs;        // coarse row completed by this fine row (as its row 2I+2)
+        const int G = ((rho + L.row0) >> 1) - 1;  // its global coarse row: rows outside the coarse grid are never written
+        const bool rowok = (I >= (r0 >> 1) + cs && I < (r1 >> 1) + cs && I >= 0 && I < nrc && G >= 0 &&
+                            G < (L.nrows_glob >> 1));
+        if (rowok && quadout)
+          st_stream2(r_coarse + (size_t)I * ncc + (c0 >> 1), make_double2(fma(0.25, crr[0], racc[0]), fma(0.25, crr[1], racc[1])));
+        racc[0] = 0.25 * crr[0];
+        racc[1] = 0.25 * crr[1];
+      } else {
+        racc[0] = fma(0.5, crr[0], racc[0]);
+        racc[1] = fma(0.5, crr[1], racc[1]);
+      }
+    }
+    if (NU == 0 && !RESTRICT && t >= r0 && t < r1 && quadout) {
+      // pure prolongation-correction pass: write the corrected iterate
+      double *dst = v_out + (size_t)t * L.ncols + c0;
+      if (st32) st_stream4(dst, x[0], x[1], x[2], x[3]);
+      else { st_stream2(dst, make_double2(x[0], x[1])); st_stream2(dst + 2, make_double2(x[2], x[3])); }
+    }
+    if (WFREG) {  // w f moves on with its row
+#pragma unroll
+      for (int k = NSTAGE - 1; k > 0; --k)
+#pragma unroll
+        for (int q = 0; q < C; ++q) wfq[k][q] = wfq[k - 1][q];
+    }
+    vs = (vs + 1 == kVR) ? 0 : vs + 1;
+    fs = (fs + 1 == kFR) ? 0 : fs + 1;
+  };
+
+#pragma unroll
+  for (int d = 0; d < AHEAD; ++d) issue(t_begin + d, d, d);
+
+  using TrueT = std::integral_constant<bool, true>;
+  using FalseT = std::integral_constant<bool, false>;
+  for (int t = t_begin; t <= t_last; t += 2) {  // t_begin is even
+    // rows t - NSTAGE .. t + 1 (global) all inside the grid?
+    const int g = t + L.row0;
+    const bool slow = (g - NSTAGE < 0) || (g + 1 >= L.nrows_glob);
+    if (!slow) {
+      step(t, FalseT{}, FalseT{});
+      step(t + 1, TrueT{}, FalseT{});
+    } else {
+      step(t, FalseT{}, TrueT{});
+      step(t + 1, TrueT{}, TrueT{});
+    }
+  }
+  ucpa_wait<0>();
+  if (RQ) {
+    // the stage summed x (w A_s x)' with (w A_s x)' = -(omega x + beta S4): undo sign and scale
+    const double a = -warp_sum(rq_num) / w, b = warp_sum(rq_den);
+    if (lane == 0) { r_coarse[rq_slot] = a; r_coarse[rq_nslots + rq_slot] = b; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+size_t uni_smem_bytes(bool prolong, bool zerov, int nstage, bool wfreg) {
+  size_t gran = (size_t)((zerov ? 0 : uni_vring(nstage)) + uni_fring(nstage, wfreg)) * 64 + (prolong ? kERingU * 32 : 0);
+  return gran * 16 * kWarpsU;
+}
+
+int g_num_sms = 0;
+
+}  // namespace
+
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// Chunk height for a streaming leg: CTAs = gx * chunks should fill whole waves of `slots` resident CTAs (a grid a few
+// CTAs over a wave costs a whole extra pass at the tail), chunks no taller than 128 rows and, while the grid allows it,
+// no shorter than 32 (every chunk recomputes ~nstage rows of overlap).
+int leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc) {
+  if (nrows <= 16) return nrows;
+  int best = 0;
+  double best_cost = 1e300;
+  for (int waves = 1; waves <= 8; ++waves) {
+    int chunks = (int)(((long long)waves * slots) / gx);
+    if (chunks < 1) continue;
+    int rpc = (nrows + chunks - 1) / chunks;
+    rpc = (rpc + 1) & ~1;
+    if (rpc < 16) rpc = 16;
+    if (rpc > max_rpc) rpc = max_rpc;
+    if (rpc > nrows) rpc = nrows;
+    const int nch = (nrows + rpc - 1) / rpc;
+    const int w = (int)(((long long)gx * nch + slots - 1) / slots);       // waves actually needed
+    const double cost = (double)w * (rpc + nstage + 2);                   // time ~ waves x rows streamed per CTA
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = rpc; }
+  }
+  return best > 0 ? best : (nrows < 128 ? nrows : 128);
+}
+
+int g_uni_minctas = 0;  // resident CTAs per SM the 4-sweep Jacobi legs are compiled for: 0 = default, 2 or 3 (A/B timing)
+int g_uni_wfreg = 1;    // 4-sweep Jacobi legs: w f carried in registers (1) or parked in the f ring (0)
+
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, bool WFREG, int MINCTAS>
+static cudaError_t launch_uni_m(const LevelDev &L, double shift, double omega, const double *v_in, const double *f,
+                                double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s, int *slots_out) {
+  constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);
+  constexpr int USEFUL = 32 * kC - 2 * uni_halo(NU);
+  auto kern = uni5_leg_kernel<NU, PROLONG, RESTRICT, ZEROV, GS, WFREG, MINCTAS>;
+  const size_t smem = uni_smem_bytes(PROLONG, ZEROV, NSTAGE, WFREG);
+  static int occ = 0;  // per instantiation
+  if (!occ) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsU * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+  }
+  const int strips = (L.ncols + USEFUL - 1) / USEFUL;
+  const int gx = (strips + kWarpsU - 1) / kWarpsU;
+  const int rpc = leg_rows_per_chunk(L.nrows, gx, occ * num_sms(), NSTAGE, 1 << 20);
+  dim3 grid(gx, (L.nrows + rpc - 1) / rpc);
+  if (slots_out) {  // geometry query only
+    *slots_out = grid.x * grid.y * kWarpsU;
+    return cudaSuccess;
+  }
+  kern<<<grid, kWarpsU * 32, smem, s>>>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, rpc);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS>
+static cudaError_t launch_uni_t(const LevelDev &L, double shift, double omega, const double *v_in, const double *f,
+                                double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s, int *slots_out) {
+#define UNI_GO(WF, MC) \
+  return launch_uni_m<NU, PROLONG, RESTRICT, ZEROV, GS, WF, MC>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out)
+  if constexpr (GS == 0 && NU == 4) {
+    // the hot Jacobi legs: both w f variants and both register budgets are built (mgcmt_set_option: uni_wfreg, uni_minctas)
+    const int m = g_uni_minctas ? g_uni_minctas : 2;
+    if (g_uni_wfreg) { if (m == 3) UNI_GO(true, 3); UNI_GO(true, 2); }
+    if (m == 3) UNI_GO(false, 3);
+    UNI_GO(false, 2);
+  } else if constexpr (GS == 0) {
+    UNI_GO(true, 3);
+  } else {
+    UNI_GO(false, 2);
+  }
+#undef UNI_GO
+}
+
+template <int NU, int GS>
+static cudaError_t uni_dispatch_mode(const LevelDev &L, int mode, double shift, double omega, const double *v_in,
+                                     const double *f, double *v_out, const double *e_coarse, double *r_coarse,
+                                     cudaStream_t s, int *slots_out) {
+  switch (mode) {
+    case FUSED_SMOOTH:
+      if (NU == 0) return cudaErrorInvalidValue;
+      return launch_uni_t<NU, false, false, false, GS>(L, shift, omega, v_in, f, v_out, nullptr, nullptr, s, slots_out);
+    case FUSED_DOWN:
+      return launch_uni_t<NU, false, true, false, GS>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s, slots_out);
+    case FUSED_DOWN_ZERO:
+      return launch_uni_t<NU, false, true, true, GS>(L, shift, omega, v_in, f, v_out, nullptr, r_coarse, s, slots_out);
+    case FUSED_UP:
+      return launch_uni_t<NU, true, false, false, GS>(L, shift, omega, v_in, f, v_out, e_coarse, nullptr, s, slots_out);
+    case FUSED_UP_RQ:  // the last up-leg pass of the finest level: nu2 = 4 Jacobi sweeps or 4 red-black sweeps
+      if constexpr ((GS == 0 && NU == 4) || (GS == 1 && NU == 8))
+        return launch_uni_t<NU, true, true, false, GS>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out);
+      else
+        return cudaErrorInvalidValue;
+  }
+  return cudaErrorInvalidValue;
+}
+
+int g_fused_uni = 1;  // 0: constant-coefficient levels use the general kernels of fused.cu too (A/B, parity)
+
+bool uni5_available(const LevelDev &L) { return g_fused_uni && L.uni == 1 && L.five && L.nrows >= 2 && (L.ncols & 1) == 0; }
+
+// nu = Jacobi sweeps 0..4 (gs = 0) or red-black sweeps 1..4 (gs = 1).  slots_out != nullptr: no launch, only the
+// number of per-warp partial-sum slots a FUSED_UP_RQ launch would write.
+cudaError_t launch_uni5_leg(const LevelDev &L, int gs, int mode, int nu, double shift, double omega, const double *v_in,
+                            const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s,
+                            int *slots_out) {
+  if (!uni5_available(L)) return cudaErrorInvalidValue;
+  if (nu == 0) gs = 0;  // transfer only: no colour order involved
+#define UNI_CASE(NUV, GSV) \
+  case NUV: return uni_dispatch_mode<(GSV ? 2 * NUV : NUV), GSV>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out);
+  if (gs) {
+    switch (nu) { UNI_CASE(1, 1) UNI_CASE(2, 1) UNI_CASE(3, 1) UNI_CASE(4, 1) }
+  } else {
+    switch (nu) { UNI_CASE(0, 0) UNI_CASE(1, 0) UNI_CASE(2, 0) UNI_CASE(3, 0) UNI_CASE(4, 0) }
+  }
+#undef UNI_CASE
+  return cudaErrorInvalidValue;
+}
+
+int uni5_rq_slots(const LevelDev &L, int gs) {
+  if (!uni5_available(L)) return 0;
+  int slots = 0;
+  if (launch_uni5_leg(L, gs, FUSED_UP_RQ, 4, 0.0, 1.0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, &slots) != cudaSuccess)
+    return 0;
+  return slots;
+}
+
+}  // namespace mgcmt

@@ -1,6 +1,6 @@
 """Runs a few launches of one kernel family on the 4096^2 well so `ncu -k regex:...` can capture it.
 
-  python tools/profile_sweep.py [jacobi|vcycle|down|up] [N]
+  python tools/profile_sweep.py [jacobi|vcycle|down|down0|up|gsdown|gsdown0|gsup|down1|up1|gsdown1] [N] [option=value ...]
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -35,6 +35,18 @@ for it in range(2):
             h.fused_leg(0, 1, 4, 1.7, 2.0 / 3.0, v, f, out, None, rc)
         elif what == "up":
             h.fused_leg(0, 3, 4, 1.7, 2.0 / 3.0, v, f, out, rc, None)
+        elif what == "down0":
+            h.fused_leg(0, 2, 4, 1.7, 2.0 / 3.0, None, f, out, None, rc)
+        elif what == "gsdown":
+            h.fused_leg(0, 32 | 1, 4, 1.7, 1.0, v, f, out, None, rc)
+        elif what == "gsdown0":
+            h.fused_leg(0, 32 | 2, 4, 1.7, 1.0, None, f, out, None, rc)
+        elif what == "gsup":
+            h.fused_leg(0, 32 | 3, 4, 1.7, 1.0, v, f, out, rc, None)
+        elif what == "up1":
+            h.fused_leg(1, 3, 4, 1.7, 2.0 / 3.0, v1, f1, out1, rc1, None)
+        elif what == "gsdown1":
+            h.fused_leg(1, 32 | 1, 2, 1.7, 1.0, v1, f1, out1, None, rc1)
         elif what == "down1":
             h.fused_leg(1, 1, 4, 1.7, 2.0 / 3.0, v1, f1, out1, None, rc1)
         else:
