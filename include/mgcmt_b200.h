@@ -193,12 +193,23 @@ int mgcmt_normalize(long long n, double *d_x, void *stream);
  * matrix d_out[k(k+1)/2] of the owned rows is all-reduced between the two calls) */
 int mgcmt_gram(long long n, int k, const double *d_V, long long stride, double *d_out, void *stream);
 int mgcmt_cholqr_apply(long long n, int k, double *d_V, long long stride, const double *d_gram, void *stream);
+/* Breakdown flag of the Gram-matrix orthonormalisation (modified == 2, mgcmt_cholqr_apply): *h_flag = 1 if, since the
+ * last call, a Gram matrix was not positive definite (nearly dependent columns -- e.g. two shifts converging on the
+ * same eigenvector); the affected block is then NOT orthonormal and must be redone column by column (modified = 1).
+ * Synchronises `stream`, resets the flag. */
+int mgcmt_ortho_status(int *h_flag, void *stream);
 /* x /= sqrt(*d_sumsq) with the sum of squares read from device memory (e.g. after an all-reduce of per-rank
  * partial sums in the slab-decomposed path) */
 int mgcmt_scale_inv_norm(long long n, double *d_x, const double *d_sumsq, void *stream);
 /* y = alpha*x + y with alpha read from device memory, scaled by `sign` */
 int mgcmt_axpy_dev(long long n, const double *d_alpha, double sign, const double *d_x, double *d_y,
                    void *stream);
+/* Eigen-residual with the Rayleigh quotient kept on the device: d_r = A_0 x - (d_rq2[0] / d_rq2[1]) x and
+ * d_out_sumsq[0] = ||d_r||^2  (d_rq2 as written by mgcmt_rayleigh / mgcmt_vcycle_rq).  The reference never forms it
+ * (no convergence criterion, `2DPotGS.py:91-105` runs a fixed count); it is the convergence measure
+ * ||H v - rho v|| of ShiftMethod.solve and the right-hand side of its correction form. */
+int mgcmt_eigen_residual(mgcmt_hier_t *h, int level, const double *d_x, const double *d_rq2, double *d_r,
+                         double *d_out_sumsq, void *stream);
 /* out = a*x + b*y with host scalars (the vector updates of rqmin, MGCMTSolver.py:34-36,51,54) */
 int mgcmt_axpby(long long n, double a, const double *d_x, double b, const double *d_y, double *d_out,
                 void *stream);

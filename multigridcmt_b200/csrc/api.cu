@@ -911,6 +911,24 @@ int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2
   return MGCMT_OK;
 }
 
+int mgcmt_eigen_residual(mgcmt_hier_t *h, int level, const double *d_x, const double *d_rq2, double *d_r,
+                         double *d_out_sumsq, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (!d_rq2 || !d_out_sumsq) return fail(MGCMT_ERR_ARG, "null scalar pointer");
+  if (h->slab) return fail(MGCMT_ERR_STATE, "not available on slab pieces");
+  NEED_ALIGNED(d_x, d_r);
+  Level &L = h->lev[level];
+  if (!L.tmp) return fail(MGCMT_ERR_STATE, "level has no scratch vector in this hierarchy");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(launch_apply(L.dev, 0.0, d_x, d_r, nullptr, nullptr, s));
+  CU(launch_axpy_dev((long long)L.n, d_rq2, d_rq2 + 1, -1.0, d_x, d_r, s));  // r -= (num / den) x
+  // per-hierarchy scratch (L.tmp) for the partial sums: callable concurrently on different hierarchies / streams
+  if ((size_t)kReduceBlocks > L.n) return fail(MGCMT_ERR_STATE, "level too small");
+  CU(launch_dot((long long)L.n, d_r, d_r, L.tmp, d_out_sumsq, s));
+  return MGCMT_OK;
+}
+
 int mgcmt_normalize(long long n, double *d_x, void *stream) {
   if (n < 0 || !d_x) return fail(MGCMT_ERR_ARG, "bad normalize arguments");
   Scratch *sc;
@@ -940,6 +958,18 @@ int mgcmt_cholqr_apply(long long n, int k, double *d_V, long long stride, const 
   if (rc) return rc;
   CU(launch_chol_inverse(k, d_gram, sc->scal + 24, sc->status, (cudaStream_t)stream));
   CU(launch_cholqr_apply(n, k, d_V, stride, sc->scal + 24, (cudaStream_t)stream));
+  return MGCMT_OK;
+}
+
+int mgcmt_ortho_status(int *h_flag, void *stream) {
+  if (!h_flag) return fail(MGCMT_ERR_ARG, "null flag pointer");
+  Scratch *sc;
+  int rc = get_scratch(&sc);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(h_flag, sc->status, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemsetAsync(sc->status, 0, sizeof(int), s));
+  CU(cudaStreamSynchronize(s));
   return MGCMT_OK;
 }
 

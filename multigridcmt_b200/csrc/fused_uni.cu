@@ -34,6 +34,8 @@
 // column parity through the first column of every lane being a multiple of 4).
 //
 // Results differ from fused.cu / the oracle only in the association of the sums (tested at 1e-12).
+#include <math.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -70,12 +72,59 @@ struct UStage {
   double xc[kC], pre[kC];
 };
 
+// The coefficients of the sweep  out = a x + wf f - beta S4  (a = 1 - om, beta = om c / ds, wf = om / ds, ds = d - shift).
+// Rounding a and beta independently perturbs the ratio om : beta, which is the DIAGONAL of the operator that the
+// sweeps, the residual and the Rayleigh stage effectively use: a relative 1e-16 there is an absolute ~1e-16 * d ~ 7e-10
+// shift of the spectrum at 4096^2 (d = 4 N^2 / pi^2), systematic over all points, so it does not average out like data
+// rounding does, and a cycle amplifies it by 1 / |lambda - shift|.  The reference (and the general kernels) never
+// round the diagonal against the off-diagonals: they form c S4 + d x - shift x in the data.  Here beta = fl(omega c / ds)
+// is taken as given and the matching weight om_e = beta ds / c is carried as a double-double hi + lo (ds = d - shift
+// exactly, as hi + lo too): a = 1 - hi and -hi are exact, and the missing -lo x (|lo| < 6e-17) is added with one extra
+// fma where it matters -- in the residual / Rayleigh stage, and once per leg for the sweeps (NU * lo in the first
+// update of a point: the components it matters for are the smooth ones, which the sweeps barely change).
+struct UniCoef {
+  double a_smooth;  // 1 - om_hi
+  double a_res;     // -om_hi
+  double dlo;       // -om_lo
+  double nbeta;     // -beta
+  double wf;        // scale of f: beta / c
+  double invw;      // c / beta
+  double drem;      // (d + 4 c) - shift: what is left of the diagonal next to c (S4 - 4 x)
+};
+
+UniCoef uni_coef(double c, double du, double shift, double omega) {
+  const double hi = du - shift;
+  const double bb = hi - du;
+  const double lo = (du - (hi - bb)) + (-shift - bb);  // TwoSum: hi + lo == du - shift exactly
+  const double beta = omega * c / hi;
+  // om_e = beta (hi + lo) / c as q_hi + q_lo
+  const double p_hi = beta * hi, p_lo = fma(beta, hi, -p_hi) + beta * lo;
+  double q_hi = p_hi / c;
+  double q_lo = (fma(-q_hi, c, p_hi) + p_lo) / c;
+  // A weight a few ulps from 1 (Gauss-Seidel, omega = 1) must not multiply x: fl((1 + 2e-16) x) is x or its neighbour
+  // depending on the mantissa of x alone, a rounding error with a non-zero mean.  Split it as 1 + (om_e - 1): the
+  // product with 1 is exact and the remainder joins the low part.
+  if (fabs(q_hi - 1.0) < 1e-9) {
+    q_lo += q_hi - 1.0;
+    q_hi = 1.0;
+  }
+  UniCoef k;
+  k.a_smooth = 1.0 - q_hi;  // exact for q_hi in [1/2, 1]; otherwise the error joins dlo
+  k.a_res = -q_hi;
+  k.dlo = -q_lo + ((1.0 - k.a_smooth) - q_hi);
+  k.nbeta = -beta;
+  k.wf = beta / c;
+  k.invw = c / beta;
+  k.drem = (du + 4.0 * c) - shift;
+  return k;
+}
+
 }  // namespace
 
 // NU: Jacobi sweeps (GS = 0) or colour stages (GS = 1, two per sweep).  PROLONG && RESTRICT = up leg + Rayleigh sums.
 template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, bool WFREG, int MINCTAS>
 __global__ void __launch_bounds__(kWarpsU * 32, MINCTAS)
-uni5_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v_in,
+uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
                 const double *__restrict__ f, double *__restrict__ v_out,
                 const double *__restrict__ e_coarse, double *__restrict__ r_coarse, int rows_per_chunk) {
   constexpr int C = kC;
@@ -119,15 +168,16 @@ uni5_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict
   const int cstart = u0 - HALO;         // first column of the strip
   const int c0 = cstart + C * lane;     // first of this lane's 4 columns (a multiple of 4)
 
-  const double diag = L.uni_d - shift;
-  const double w = omega / diag;
-  const double a_smooth = 1.0 - omega, a_res = -omega;
+  const double w = K.wf;
+  const double a_smooth = K.a_smooth, a_res = K.a_res;
+  const double dres = K.dlo;                                   // low part of the x coefficient, residual / Rayleigh stage
+  const double dlump = K.dlo * (GS ? NU / 2 : NU);             // ... of all sweeps of the leg, applied with the first update
   // c0 and ncols are multiples of 4: a lane's 4 columns are inside / outside the grid (and useful or not) together
   const bool quadin = (c0 >= 0 && c0 < L.ncols);
   const bool quadout = (c0 >= u0 && c0 < u1);
-  const double nb = quadin ? -(w * L.uni_c) : 0.0;   // -beta inside the grid, 0 outside
+  const double nb = quadin ? K.nbeta : 0.0;          // -beta inside the grid, 0 outside
   const double hm = quadin ? 0.5 : 0.0;              // interpolation weight of even columns: 0 outside the grid
-  const double q4 = 0.25 / w, q2 = 0.5 / w;          // full weighting with the 1/w of the scaled residual folded in
+  const double q4 = 0.25 * K.invw, q2 = 0.5 * K.invw;  // full weighting with the 1/w of the scaled residual folded in
   const bool st32 = ((reinterpret_cast<uintptr_t>(v_out) & 31) == 0);
 
   // loader: granules lane and 32 + lane of the strip row; swizzled position G ^ ((G >> 3) & 1)
@@ -265,7 +315,10 @@ uni5_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict
 
       double out[C];
 #pragma unroll
-      for (int q = 0; q < C; ++q) out[q] = in_colour(prho, q & 1) ? fma(nb, x[q], st[k].pre[q]) : st[k].xc[q];
+      for (int q = 0; q < C; ++q) {
+        if (RQ && is_res) out[q] = st[k].pre[q] + x[q];  // Rayleigh stage: S4 - 4 x, formed in the data (see below)
+        else out[q] = in_colour(prho, q & 1) ? fma(nb, x[q], st[k].pre[q]) : st[k].xc[q];
+      }
       if (SLOW) {
         const bool rin = (unsigned)(rho + L.row0) < nglob;
 #pragma unroll
@@ -284,7 +337,18 @@ uni5_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict
 #pragma unroll
       for (int q = 0; q < C; ++q) {
         if (in_colour(prho ^ 1, q & 1)) {
-          const double base = (RQ && is_res) ? ak * x[q] : fma(ak, x[q], wfq[k][q]);
+          double base;
+          if (RQ && is_res) {
+            // Rayleigh stage: no rounded coefficient touches the data.  The stage sums x (S4 - 4 x) and x x; c and the
+            // diagonal remainder (d + 4 c - shift) multiply the two sums once at the end.  (With the sweep's scaled
+            // coefficients the sum carried a relative bias of ~1e-11 at 4096^2: products of x with omega and beta are
+            // rounded with a mean that does not vanish when the coefficients are in simple ratios.)
+            st[k].pre[q] = fma(-4.0, x[q], st[k].xc[q]);
+            continue;
+          }
+          if (is_res) base = fma(ak, x[q], fma(dres, x[q], wfq[k][q]));
+          else if (k < (GS ? 2 : 1)) base = fma(ak, x[q], fma(dlump, x[q], wfq[k][q]));
+          else base = fma(ak, x[q], wfq[k][q]);
           st[k].pre[q] = fma(nb, st[k].xc[q], base);
         }
       }
@@ -319,7 +383,8 @@ uni5_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict
         if (!gs_stage || (((pn + q) & 1) == colour)) {
           const double xm = (q == 0) ? xl[k] : st[k].xc[q - 1];
           const double xp = (q == C - 1) ? xr[k] : st[k].xc[q + 1];
-          st[k].pre[q] = fma(nb, xm + xp, st[k].pre[q]);
+          if (RQ && is_res) st[k].pre[q] += xm + xp;
+          else st[k].pre[q] = fma(nb, xm + xp, st[k].pre[q]);
         }
       }
     }
@@ -381,7 +446,9 @@ uni5_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict
   ucpa_wait<0>();
   if (RQ) {
     // the stage summed x (w A_s x)' with (w A_s x)' = -(omega x + beta S4): undo sign and scale
-    const double a = -warp_sum(rq_num) / w, b = warp_sum(rq_den);
+    // w^T A_s w = c sum x (S4 - 4 x) + (d + 4 c - shift) sum x x
+    const double b = warp_sum(rq_den);
+    const double a = fma(L.uni_c, warp_sum(rq_num), K.drem * b);
     if (lane == 0) { r_coarse[rq_slot] = a; r_coarse[rq_nslots + rq_slot] = b; }
   }
 }
@@ -457,7 +524,7 @@ static cudaError_t launch_uni_m(const LevelDev &L, double shift, double omega, c
     *slots_out = grid.x * grid.y * kWarpsU;
     return cudaSuccess;
   }
-  kern<<<grid, kWarpsU * 32, smem, s>>>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, rpc);
+  kern<<<grid, kWarpsU * 32, smem, s>>>(L, uni_coef(L.uni_c, L.uni_d, shift, omega), v_in, f, v_out, e_coarse, r_coarse, rpc);
   count_launch();
   return cudaGetLastError();
 }

@@ -133,6 +133,99 @@ class ShiftMethod:
         h = hist.cpu().numpy()
         return h[:, :, 0] / h[:, :, 1]
 
+    # ---- iteration to a tolerance (the reference has no convergence criterion) -----------
+    def _rayleigh_block(self, out):
+        """out[c] = (v_c^T H v_c, v_c^T v_c) of the current block, one fused pass per vector (no host sync)"""
+        for c in range(self.k):
+            self.hier[0].rayleigh(0, self.block[c], out[c])
+
+    def _residual_block(self, rq, R, rr):
+        """R[c] = H v_c - rho_c v_c with rho_c = rq[c,0] / rq[c,1] read on the device; rr[c] = ||R[c]||^2"""
+        torch, lib = self._torch, self._lib
+        for c in range(self.k):
+            _lib.check(lib.mgcmt_eigen_residual(self.hier[0].handle, 0, _ptr(self.block[c]), _ptr(rq[c]), _ptr(R[c]),
+                                                _ptr(rr[c]), _stream_ptr(torch)))
+
+    def _check_ortho(self):
+        """Gram-matrix orthonormalisation broke down since the last check (mgcmt_ortho_status)?  Then the block is redone
+        column by column (MGCMTProcessor.gramschmidt, modified=1) -- the ordering the Gram form reproduces."""
+        import ctypes as C
+        torch, lib = self._torch, self._lib
+        flag = C.c_int(0)
+        _lib.check(lib.mgcmt_ortho_status(C.byref(flag), _stream_ptr(torch)))
+        if flag.value:
+            self.ortho_breakdowns = getattr(self, "ortho_breakdowns", 0) + 1
+            _lib.check(lib.mgcmt_gramschmidt(self.n, self.k, _ptr(self.block), 1, _stream_ptr(torch)))
+        return bool(flag.value)
+
+    def correction_step(self, rq, R, rr):
+        """One iteration in correction form (fixed shifts):  r_i = H v_i - rho_i v_i,  v_i <- v_i - Vcycle_{mu_i}(0, r_i),
+        orthonormalise.  With an exact solve in place of the V-cycle this is the reference's inverse iteration
+        ((H - mu)^-1 r = v - (mu - rho)... = v + (mu - rho)(H - mu)^-1 v, so v - that is parallel to (H - mu)^-1 v,
+        2DPotGS.py:95-96); with the V-cycle as approximate inverse its fixed points are EXACT eigenvectors (r = 0),
+        whereas the plain form converges to the dominant eigenvector of the V-cycle operator itself, which differs
+        from H's at the level of the cycle's mode mixing.  A labelled departure from the reference's loop."""
+        torch, lib = self._torch, self._lib
+        self._rayleigh_block(rq)
+        self._residual_block(rq, R, rr)
+        W = self.blocks[1 - self.cur]
+        main = torch.cuda.current_stream()
+        ns = len(self.streams)
+        for s in self.streams:
+            s.wait_stream(main)
+        for c in range(self.k):
+            with torch.cuda.stream(self.streams[c % ns]):
+                _lib.check(lib.mgcmt_vcycle(self.hier[c % ns].handle, self.shifts[c], self.nu1, self.nu2, self.code, self.omega,
+                                            _ptr(W[c]), _ptr(R[c]), 1, _stream_ptr(torch)))
+                _lib.check(lib.mgcmt_axpby(self.n, 1.0, _ptr(self.block[c]), -1.0, _ptr(W[c]), _ptr(W[c]), _stream_ptr(torch)))
+        for s in self.streams:
+            main.wait_stream(s)
+        _lib.check(lib.mgcmt_gramschmidt(self.n, self.k, _ptr(W), self.ortho, _stream_ptr(torch)))
+        self.cur = 1 - self.cur
+        self.iterations += 1
+
+    def solve(self, tol=1e-10, max_iters=200, form="reference", update_shift=False, check_every=1, exact=None):
+        """Iterate until every eigenpair satisfies ||H v - rho v||_2 <= tol (||v|| = 1, rho = v^T H v) and, when the exact
+        eigenvalues are given, |rho - exact| <= tol.  form="reference": the drivers' loop (step(): w = Vcycle(0, v), normalise,
+        Gram-Schmidt -- 2DPotGS.py:91-105), which has no stopping rule of its own; form="correction": correction_step().
+        update_shift=True replaces mu_i by the current rho_i at every check (Rayleigh-quotient iteration; departs from the
+        reference, which keeps the coarse-grid eigenvalues as shifts; each new shift costs one coarsest-level inverse).
+        Returns a dict: converged, iterations, eigenvalues, residual_norms, history [(iteration, residual norms, rho)]."""
+        torch = self._torch
+        rq = torch.zeros(self.k, 2, dtype=torch.float64, device="cuda")
+        rr = torch.zeros(self.k, 1, dtype=torch.float64, device="cuda")
+        R = torch.empty(self.k, self.n, dtype=torch.float64, device="cuda")
+        history = []
+        converged = False
+        it0 = self.iterations
+        res = rho = None
+        while True:
+            # convergence check on the current (orthonormal) block
+            self._rayleigh_block(rq)
+            self._residual_block(rq, R, rr)
+            self._check_ortho()
+            rq_h, rr_h = rq.cpu().numpy(), rr.cpu().numpy()[:, 0]
+            rho = rq_h[:, 0] / rq_h[:, 1]
+            res = np.sqrt(rr_h / rq_h[:, 1])
+            history.append((self.iterations - it0, res.copy(), rho.copy()))
+            ok = bool(np.all(res <= tol))
+            if exact is not None:
+                ok = ok and bool(np.all(np.abs(rho - np.asarray(exact)) <= tol))
+            if ok:
+                converged = True
+                break
+            if self.iterations - it0 >= max_iters:
+                break
+            if update_shift:
+                self.shifts = [float(x) for x in rho]
+            for _ in range(max(1, int(check_every))):
+                if form == "correction":
+                    self.correction_step(rq, R, rr)
+                else:
+                    self.step()
+        return {"converged": converged, "iterations": self.iterations - it0, "eigenvalues": rho, "residual_norms": res,
+                "history": history, "form": form, "update_shift": bool(update_shift)}
+
     def last_rayleigh(self):
         """Rayleigh quotients of the last step's V-cycle outputs (before the orthonormalisation)"""
         r = self.rq.cpu().numpy()

@@ -62,6 +62,8 @@ def load():
         lib.orc_vcycle.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
         lib.orc_vcycle_smoother.restype = C.c_int
         lib.orc_vcycle_smoother.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp]
+        lib.orc_block_step.restype = C.c_int
+        lib.orc_block_step.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, dp, C.c_double, C.c_int, C.c_int, dp, dp, dp]
         _lib = lib
     return _lib
 
@@ -99,3 +101,25 @@ class WellHierarchy:
                 self.h = None
         except Exception:
             pass
+
+
+class ShiftBlock:
+    """The shift-method step of the drivers (2DPotGS.py:91-105) on a block of k vectors, all host threads: k V-cycles
+    (one hierarchy per shift, so every shift keeps its coarsest LU), Rayleigh sums, modified Gram-Schmidt."""
+
+    def __init__(self, n, lowest, shifts, smoother="wjacobi", omega=None):
+        self.n, self.k = n, len(shifts)
+        self.hs = [WellHierarchy(n, lowest) for _ in shifts]
+        self.shifts = np.ascontiguousarray(shifts, dtype=np.float64)
+        self.code = {"wjacobi": 0, "rbgs": 1}[smoother]
+        self.omega = (2.0 / 3.0 if self.code == 0 else 1.0) if omega is None else float(omega)
+        self._handles = (C.c_void_p * self.k)(*[h.h for h in self.hs])
+        self.lam = np.zeros(2 * self.k)
+
+    def step(self, V, W, nu1=4, nu2=4):
+        """W <- orthonormalised V-cycle outputs of V (both (k, n*n) float64 C-contiguous); returns Rayleigh quotients"""
+        rc = load().orc_block_step(self._handles, self.k, self.code, _p(self.shifts), self.omega, int(nu1), int(nu2), _p(V), _p(W),
+                                   _p(self.lam))
+        if rc:
+            raise RuntimeError("C oracle: singular coarsest operator")
+        return self.lam[0::2] / self.lam[1::2]

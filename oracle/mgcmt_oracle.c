@@ -21,8 +21,9 @@ typedef struct {
   int n;                                   /* n x n grid */
   double *ka[3], *ma[3], *kb[3], *mb[3];   /* lo, di, up; length n */
   double *v, *f, *t;                       /* work vectors (levels >= 1: v, f; all: t) */
-  double *lu;                              /* coarsest: dense LU of (A - shift I), n^2 x n^2, row-major */
+  double *lu;                              /* coarsest: banded LU of (A - shift I), n^2 rows x lu_w window */
   int *piv;
+  int lu_kl, lu_ku, lu_w;
   double lu_shift;
   int lu_valid;
 } level_t;
@@ -240,31 +241,46 @@ static void prolong_add(const level_t *L, const double *e, double *v) {
     }
 }
 
+/* Coarsest level: exact solve (`spsolve(shifted_matrix, f)`, MGCMTSolver.py:305-308) by LU with partial pivoting.  The
+ * 9-point operator on an n x n grid has half-bandwidth n + 1, so the factorisation works on the band only (window
+ * storage: row i keeps columns i - kl .. i + ku + kl, the extra kl columns take the fill of the row interchanges) --
+ * O(N kl (kl + ku)) work instead of O(N^3), which is what makes lowest_level = 64 (BASELINE config 3: "7 levels" at
+ * 4096^2, N = 4096 unknowns) usable.  Multipliers are not permuted retroactively, so the solve interleaves the
+ * interchanges with the eliminations (the LAPACK gbtrf/gbtrs convention). */
+#define BW(L, i, c) (L)->lu[(size_t)(i) * (L)->lu_w + ((c) - ((i) - (L)->lu_kl))]
 static int coarse_factor(level_t *L, double shift) {
   const int n = L->n, N = n * n;
-  if (!L->lu) { L->lu = dalloc((size_t)N * N); L->piv = (int *)calloc(N, sizeof(int)); }
-  double *A = L->lu;
+  const int kl = (n + 1 < N - 1) ? n + 1 : N - 1, ku = kl;
+  L->lu_kl = kl;
+  L->lu_ku = ku;
+  L->lu_w = 2 * kl + ku + 1;
+  if (!L->lu) { L->lu = dalloc((size_t)N * L->lu_w); L->piv = (int *)calloc(N, sizeof(int)); }
+  memset(L->lu, 0, sizeof(double) * (size_t)N * L->lu_w);
   double *unit = dalloc(N);
-  for (int c = 0; c < N; ++c) {      /* column c of A_s = A_s e_c */
-    memset(unit, 0, sizeof(double) * N);
+  for (int c = 0; c < N; ++c) {      /* column c of A_s = A_s e_c, rows within the band */
     unit[c] = 1.0;
-    for (int r = 0; r < N; ++r) A[(size_t)r * N + c] = apply_pt(L, shift, unit, r / n, r % n);
+    const int rlo = c - ku < 0 ? 0 : c - ku, rhi = c + kl > N - 1 ? N - 1 : c + kl;
+    for (int r = rlo; r <= rhi; ++r) BW(L, r, c) = apply_pt(L, shift, unit, r / n, r % n);
+    unit[c] = 0.0;
   }
   free(unit);
-  for (int k = 0; k < N; ++k) {      /* LU with partial pivoting */
+  for (int k = 0; k < N; ++k) {
+    const int rhi = k + kl > N - 1 ? N - 1 : k + kl;
+    const int chi = k + ku + kl > N - 1 ? N - 1 : k + ku + kl;
     int p = k;
-    double best = fabs(A[(size_t)k * N + k]);
-    for (int r = k + 1; r < N; ++r)
-      if (fabs(A[(size_t)r * N + k]) > best) { best = fabs(A[(size_t)r * N + k]); p = r; }
+    double best = fabs(BW(L, k, k));
+    for (int r = k + 1; r <= rhi; ++r)
+      if (fabs(BW(L, r, k)) > best) { best = fabs(BW(L, r, k)); p = r; }
     L->piv[k] = p;
     if (best == 0.0) return 1;
     if (p != k)
-      for (int c = 0; c < N; ++c) { double s = A[(size_t)k * N + c]; A[(size_t)k * N + c] = A[(size_t)p * N + c]; A[(size_t)p * N + c] = s; }
-    for (int r = k + 1; r < N; ++r) {
-      const double m = A[(size_t)r * N + k] / A[(size_t)k * N + k];
-      A[(size_t)r * N + k] = m;
+      for (int c = k; c <= chi; ++c) { double t = BW(L, k, c); BW(L, k, c) = BW(L, p, c); BW(L, p, c) = t; }
+    const double piv = BW(L, k, k);
+    for (int r = k + 1; r <= rhi; ++r) {
+      const double m = BW(L, r, k) / piv;
+      BW(L, r, k) = m;
       if (m != 0.0)
-        for (int c = k + 1; c < N; ++c) A[(size_t)r * N + c] -= m * A[(size_t)k * N + c];
+        for (int c = k + 1; c <= chi; ++c) BW(L, r, c) -= m * BW(L, k, c);
     }
   }
   L->lu_shift = shift;
@@ -273,21 +289,22 @@ static int coarse_factor(level_t *L, double shift) {
 }
 
 static void coarse_solve(level_t *L, const double *f, double *v) {
-  const int N = L->n * L->n;
-  const double *A = L->lu;
+  const int N = L->n * L->n, kl = L->lu_kl, ku = L->lu_ku;
   memcpy(v, f, sizeof(double) * N);
-  for (int k = 0; k < N; ++k) {   /* all row interchanges first (the stored multipliers are in final row order) */
+  for (int k = 0; k < N; ++k) {
     const int p = L->piv[k];
-    if (p != k) { double s = v[k]; v[k] = v[p]; v[p] = s; }
+    if (p != k) { double t = v[k]; v[k] = v[p]; v[p] = t; }
+    const int rhi = k + kl > N - 1 ? N - 1 : k + kl;
+    for (int r = k + 1; r <= rhi; ++r) v[r] -= BW(L, r, k) * v[k];
   }
-  for (int k = 0; k < N; ++k)
-    for (int r = k + 1; r < N; ++r) v[r] -= A[(size_t)r * N + k] * v[k];
   for (int k = N - 1; k >= 0; --k) {
-    double s = v[k];
-    for (int c = k + 1; c < N; ++c) s -= A[(size_t)k * N + c] * v[c];
-    v[k] = s / A[(size_t)k * N + k];
+    const int chi = k + ku + kl > N - 1 ? N - 1 : k + ku + kl;
+    double t = v[k];
+    for (int c = k + 1; c <= chi; ++c) t -= BW(L, k, c) * v[c];
+    v[k] = t / BW(L, k, k);
   }
 }
+#undef BW
 
 static void smooth(const level_t *L, int smoother, double shift, double omega, int nu, double *v, const double *f, double *tmp) {
   if (smoother == 1) rbgs(L, shift, omega, nu, v, f);
@@ -319,4 +336,61 @@ int orc_vcycle(hier_t *h, double shift, double omega, int nu1, int nu2, double *
 /* smoother: 0 = weighted Jacobi (MGCMTSolver.py:182-208), 1 = red-black Gauss-Seidel / SOR (see rbgs above) */
 int orc_vcycle_smoother(hier_t *h, int smoother, double shift, double omega, int nu1, int nu2, double *v, const double *f) {
   return cycle(h, 0, smoother, shift, omega, nu1, nu2, v, f);
+}
+
+/* ---- one outer iteration of the shift method on a block of k vectors (2DPotGS.py:91-105), all host threads ----------
+ * for each c:  w_c = vcycle(0, v_c, H, shift = mu_c)            (2DPotGS.py:95; hs[c]: the hierarchy that caches mu_c's LU)
+ *              lam[2c] = w_c^T H w_c, lam[2c+1] = w_c^T w_c     (the Rayleigh quotient of :103 on the un-normalised w)
+ * then         W = gramschmidt(W)                               (MGCMTProcessor.py:44-50, modified: normalise u_i, subtract
+ *                                                                its projection from all later columns)
+ * V, W: k vectors of n*n doubles, vector-major.  Used by bench.py's reference arm so that it times the same step as
+ * the GPU arm (cycles + Rayleigh sums + block orthonormalisation), not the cycles alone. */
+static double dot_omp(const double *x, const double *y, size_t n) {
+  double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (long long i = 0; i < (long long)n; ++i) s += x[i] * y[i];
+  return s;
+}
+
+int orc_block_step(hier_t **hs, int k, int smoother, const double *shifts, double omega, int nu1, int nu2, const double *V,
+                   double *W, double *lam) {
+  const level_t *L0 = &hs[0]->lev[0];
+  const int n = L0->n;
+  const size_t nn = (size_t)n * n;
+  for (int c = 0; c < k; ++c) {
+    double *w = W + (size_t)c * nn;
+    memset(w, 0, sizeof(double) * nn);
+    if (cycle(hs[c], 0, smoother, shifts[c], omega, nu1, nu2, w, V + (size_t)c * nn)) return 1;
+    double num = 0.0, den = 0.0;
+    double *zero = dalloc(n);
+#pragma omp parallel
+    {
+      double *row = (double *)malloc(sizeof(double) * n);
+#pragma omp for reduction(+ : num, den) schedule(static)
+      for (int i = 0; i < n; ++i) {
+        apply_row(L0, 0.0, w, i, zero, row);
+        const double *wi = w + (size_t)i * n;
+        for (int j = 0; j < n; ++j) { num += wi[j] * row[j]; den += wi[j] * wi[j]; }
+      }
+      free(row);
+    }
+    free(zero);
+    lam[2 * c] = num;
+    lam[2 * c + 1] = den;
+  }
+  for (int i = 0; i < k; ++i) {
+    double *ui = W + (size_t)i * nn;
+    const double nrm = sqrt(dot_omp(ui, ui, nn));
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < (long long)nn; ++t) ui[t] /= nrm;
+    if (i + 1 == k) break;
+    const double uu = dot_omp(ui, ui, nn);
+    for (int j = i + 1; j < k; ++j) {
+      double *wj = W + (size_t)j * nn;
+      const double a = dot_omp(wj, ui, nn) / uu;
+#pragma omp parallel for schedule(static)
+      for (long long t = 0; t < (long long)nn; ++t) wj[t] -= a * ui[t];
+    }
+  }
+  return 0;
 }

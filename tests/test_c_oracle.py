@@ -30,3 +30,26 @@ def test_c_oracle_rbgs_matches_numpy_oracle(N, low, shift, omega):
                       smoother=functools.partial(osv.rbgs, omega=omega))
     got = c_oracle.WellHierarchy(N, low).vcycle(np.zeros(N * N), f, shift, smoother="rbgs", omega=omega)
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-11
+
+
+def test_c_oracle_block_step_matches_numpy_oracle():
+    """the reference arm's step (k V-cycles + Rayleigh sums + modified Gram-Schmidt, 2DPotGS.py:91-105) in C/OpenMP
+    against the same loop written with the numpy oracle; lowest_level = 16 exercises the banded coarsest LU"""
+    import c_oracle
+    import mgcmt_oracle as orc
+    N = 128
+    osm, osv, op = orc.StencilMaker(), orc.Solver(), orc.Processor()
+    H = (-1 / np.pi ** 2) * osm.laplacian(N, "2d")
+    V = np.random.RandomState(0).random_sample((3, N * N))
+    shifts = [1.7, 4.3, 4.4]
+    for low, smoother in ((8, "wjacobi"), (16, "rbgs")):
+        blk = c_oracle.ShiftBlock(N, low, shifts, smoother=smoother)
+        W = np.zeros_like(V)
+        lam = blk.step(V, W)
+        kw = {"smoother": osv.rbgs} if smoother == "rbgs" else {}
+        Wn = np.stack([osv.vcycle(np.zeros(N * N), V[c].copy(), H, osm, shift=shifts[c], dimension="2d", lowest_level=low, **kw)
+                       for c in range(3)])
+        lam_n = np.array([float(w @ (H @ w)) / float(w @ w) for w in Wn])
+        Q = op.gramschmidt(Wn.T.copy()).T
+        assert np.abs(lam - lam_n).max() < 1e-11
+        assert np.abs(Q - W).max() < 1e-11
