@@ -5,10 +5,13 @@
 
 A "step" is one outer iteration of the shift method on the block of the 4 lowest eigenvectors of the 2-D
 infinite well (2DPotGS.py:91-105): for each vector one V(4,4)-cycle of (H - mu_i I) w = v_i, normalise,
-Rayleigh quotient; then modified Gram-Schmidt of the block.  `value` counts smoother unknown-updates/s
-(8 sweeps on every smoothing level of every cycle) with all vectors resident in HBM; `e2e` is the same
-step through the reference-facing MGCMTSolver.vcycle / MGCMTProcessor.gramschmidt calls with HOST numpy
-arrays (pinned), host<->device copies inside the timed region.
+Rayleigh quotient; then modified Gram-Schmidt of the block.  Default workload = BASELINE.json configs[2]:
+4096^2, red-black Gauss-Seidel smoother, 7 levels (lowest_level = 64, exact coarsest solve on 64^2); the
+weighted-Jacobi / lowest_level = 8 variant (the reference's own 2-D choice, 2DPot.py:89) is a side line.
+`value` counts smoother unknown-updates/s (8 sweeps on every smoothing level of every cycle) with all vectors
+resident in HBM; `e2e` is the same cycles through the reference-facing MGCMTSolver.vcycle call with HOST numpy
+arrays, host<->device copies inside the timed region.  `roofline` is per kernel: bytes that leg must move
+(18 B per unknown for the zero-start down leg, 26 B for the up leg) / its CUDA-event time / measured HBM peak.
 
 Prints ONE JSON line (rank 0).  Nothing here reads /root/reference.
 """
@@ -47,8 +50,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--grid", dest="n", type=int, default=0, help="grid size N (N x N unknowns); default 4096 (16384 for --gpus > 1)")
-    ap.add_argument("--lowest", type=int, default=8, help="lowest_level (reference's 2-D choice: 8, 2DPot.py:89)")
-    ap.add_argument("--smoother", default="wjacobi", choices=["wjacobi", "rbgs"])
+    ap.add_argument("--lowest", type=int, default=0,
+                    help="lowest_level; default 64 (BASELINE config 3: 7 levels at 4096^2) on 1 GPU, 8 (2DPot.py:89) on the slab path")
+    ap.add_argument("--smoother", default="", choices=["", "wjacobi", "rbgs"],
+                    help="default rbgs (BASELINE config 3) on 1 GPU, wjacobi on the slab path")
+    ap.add_argument("--no-side", action="store_true", help="skip the side lines (other smoother / lowest_level, convergence run, scaling base)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-n", type=int, default=2048, help="grid size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -193,24 +199,49 @@ def omp_threads():
         return os.cpu_count() or 1
 
 
-def cpu_sample_c(N, lowest, cycles=8):
+def workload_config(N, smoother, lowest, k=4):
+    """the `config` both arms print: what is computed, nothing about how"""
+    levels, g = 1, N
+    while g > lowest:
+        levels += 1
+        g //= 2
+    return {"workload": "2D infinite well %d^2, lowest %d eigenpairs, shift method (2DPotGS.py:91-105): %d x V(4,4) + Rayleigh "
+                        "quotient + modified Gram-Schmidt per step" % (N, k, k),
+            "grid": N, "eigenpairs": k, "smoother": smoother, "lowest_level": lowest, "levels": levels,
+            "l2": "working set %.1f GB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (10 * N * N * 8 / 1e9)}
+
+
+def start_block_host(N):
+    import numpy as np
+    P = interp1(N)
+    shifts = [ev1(N0, a) + ev1(N0, b) for a, b in MODES]
+    V = np.stack([np.kron(P @ vec1(N0, a), P @ vec1(N0, b)) for a, b in MODES])
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    return np.ascontiguousarray(V), shifts
+
+
+def cpu_block_sample(N, smoother, lowest, steps=2, budget_s=25.0):
     """The matrix-free C/OpenMP port of the path (oracle/mgcmt_oracle.c, held to the numpy oracle by
-    tests/test_c_oracle.py) on all host cores: `cycles` V(4,4)-cycles of the bench workload itself."""
+    tests/test_c_oracle.py) on all host cores: `steps` whole shift-method steps of the bench workload (k V-cycles +
+    Rayleigh sums + modified Gram-Schmidt), after one untimed step that also factors the coarsest operators."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
-    h = c_oracle.WellHierarchy(N, lowest)
-    P = interp1(N)
-    shifts = [ev1(N0, a) + ev1(N0, b) for a, b in MODES]
-    v = np.kron(P @ vec1(N0, 1), P @ vec1(N0, 2))
-    v /= np.linalg.norm(v)
-    z = np.zeros(N * N)
-    h.vcycle(z, v, shifts[1])   # factor the coarsest operator, touch memory
+    V, shifts = start_block_host(N)
+    W = np.zeros_like(V)
+    blk = c_oracle.ShiftBlock(N, lowest, shifts, smoother=smoother)
+    blk.step(V, W)
+    V, W = W, V
+    done = 0
     t0 = time.perf_counter()
-    for c in range(cycles):
-        h.vcycle(z, v, shifts[1])
+    for _ in range(steps):
+        blk.step(V, W)
+        V, W = W, V
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return updates_per_cycle(N, lowest) * cycles / dt, dt
+    return len(MODES) * updates_per_cycle(N, lowest) * done / dt, dt, done
 
 
 def cpu_sample(n_cpu, lowest, repeats=1):
@@ -235,11 +266,17 @@ def cpu_sample(n_cpu, lowest, repeats=1):
     return updates_per_cycle(n_cpu, lowest) / best, best
 
 
+def defaults(args, multi):
+    smoother = args.smoother or ("wjacobi" if multi else "rbgs")
+    lowest = args.lowest or (8 if multi else 64)
+    return smoother, lowest
+
+
 def run_reference(args):
     """The reference arm: the CPU implementation of the path on the host cores.  The reference itself is Python 2 and
     cannot be installed or run on this box, so this is the C/OpenMP port of its arithmetic (kind "port") with all host
-    threads, on the bench workload of the same --gpus (4096^2; 16384^2 for N > 1): each step = the 4 V(4,4)-cycles of one
-    shift-method iteration, as many steps as fit the time budget."""
+    threads, on the bench workload of the same --gpus (4096^2; 16384^2 for N > 1): each step is the same step our arm
+    times (k V-cycles + Rayleigh sums + modified Gram-Schmidt, all threaded), as many steps as fit the time budget."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -248,19 +285,16 @@ def run_reference(args):
     import c_oracle
     multi = (int(os.environ.get("WORLD_SIZE", "1")) > 1 or args.gpus > 1) and not args.replicas
     N = args.n or (16384 if multi else 4096)      # the same workload as our arm at this --gpus (16384^2 when slab-decomposed)
-    lowest = args.lowest
-    h = c_oracle.WellHierarchy(N, lowest)
-    P = interp1(N)
-    shifts = [ev1(N0, a) + ev1(N0, b) for a, b in MODES]
-    V = [np.kron(P @ vec1(N0, a), P @ vec1(N0, b)) for a, b in MODES]
-    V = [v / np.linalg.norm(v) for v in V]
-    z = np.zeros(N * N)
+    smoother, lowest = defaults(args, multi)
+    V, shifts = start_block_host(N)
+    W = np.zeros_like(V)
     k = len(MODES)
+    blk = c_oracle.ShiftBlock(N, lowest, shifts, smoother=smoother)
+    bufs = [V, W]
 
     def step():
-        for c in range(k):
-            w = h.vcycle(z, V[c], shifts[c])
-            V[c] = w / np.linalg.norm(w)
+        blk.step(bufs[0], bufs[1])
+        bufs.reverse()
     budget_s = 150.0
     t_start = time.perf_counter()
     warm = 0
@@ -277,15 +311,17 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = k * updates_per_cycle(N, lowest) * done / dt
     cores = omp_threads()
-    sample = ("%d of the requested %d steps (time-bounded); each step = 4 V(4,4)-cycles (wjacobi, lowest_level=%d) + "
-              "normalisation at %d^2; matrix-free C/OpenMP port, %d threads" % (done, args.steps, lowest, N, cores))
+    sample = ("%d of the requested %d steps (time-bounded); each step = %d V(4,4)-cycles (%s, lowest_level=%d) + Rayleigh sums + "
+              "modified Gram-Schmidt at %d^2; matrix-free C/OpenMP port, %d threads" % (done, args.steps, k, smoother, lowest, N, cores))
+    cfg = workload_config(N, smoother, lowest, k)
+    if multi:
+        cfg["l2"] = "per-rank working set >> 126 MB L2"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": done, "warmup": warm, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
-        "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "2D infinite well %d^2, lowest 4 eigenpairs, shift method: 4 x V(4,4) per step (CPU port of the "
-                               "reference's arithmetic; the Python-2 reference itself cannot run here)" % N,
-                   "smoother": "wjacobi", "lowest_level": lowest},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "impl_detail": "CPU port of the reference's arithmetic (oracle/mgcmt_oracle.c); the Python-2 reference itself cannot run here",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -296,6 +332,47 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+LEG_KINDS = {1: ("down leg, zero start", 18.0), 2: ("down leg", 26.0), 3: ("up leg", 26.0), 4: ("up leg + Rayleigh sums", 26.0)}
+
+
+def time_steps(torch, run, nsteps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(nsteps)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def leg_profile(lib, torch, loop, nserial, n, smoother, peak, traffic_tab, N):
+    """serial pass of the same step on ONE stream with CUDA events around every finest-level leg (inside the timed
+    region the cycles overlap on several streams, so a bracketed kernel would be timed sharing the GPU)"""
+    lib.mgcmt_profile_enable(1)
+    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    es0.record()
+    for _ in range(nserial):
+        loop.step(serial=True)
+    es1.record()
+    torch.cuda.synchronize()
+    ms_serial = es0.elapsed_time(es1) / nserial
+    ms_k = (C.c_double * 5)()
+    cnt_k = (C.c_longlong * 5)()
+    lib.mgcmt_profile_read_kinds(ms_k, cnt_k)
+    lib.mgcmt_profile_enable(0)
+    kernels = []
+    for kind, (label, bpu) in LEG_KINDS.items():
+        if cnt_k[kind] == 0:
+            continue
+        per = ms_k[kind] / cnt_k[kind]
+        gbs = bpu * n / (per * 1e-3) / 1e9
+        name = ("uni5_leg_kernel<%s>" % ("GS: 8 colour stages" if smoother == "rbgs" else "4 Jacobi sweeps")) + " finest-level " + label
+        kernels.append({"kernel": name, "kind": label, "launch_ms": per, "launches_timed": int(cnt_k[kind]),
+                        "algorithmic_bytes_per_launch": bpu * n, "bytes_per_unknown": bpu, "achieved": gbs, "frac": gbs / peak,
+                        "share_of_step": ms_k[kind] / (ms_serial * nserial),
+                        "traffic": traffic_tab.get("%s:%s" % (smoother, label)) if N == 4096 else None})
+    return kernels, ms_serial
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -312,25 +389,26 @@ def run_ours(args):
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             dist.barrier()
 
-    from multigridcmt_b200 import MGCMTProcessor, MGCMTSolver, MGCMTStencilMaker, _lib
-    from multigridcmt_b200.hierarchy import _ptr, _stream_ptr, get_hierarchy
+    from multigridcmt_b200 import MGCMTProcessor, MGCMTSolver, MGCMTStencilMaker, ZeroVector, _lib
+    from multigridcmt_b200.hierarchy import _ptr, _stream_ptr
+    from multigridcmt_b200.eigensolver import ShiftMethod
     lib = _lib.load()
     sm, solver, proc = MGCMTStencilMaker(), MGCMTSolver(), MGCMTProcessor()
 
     N = args.n or 4096
-    lowest = args.lowest
+    smoother, lowest = defaults(args, False)
     n = N * N
     H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
     V_host, shifts = initial_block(N)
     k = len(MODES)
+    exact = np.array([ev1(N, a) + ev1(N, b) for a, b in MODES])
     # The timed object is the package's own device-resident outer loop (multigridcmt_b200/eigensolver.py): the k
     # eigenvectors of a step are independent until the Gram-Schmidt, so each V-cycle gets its own CUDA stream and its
     # own hierarchy (level work vectors) -- the latency-bound coarse levels of one cycle overlap the HBM-bound fine
     # levels of another.  With N ranks and --replicas every rank runs the same independent block.
-    from multigridcmt_b200.eigensolver import ShiftMethod
-    loop = ShiftMethod(H, shifts, V_host, dimension="2d", lowest_level=lowest, nu1=4, nu2=4, smoother=args.smoother,
+    t_setup = time.perf_counter()
+    loop = ShiftMethod(H, shifts, V_host, dimension="2d", lowest_level=lowest, nu1=4, nu2=4, smoother=smoother,
                        ortho=("gram" if args.ortho == "gram" else "mgs"), streams=args.streams)
-    h = loop.hier[0]
     nstreams = len(loop.streams)
     rq = loop.rq
     ortho_mode = loop.ortho
@@ -340,6 +418,9 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
         clocks.wait_first()
+    step()                       # builds the k coarsest inverses (one per shift)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -360,97 +441,17 @@ def run_ours(args):
     run, graphed = make_runner(step, torch, not args.no_graph)
     run(2)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.time()
-    e0.record()
-    run(args.steps)
-    e1.record()
-    torch.cuda.synchronize()
+    ms = time_steps(torch, run, args.steps)
     t_end = time.time()
-    launches_timed = launches_per_step * args.steps
-    # roofline pass: the same step, run serially on one stream so that the CUDA events bracketing every
-    # finest-level leg (on its launching stream) time that kernel alone, not its share of an overlapped GPU
-    lib.mgcmt_profile_enable(1)
-    es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    es0.record()
-    nserial = min(args.steps, 10)
-    for _ in range(nserial):
-        step(serial=True)
-    es1.record()
-    torch.cuda.synchronize()
-    ms_serial = es0.elapsed_time(es1) / nserial
+    launches = launches_per_step * args.steps
+    lam = (rq[:, 0] / rq[:, 1]).cpu().tolist()   # Rayleigh quotients of the last timed step's V-cycle outputs
     if world > 1:
         dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = launches_timed
-    dom_ms, dom_cnt = C.c_double(), C.c_longlong()
-    lib.mgcmt_profile_read(C.byref(dom_ms), C.byref(dom_cnt))
-    lib.mgcmt_profile_enable(0)
-    lam = (rq[:, 0] / rq[:, 1]).cpu().tolist()   # eigenvalue estimates of the measured (Jacobi) run
-    # the other smoother of the path, same step (BASELINE config 3 names red-black Gauss-Seidel): a short side run
-    other = None
-    if world == 1 and args.smoother == "wjacobi":
-        loop.set_smoother("rbgs")
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        eo0, eo1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        eo0.record()
-        for _ in range(20):
-            step()
-        eo1.record()
-        torch.cuda.synchronize()
-        ms_o = eo0.elapsed_time(eo1) / 20
-        lam_o = (rq[:, 0] / rq[:, 1]).cpu().tolist()
-        other = {"smoother": "rbgs (four-colour = red-black on the 5-point level, omega = 1)", "ms_per_step": ms_o,
-                 "vcycles_per_s": k / (ms_o * 1e-3), "value": k * updates_per_cycle(N, lowest) / (ms_o * 1e-3),
-                 "eigenvalues": lam_o}
-        loop.set_smoother(args.smoother)
-    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
-    if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    exact = [ev1(N, a) + ev1(N, b) for a, b in MODES]
-
-    ups_step = k * updates_per_cycle(N, lowest)
-    value = world * ups_step * args.steps / (ms * 1e-3)
-
-    # ---- e2e: the reference-facing call with host buffers (pinned), copies inside the timed region -----
-    e2e = None
-    if args.e2e_steps > 0:
-        Vh = torch.from_numpy(V_host.copy()).pin_memory()
-        zero_h = torch.zeros(n, dtype=torch.float64).pin_memory()
-        Vnp = Vh.numpy()
-        znp = zero_h.numpy()
-
-        def e2e_step():
-            # the call a user of the reference makes (2DPotGS.py:95), host arrays in, host array out;
-            # what the caller then does with w on the host (numpy normalisation) is not part of the path
-            for c in range(k):
-                w = solver.vcycle(znp, Vnp[c], H, sm, shift=shifts[c], dimension="2d", lowest_level=lowest,
-                                  smoother=(solver.rbgs if args.smoother == "rbgs" else None))
-                assert w.shape == (n,)
-                znp.shape = (n,)
-        e2e_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * ups_step * args.e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": k * 2 * n * 8, "d2h_bytes_per_step": k * n * 8,
-               "steps": args.e2e_steps, "call": "MGCMTSolver.vcycle(numpy, numpy, H, sm, shift=, dimension='2d')"}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
 
     peaks = {}
     try:
@@ -459,58 +460,164 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    # dominant kernel = a finest-level V-cycle leg (fused_leg_kernel: 4 Jacobi sweeps + residual/restriction
-    # or prolongation/correction in ONE pass).  Algorithmic bytes per SURVEY.md section 8(d): 4 x 24 B
-    # (sweeps) + 18 B (transfer) = 114 B per fine unknown and leg; the fused kernel actually moves ~26 B
-    # per unknown (ncu: profiles/), which is why `achieved` can exceed the copy-bandwidth peak.
+    kernels, ms_serial = leg_profile(lib, torch, loop, min(args.steps, 10), n, smoother, peak, TRAFFIC_NCU, N)
+
+    ups_step = k * updates_per_cycle(N, lowest)
+    value = world * ups_step * args.steps / (ms * 1e-3)
+
+    # ---- side lines (not the headline): the other smoother / depth, convergence to 1e-10, the strong-scaling base ----
+    side, converge, scaling_base = [], None, None
+    if world == 1 and not args.no_side:
+        for sm_o, low_o in (("wjacobi", 8), ("rbgs", 8), ("wjacobi", 64)):
+            if (sm_o, low_o) == (smoother, lowest):
+                continue
+            lo = ShiftMethod(H, shifts, V_host, dimension="2d", lowest_level=low_o, smoother=sm_o, ortho="gram", streams=args.streams)
+            for _ in range(4):
+                lo.step()
+            run_o, _g = make_runner(lo.step, torch, not args.no_graph)
+            run_o(2)
+            torch.cuda.synchronize()
+            ms_o = time_steps(torch, run_o, 20) / 20
+            kern_o, _ = leg_profile(lib, torch, lo, 4, n, sm_o, peak, TRAFFIC_NCU, N)
+            side.append({"smoother": sm_o, "lowest_level": low_o, "ms_per_step": ms_o, "vcycles_per_s": k / (ms_o * 1e-3),
+                         "value": k * updates_per_cycle(N, low_o) / (ms_o * 1e-3),
+                         "legs": [{"kind": kk["kind"], "launch_ms": kk["launch_ms"], "frac": kk["frac"]} for kk in kern_o]})
+            del lo, run_o
+        # north_star: lowest 4 eigenpairs to 1e-10.  The reference's loop has no stopping rule and, as a
+        # power iteration on the V-cycle operator, stagnates at the cycle's own mode mixing; the correction form
+        # (ShiftMethod.correction_step, same cycles, right-hand side = eigen-residual) has exact eigenvectors as fixed points.
+        floor = 0.5 * np.finfo(float).eps * 8.0 * N * N / np.pi ** 2   # fp64 evaluation floor of ||H v - rho v||: eps/2 * ||H||_inf
+        conv = {}
+        for form in ("reference", "correction"):
+            lc = ShiftMethod(H, shifts, V_host, dimension="2d", lowest_level=lowest, smoother=smoother, ortho="gram", streams=args.streams)
+            lc.step(); lc.blocks[lc.cur].copy_(torch.from_numpy(V_host).cuda()); lc.iterations = 0   # coarsest inverses built, block reset
+            torch.cuda.synchronize()
+            tc = time.perf_counter()
+            r = lc.solve(tol=max(1e-10, floor), max_iters=(40 if form == "correction" else 25), form=form, exact=None)
+            torch.cuda.synchronize()
+            tcs = time.perf_counter() - tc
+            hist = r["history"]
+            it_eig = next((it for it, res, rho in hist if np.all(np.abs(rho - exact) <= 1e-10)), None)
+            conv[form] = {"converged": bool(r["converged"]), "iterations": int(r["iterations"]), "time_ms": 1e3 * tcs,
+                          "iters_to_eigenvalues_1e-10": it_eig,
+                          "residual_norms": [float(x) for x in r["residual_norms"]],
+                          "eigenvalue_abs_err": [float(x) for x in np.abs(r["eigenvalues"] - exact)],
+                          "residual_tolerance": max(1e-10, floor)}
+            del lc
+        converge = {"criterion": "||H v - rho v||_2 <= max(1e-10, eps/2 ||H||_inf) and |rho - closed form| <= 1e-10 (SURVEY D8); "
+                                 "at %d^2 ||H||_inf = %.2e, so the fp64 floor of the residual norm is %.1e" % (N, 8.0 * N * N / np.pi ** 2, floor),
+                    "reference_form": conv["reference"], "correction_form": conv["correction"]}
+        if N == 4096:
+            try:   # the 1-GPU time of the multi-GPU workload (16384^2, Jacobi, lowest 8): denominator of the strong-scaling curve
+                Nb, lowb = 16384, 8
+                Hb = (-1.0 / np.pi ** 2) * sm.laplacian(Nb, "2d", matrix_free=True)
+                Vb, shb = initial_block(Nb)
+                lb = ShiftMethod(Hb, shb, Vb, dimension="2d", lowest_level=lowb, smoother="wjacobi", ortho="gram", streams=args.streams)
+                del Vb
+                for _ in range(3):
+                    lb.step()
+                torch.cuda.synchronize()
+                ms_b = time_steps(torch, lambda m: [lb.step() for _ in range(m)], 6) / 6
+                scaling_base = {"grid": Nb, "smoother": "wjacobi", "lowest_level": lowb, "n_gpus": 1, "ms_per_step": ms_b,
+                                "value": k * updates_per_cycle(Nb, lowb) / (ms_b * 1e-3),
+                                "note": "same step as `--gpus N>1` (row slabs) on one GPU: divide the N-GPU ms_per_step into this"}
+                del lb
+                torch.cuda.empty_cache()
+            except Exception as e:   # e.g. out of memory on a smaller part
+                scaling_base = {"error": str(e).splitlines()[0] if str(e) else type(e).__name__}
+
+    # ---- e2e: the reference-facing call with host buffers, copies inside the timed region -----
+    e2e = None
+    if args.e2e_steps > 0:
+        Vh = torch.from_numpy(V_host.copy()).pin_memory()
+        Vnp = Vh.numpy()
+        Vpage = V_host.copy()
+        zero = ZeroVector(n)
+        kw = {"smoother": solver.rbgs} if smoother == "rbgs" else {}
+
+        def e2e_step(src, v0):
+            # the call a user of the reference makes (2DPotGS.py:95), host arrays in, host array out;
+            # what the caller then does with w on the host (numpy normalisation) is not part of the path
+            for c in range(k):
+                w = solver.vcycle(v0, src[c], H, sm, shift=shifts[c], dimension="2d", lowest_level=lowest, **kw)
+                assert w.shape == (n,)
+
+        def timed(src, v0):
+            e2e_step(src, v0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step(src, v0)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return world * ups_step * args.e2e_steps / dt
+        v_pinned = timed(Vnp, zero)
+        v_page = timed(Vpage, zero)
+        zeros_np = np.zeros(n)
+
+        def with_zero_upload():
+            r = timed(Vnp, zeros_np)
+            zeros_np.shape = (n,)
+            return r
+        v_zero_upload = with_zero_upload()
+        e2e = {"value": v_pinned, "unit": UNIT, "h2d_bytes_per_step": k * n * 8, "d2h_bytes_per_step": k * n * 8,
+               "steps": args.e2e_steps,
+               "call": "MGCMTSolver.vcycle(ZeroVector(n), numpy f (pinned), H, sm, shift=, dimension='2d', lowest_level=%d%s)"
+                       % (lowest, ", smoother=solver.rbgs" if smoother == "rbgs" else ""),
+               "pageable_f": v_page, "with_numpy_zero_v0_upload": v_zero_upload}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     roofline = None
-    if dom_cnt.value > 0:
-        per_launch_ms = dom_ms.value / dom_cnt.value
-        if args.smoother == "wjacobi":
-            dom_bytes = 114.0 * n
-            kname = "fused_leg_kernel<FIVE,NU=4> (finest-level leg: 4 sweeps + transfer fused)"
-            actual = 26.0 * n
-        else:
-            dom_bytes = 114.0 * n
-            kname = "fused_leg_kernel<FIVE,GS,NU=8> (finest-level leg: 4 red-black sweeps = 8 colour stages + transfer fused)"
-            actual = 26.0 * n
-        achieved = dom_bytes / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": TRAFFIC_NCU.get(args.smoother if N == 4096 else ""), "kernel": kname,
-                    "launch_ms": per_launch_ms, "launches_timed": dom_cnt.value,
-                    "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_kind,
-                    "share_of_step": dom_ms.value / (ms_serial * nserial),
-                    "timed_in": "serial pass of %d steps after the timed region (%.3f ms/step on one stream)" % (nserial, ms_serial),
-                    "expected_dram_bytes_per_launch": actual,
-                    "dram_gbs_if_expected_traffic": (actual / (per_launch_ms * 1e-3) / 1e9) if actual else None,
-                    "step_frac_304B": (304.0 * n * k * args.steps / (ms * 1e-3) / 1e9) / peak}
+    if kernels:
+        dom = max(kernels, key=lambda kk: kk["share_of_step"])
+        roofline = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": dom["traffic"], "kernel": dom["kernel"], "launch_ms": dom["launch_ms"],
+                    "launches_timed": dom["launches_timed"], "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                    "peak_source": peak_kind, "share_of_step": dom["share_of_step"],
+                    "timed_in": "serial pass of %d steps after the timed region (%.3f ms/step on one stream), CUDA events on the launching stream"
+                                % (min(args.steps, 10), ms_serial),
+                    "kernels": kernels,
+                    "algorithmic_speedup": {"unfused_bytes_per_unknown_and_cycle": 304.0,
+                                            "step_GBs_at_304B": 304.0 * n * k * args.steps / (ms * 1e-3) / 1e9,
+                                            "note": "SURVEY 8(d)'s figure for one kernel per operator; the fused legs move 18-26 B per "
+                                                    "unknown and leg instead of 114 B, which is a traffic saving, not bandwidth"}}
 
     cpu_baseline = None
     if not args.no_cpu and world == 1:
-        v_c, t_c = cpu_sample_c(N, lowest, cycles=8)
-        v_cpu, t_cpu = cpu_sample(args.cpu_n, lowest)
+        v_c, t_c, done_c = cpu_block_sample(N, smoother, lowest, steps=4)
         cpu_baseline = {"value": v_c, "unit": UNIT, "cores": omp_threads(), "kind": "port",
-                        "sample": "8 V(4,4)-cycles (wjacobi, lowest_level=%d) of the %d^2 workload: %.2f s with the matrix-free "
-                                  "C/OpenMP port on %d threads" % (lowest, N, t_c, omp_threads()),
-                        "scipy_port_1core": {"value": v_cpu, "sample": "1 V(4,4)-cycle at %d^2, hierarchy prebuilt, %.2f s, "
-                                             "scipy CSC SpMV (the port pinned to the real reference; single-threaded)"
-                                             % (args.cpu_n, t_cpu)}}
+                        "sample": "%d shift-method steps (%d V(4,4)-cycles each, %s, lowest_level=%d, + Rayleigh sums + modified "
+                                  "Gram-Schmidt) of the %d^2 workload: %.2f s with the matrix-free C/OpenMP port on %d threads"
+                                  % (done_c, k, smoother, lowest, N, t_c, omp_threads())}
+        if not args.no_side:
+            v_cpu, t_cpu = cpu_sample(args.cpu_n, 8)
+            cpu_baseline["scipy_port_1core"] = {"value": v_cpu, "sample": "1 V(4,4)-cycle (wjacobi, lowest_level=8) at %d^2, hierarchy prebuilt, "
+                                                "%.2f s, scipy CSC SpMV (the port pinned to the real reference; single-threaded)" % (args.cpu_n, t_cpu)}
 
+    cfg = workload_config(N, smoother, lowest, k)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "2D infinite well %d^2, lowest 4 eigenpairs, shift method: 4 x V(4,4) + normalise + "
-                               "Rayleigh quotient + MGS per step" % N,
-                   "smoother": args.smoother, "lowest_level": lowest, "levels": h.num_levels,
-                   "parallelism": "replicas x%d" % world if world > 1 else "1 GPU", "streams": nstreams, "cuda_graph": graphed,
-                   "ortho": ("Gram-matrix form of the Gram-Schmidt step (12 instead of 29 vector passes); rel. difference to "
-                             "column-by-column MGS on this block: %.1e" % ortho_check) if ortho_mode == 2 else "column-by-column MGS",
-                   "l2": "working set %.1f GB >> 126 MB L2 (inputs larger than L2)" % (10 * n * 8 / 1e9)},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "impl_detail": {"parallelism": "replicas x%d" % world if world > 1 else "1 GPU", "streams": nstreams, "cuda_graph": graphed,
+                        "ortho": ("Gram-matrix form of the Gram-Schmidt step (12 instead of 29 vector passes); rel. difference to "
+                                  "column-by-column MGS on this block: %.1e" % ortho_check) if ortho_mode == 2 else "column-by-column MGS",
+                        "setup_s": setup_s, "setup": "hierarchies + %d coarsest inverses (%d unknowns each, banded LU above 256)" % (k, lowest * lowest),
+                        "scaling_note": "--gpus 1 runs BASELINE config 3 (4096^2); --gpus N>1 runs config 5 (16384^2 in row slabs): "
+                                        "use scaling_base as the 1-GPU point of the strong-scaling curve"},
         "vcycles_per_s": world * k * args.steps / (ms * 1e-3),
         "eigenvalues": lam, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam, exact)],
         "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline,
-        "cpu_baseline": cpu_baseline, "other_smoother": other,
+        "cpu_baseline": cpu_baseline, "side_lines": side, "converge": converge, "scaling_base": scaling_base,
     }
     print(json.dumps(line))
     if world > 1:
@@ -564,7 +671,9 @@ def run_slab(args):
     from multigridcmt_b200.slab import HALO, SlabVCycle, TorchDistComm
     lib = _lib.load()
     N = args.n or 16384
-    lowest = args.lowest
+    smoother_s, lowest = defaults(args, True)
+    if smoother_s != "wjacobi":
+        raise SystemExit("bench.py: the slab path runs the weighted-Jacobi legs")
     k = len(MODES)
     sm = MGCMTStencilMaker()
     H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)

@@ -63,6 +63,15 @@ const char *mgcmt_last_error(void);
 long long mgcmt_launch_count(void);
 int mgcmt_profile_enable(int on);
 int mgcmt_profile_read(double *ms_total, long long *intervals);
+/* the same per kind of finest-level launch (arrays of MGCMT_PROF_KINDS entries): the legs of a V-cycle move different
+ * amounts of data (zero-start down leg 18 B, down / up leg 26 B per unknown), so a roofline fraction is per kind */
+#define MGCMT_PROF_SWEEP 0      /* a single smoother sweep / un-fused smoother call */
+#define MGCMT_PROF_DOWN_ZERO 1  /* fused down leg, zero initial guess (v not read) */
+#define MGCMT_PROF_DOWN 2       /* fused down leg */
+#define MGCMT_PROF_UP 3         /* fused up leg */
+#define MGCMT_PROF_UP_RQ 4      /* fused up leg that also leaves the Rayleigh sums (mgcmt_vcycle_rq) */
+#define MGCMT_PROF_KINDS 5
+int mgcmt_profile_read_kinds(double *ms_by_kind, long long *intervals_by_kind);
 
 /* ---- hierarchy -------------------------------------------------------------------------------
  * Builds all levels from the finest grid (nrows x ncols) down to the level whose column count is

@@ -41,6 +41,20 @@ def _is_complex(x):
     return np.iscomplexobj(x)
 
 
+class ZeroVector:
+    """Stands for `np.zeros(n)` as the start vector of `vcycle` / `vcycle_matrix`: every driver of the reference starts
+    its cycles from zero (`w0 = np.zeros(n)`, 2DPotGS.py:94, 2DPot.py:88), and shipping 8 n bytes of zeros over PCIe per
+    call -- to have the first smoothing pass read them back from HBM -- is a third of the host traffic of a cycle.
+    `solver.vcycle(ZeroVector(n), f, H, ...)` uploads nothing and takes the zero-start legs (the down leg never reads v)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = (self.n,)
+
+    def __len__(self):
+        return self.n
+
+
 def _inplace_column(x, n):
     """The reference does `x.shape = (n, 1)` on the caller's array; mimic it when possible."""
     if isinstance(x, np.ndarray):
@@ -223,10 +237,12 @@ class MGCMTSolver:
             grid_dimension = n
         elif dimension == "2d":
             grid_dimension = np.sqrt(n)
-        dev_in = is_device_tensor(v0)
+        zero_start = isinstance(v0, ZeroVector)
+        dev_in = is_device_tensor(f if zero_start else v0)
         if not dev_in:
             _inplace_column(f, n)
-            _inplace_column(v0, n)
+            if not zero_start:
+                _inplace_column(v0, n)
         if grid_dimension < 2:
             print("Length of start vector is not a power of 2")
             return None
@@ -236,17 +252,20 @@ class MGCMTSolver:
             # the reference would recurse until the stencil maker prints its power-of-two message
             print("Length of start vector is not a power of 2")
             return None
-        op = self._route(A, dimension, v0, f)
+        op = self._route(A, dimension, f if zero_start else v0, f)
         if isinstance(op, BandedOperator):
-            return self._vcycle_banded(op, v0, f, nu1, nu2, code, omega, shift, low)
+            return self._vcycle_banded(op, np.zeros(n) if zero_start else v0, f, nu1, nu2, code, omega, shift, low)
         h = get_hierarchy(op, low)
-        v = to_device(v0)
-        if dev_in:
-            v = v.clone()
         fd = to_device(f)
-        if fd.data_ptr() == v.data_ptr():
-            fd = fd.clone()
-        h.vcycle(shift, nu1, nu2, code, omega, v, fd)
+        if zero_start:
+            v = _lib.require_cuda().empty(n, dtype=fd.dtype, device=fd.device)
+        else:
+            v = to_device(v0)
+            if dev_in:
+                v = v.clone()
+            if fd.data_ptr() == v.data_ptr():
+                fd = fd.clone()
+        h.vcycle(shift, nu1, nu2, code, omega, v, fd, v0_is_zero=zero_start)
         coarsest_direct = (h.num_levels == 1)
         if dev_in:
             return v.reshape(n, 1) if coarsest_direct else v

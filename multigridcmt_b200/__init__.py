@@ -8,8 +8,8 @@ Everything numerical runs in libmgcmt_b200.so (hand-written sm_100a CUDA, C ABI 
 include/mgcmt_b200.h); there is no CPU fallback.
 """
 from .MGCMTProcessor import MGCMTProcessor
-from .MGCMTSolver import MGCMTSolver
+from .MGCMTSolver import MGCMTSolver, ZeroVector
 from .MGCMTStencilMaker import MGCMTStencilMaker
 from .operators import SeparableOperator, UnsupportedOperator
 
-__all__ = ["MGCMTStencilMaker", "MGCMTSolver", "MGCMTProcessor", "SeparableOperator", "UnsupportedOperator"]
+__all__ = ["MGCMTStencilMaker", "MGCMTSolver", "MGCMTProcessor", "SeparableOperator", "UnsupportedOperator", "ZeroVector"]

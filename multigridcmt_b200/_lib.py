@@ -33,6 +33,7 @@ SIGNATURES = {
     "mgcmt_launch_count": (_LL, []),
     "mgcmt_profile_enable": (_I, [_I]),
     "mgcmt_profile_read": (_I, [C.POINTER(_D), C.POINTER(_LL)]),
+    "mgcmt_profile_read_kinds": (_I, [C.POINTER(_D), C.POINTER(_LL)]),
     "mgcmt_hier_create": (_I, [C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
     "mgcmt_hier_create2": (_I, [C.POINTER(_P), _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "mgcmt_hier_create_slab": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

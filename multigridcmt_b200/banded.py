@@ -171,17 +171,16 @@ _RECOGNISED = {}
 
 
 def recognise_banded(A):
-    """BandedOperator.from_sparse with a small identity cache (drivers pass the same matrix every call)."""
+    """BandedOperator.from_sparse with a small identity cache (drivers pass the same matrix every call); entries are
+    validated by a weak reference to the matrix and a position-sensitive fingerprint (operators.data_fingerprint)."""
+    from .operators import _cache_lookup, _cache_store
     if isinstance(A, BandedOperator):
         return A
-    fp = (id(A), A.shape, getattr(A, "nnz", None)) + data_fingerprint(A)
-    hit = _RECOGNISED.get(id(A))
-    if hit is not None and hit[0] == fp:
-        return hit[1]
-    op = BandedOperator.from_sparse(A)
-    if len(_RECOGNISED) > 64:
-        _RECOGNISED.clear()
-    _RECOGNISED[id(A)] = (fp, op)
+    fp = (A.shape, getattr(A, "nnz", None)) + data_fingerprint(A)
+    op = _cache_lookup(_RECOGNISED, A, fp)
+    if op is None:
+        op = BandedOperator.from_sparse(A)
+        _cache_store(_RECOGNISED, A, fp, op)
     return op
 
 

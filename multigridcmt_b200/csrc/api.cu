@@ -24,6 +24,7 @@ thread_local std::string g_err;
 struct Profile {
   bool on = false;
   std::vector<cudaEvent_t> pool;  // pairs
+  std::vector<int> kind;          // per event: MGCMT_PROF_* of the interval it opens / closes
   size_t used = 0;
 } g_prof;
 
@@ -32,14 +33,17 @@ int g_opt_fused = 1;
 int g_opt_fused_min_cols = 64;
 int g_opt_tile_max_cols = 256;   // levels this narrow (or narrower) use the shared-memory tile legs
 int g_opt_tail_max_cols = 32;    // levels this narrow are collapsed into the single-CTA tail kernel
+int g_opt_coarse_banded = 2;     // coarsest inverse through the banded LU: 0 never, 1 whenever it fits, 2 = when n > 256
 
-void prof_mark(cudaStream_t s) {
+void prof_mark(cudaStream_t s, int kind = MGCMT_PROF_SWEEP) {
   if (!g_prof.on) return;
   if (g_prof.used == g_prof.pool.size()) {
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     g_prof.pool.push_back(e);
+    g_prof.kind.push_back(0);
   }
+  g_prof.kind[g_prof.used] = kind;
   cudaEventRecord(g_prof.pool[g_prof.used++], s);
 }
 
@@ -201,12 +205,21 @@ int get_inverse(mgcmt_hier *h, double shift, cudaStream_t s, double **out) {
     CU(cudaMalloc(&inv, sizeof(double) * (size_t)n * n));
   }
   double *aug = nullptr, *mult = nullptr;
-  CU(cudaMalloc(&aug, sizeof(double) * (size_t)n * 2 * n));
-  CU(cudaMalloc(&mult, sizeof(double) * (n + 4)));
   CU(cudaMemsetAsync(h->status, 0, sizeof(int), s));
-  CU(launch_build_dense(L.dev, shift, aug, s));
-  CU(launch_gauss_jordan(n, aug, h->status, mult, s));
-  CU(launch_extract_inverse(n, aug, inv, s));
+  // banded LU for coarsest levels beyond a few hundred unknowns (g_opt_coarse_banded: 0 never, 1 whenever it fits,
+  // 2 = auto: n > 256), dense Gauss-Jordan otherwise; both with partial pivoting, both leave the dense inverse
+  const bool banded = band_inverse_fits(L.dev) && (g_opt_coarse_banded == 1 || (g_opt_coarse_banded == 2 && n > 256));
+  if (banded) {
+    const int kl = (L.dev.nrows > 1) ? (L.dev.ncols + 1 < n - 1 ? L.dev.ncols + 1 : n - 1) : 1;
+    CU(cudaMalloc(&aug, sizeof(double) * band_workspace_doubles(n, kl, kl)));
+    CU(launch_band_inverse2d(L.dev, shift, inv, h->status, aug, s));
+  } else {
+    CU(cudaMalloc(&aug, sizeof(double) * (size_t)n * 2 * n));
+    CU(cudaMalloc(&mult, sizeof(double) * (n + 4)));
+    CU(launch_build_dense(L.dev, shift, aug, s));
+    CU(launch_gauss_jordan(n, aug, h->status, mult, s));
+    CU(launch_extract_inverse(n, aug, inv, s));
+  }
   int st = 0;
   CU(cudaMemcpyAsync(&st, h->status, sizeof(int), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -288,10 +301,11 @@ int fused_down(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu
     v_zero = false;
   }
   if (v_zero && left == 0) CU(cudaMemsetAsync(a, 0, sizeof(double) * L.n, s));
-  if (l == 0) prof_mark(s);
+  const int dkind = (v_zero && left > 0) ? MGCMT_PROF_DOWN_ZERO : MGCMT_PROF_DOWN;
+  if (l == 0) prof_mark(s, dkind);
   CU(launch_pass(h, l, gs, (v_zero && left > 0) ? FUSED_DOWN_ZERO : FUSED_DOWN, left, shift, omega, a, f, b, nullptr,
                  C.f, s));
-  if (l == 0) prof_mark(s);
+  if (l == 0) prof_mark(s, dkind);
   if (left > 0) { double *t = a; a = b; b = t; }
   *cur = a;
   return MGCMT_OK;
@@ -305,7 +319,8 @@ int fused_up(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu2,
   double *a = cur, *b = (cur == v) ? L.tmp : v;
   int left = nu2;
   const int first = left > maxpass ? maxpass : left;
-  if (l == 0) prof_mark(s);
+  const int ukind = (l == 0 && h->rq_out) ? MGCMT_PROF_UP_RQ : MGCMT_PROF_UP;
+  if (l == 0) prof_mark(s, ukind);
   // finest level, Rayleigh quotient requested and this pass is the last one: the up leg also leaves the partial sums
   const int slots = (l == 0 && h->rq_out && first == 4 && left == 4 && !use_tile(h, l)) ? fused_rq_slots(L.dev, gs ? 1 : 0) : 0;
   if (slots > 0) {
@@ -322,7 +337,7 @@ int fused_up(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu2,
   } else {
     CU(launch_pass(h, l, gs, FUSED_UP, first, shift, omega, a, f, b, e, nullptr, s));
   }
-  if (l == 0) prof_mark(s);
+  if (l == 0) prof_mark(s, ukind);
   { double *t = a; a = b; b = t; }
   left -= first;
   while (left > 0) {
@@ -392,19 +407,34 @@ int mgcmt_profile_enable(int on) {
   return MGCMT_OK;
 }
 
-int mgcmt_profile_read(double *ms_total, long long *intervals) {
+int mgcmt_profile_read_kinds(double *ms_by_kind, long long *intervals_by_kind) {
   CU(cudaDeviceSynchronize());
-  double tot = 0.0;
-  long long cnt = 0;
+  double tot[MGCMT_PROF_KINDS] = {0};
+  long long cnt[MGCMT_PROF_KINDS] = {0};
   for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, g_prof.pool[i], g_prof.pool[i + 1]));
-    tot += ms;
-    ++cnt;
+    const int k = g_prof.kind[i];
+    if (k >= 0 && k < MGCMT_PROF_KINDS) { tot[k] += ms; ++cnt[k]; }
   }
   g_prof.used = 0;
-  if (ms_total) *ms_total = tot;
-  if (intervals) *intervals = cnt;
+  for (int k = 0; k < MGCMT_PROF_KINDS; ++k) {
+    if (ms_by_kind) ms_by_kind[k] = tot[k];
+    if (intervals_by_kind) intervals_by_kind[k] = cnt[k];
+  }
+  return MGCMT_OK;
+}
+
+int mgcmt_profile_read(double *ms_total, long long *intervals) {
+  double tot[MGCMT_PROF_KINDS];
+  long long cnt[MGCMT_PROF_KINDS];
+  int rc = mgcmt_profile_read_kinds(tot, cnt);
+  if (rc) return rc;
+  double t = 0.0;
+  long long c = 0;
+  for (int k = 0; k < MGCMT_PROF_KINDS; ++k) { t += tot[k]; c += cnt[k]; }
+  if (ms_total) *ms_total = t;
+  if (intervals) *intervals = c;
   return MGCMT_OK;
 }
 const char *mgcmt_last_error(void) { return g_err.c_str(); }
@@ -737,6 +767,11 @@ int mgcmt_set_option(const char *name, int value) {
   if (!strcmp(name, "fused_min_cols")) { g_opt_fused_min_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tile_max_cols")) { g_opt_tile_max_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tail_max_cols")) { g_opt_tail_max_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "coarse_banded")) {
+    if (value < 0 || value > 2) return fail(MGCMT_ERR_ARG, "coarse_banded must be 0, 1 or 2 (auto)");
+    g_opt_coarse_banded = value;
+    return MGCMT_OK;
+  }
   if (!strcmp(name, "fused_uni")) { mgcmt::g_fused_uni = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_wfreg")) { mgcmt::g_uni_wfreg = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_minctas")) {

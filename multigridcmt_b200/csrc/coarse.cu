@@ -178,4 +178,202 @@ cudaError_t launch_gemv(int n, const double *inv, const double *x, double *y, cu
   return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Banded route to the same dense inverse, for coarsest levels of thousands of unknowns (lowest_level = 64 in 2-D:
+// 4096 unknowns, the "7 levels" of a 4096^2 grid).  The 9-point operator has half-bandwidth kl = ncols + 1, so LU with
+// partial pivoting touches kl rows x (kl + ku + kl) columns per pivot instead of n x 2n (the Gauss-Jordan above: ~20 000
+// launches and 2 TB of traffic at n = 4096).  Window storage as in the CPU oracle / LAPACK gbtrf: row i keeps columns
+// i - kl .. i + ku + kl; multipliers are not permuted retroactively, so the solves interleave interchanges and
+// eliminations.  Three launches: build the band, factor it (one CTA, the kl + 1 active rows live in shared memory and
+// slide down the matrix), then one thread per column of the identity runs the forward and backward substitution on the
+// n x n result in place (rows k .. k + kl of all columns are the working set: L2-resident).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ double level_entry(const LevelDev &L, double shift, int r, int c) {
+  const int i = r / L.ncols, j = r - i * L.ncols;
+  const int i2 = c / L.ncols, j2 = c - i2 * L.ncols;
+  const int di = i2 - i, dj = j2 - j;
+  if (di < -1 || di > 1 || dj < -1 || dj > 1) return 0.0;
+  const int gi = L.row0 + i;
+  const double ka = di < 0 ? L.ka_lo[gi] : (di == 0 ? L.ka_di[gi] : L.ka_up[gi]);
+  const double kb = dj < 0 ? L.kb_lo[j] : (dj == 0 ? L.kb_di[j] : L.kb_up[j]);
+  double val;
+  if (L.five) {
+    val = (di == 0 && dj == 0) ? ka + kb : (di == 0 ? kb : (dj == 0 ? ka : 0.0));
+  } else {
+    const double ma = di < 0 ? L.ma_lo[gi] : (di == 0 ? L.ma_di[gi] : L.ma_up[gi]);
+    const double mb = dj < 0 ? L.mb_lo[j] : (dj == 0 ? L.mb_di[j] : L.mb_up[j]);
+    val = ma * kb + ka * mb;
+  }
+  if (di == 0 && dj == 0) val -= shift;
+  return val;
+}
+
+// band[i * wp + (c - i + kl)] = (A - shift I)[i][c] for |c - i| <= ku, 0 in the fill columns
+__global__ void band_build_kernel(LevelDev L, double shift, int n, int kl, int ku, int wp, double *__restrict__ band) {
+  const long long total = (long long)n * wp;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / wp), w = (int)(idx - (long long)i * wp);
+    const int c = i - kl + w;
+    double v = 0.0;
+    if (c >= 0 && c < n && c - i <= ku && i - c <= kl) v = level_entry(L, shift, i, c);
+    band[idx] = v;
+  }
+}
+
+// One CTA.  Shared memory: R = kl + 1 row windows (circular: row i lives in slot i % R), each wp doubles.
+__global__ void __launch_bounds__(1024)
+band_factor_kernel(int n, int kl, int ku, int wp, double *__restrict__ band, int *__restrict__ piv, int *__restrict__ status) {
+  extern __shared__ double S[];
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_p;
+  const int R = kl + 1;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int idx = tid; idx < min(R, n) * wp; idx += nt) S[idx] = band[idx];
+  __syncthreads();
+  for (int k = 0; k < n; ++k) {
+    const int rhi = min(k + kl, n - 1), chi = min(k + ku + kl, n - 1);
+    const int nr = rhi - k + 1;
+    // 1. pivot: largest |A[r][k]|, r = k .. rhi (first wins ties, as in the oracle)
+    {
+      double best = -1.0;
+      int bi = k;
+      for (int t = tid; t < nr; t += nt) {
+        const double a = fabs(S[((k + t) % R) * wp + (kl - t)]);
+        if (a > best) { best = a; bi = k + t; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = bi; }
+      __syncthreads();
+      if (tid < 32) {
+        const int nw = (nt + 31) >> 5;
+        best = tid < nw ? s_val[tid] : -1.0;
+        bi = tid < nw ? s_idx[tid] : k;
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (tid == 0) {
+          s_p = bi;
+          piv[k] = bi;
+          if (!(best > 0.0)) *status = 1;  // singular (or NaN)
+        }
+      }
+      __syncthreads();
+    }
+    const int p = s_p;
+    double *rowk = S + (k % R) * wp;  // element (k, c) at rowk[c - k + kl]
+    // 2. interchange rows k and p in columns k .. chi
+    if (p != k) {
+      double *rowp = S + (p % R) * wp;
+      for (int c = k + tid; c <= chi; c += nt) {
+        const double a = rowk[c - k + kl], b = rowp[c - p + kl];
+        rowk[c - k + kl] = b;
+        rowp[c - p + kl] = a;
+      }
+      __syncthreads();
+    }
+    // 3. multipliers, 4. elimination: one warp per row r, lanes over the columns
+    const double pv = rowk[kl];
+    const double ipv = (pv != 0.0) ? 1.0 / pv : 0.0;
+    (void)ipv;
+    for (int r = k + 1 + (tid >> 5); r <= rhi; r += (nt >> 5)) {
+      double *rowr = S + (r % R) * wp;
+      const double m = (pv != 0.0) ? rowr[k - r + kl] / pv : 0.0;
+      __syncwarp();
+      if ((tid & 31) == 0) rowr[k - r + kl] = m;
+      if (m != 0.0)
+        for (int c = k + 1 + (tid & 31); c <= chi; c += 32) rowr[c - r + kl] -= m * rowk[c - k + kl];
+    }
+    __syncthreads();
+    // 5. row k is final: back to global; its slot takes row k + R
+    for (int w = tid; w < wp; w += nt) band[(size_t)k * wp + w] = rowk[w];
+    if (k + R < n)
+      for (int w = tid; w < wp; w += nt) rowk[w] = band[(size_t)(k + R) * wp + w];
+    __syncthreads();
+  }
+}
+
+// One thread per column j of the identity: X[:, j] = A^-1 e_j, X row-major n x n (X[k * n + j]).
+__global__ void band_inverse_solve_kernel(int n, int kl, int ku, int wp, const double *__restrict__ band,
+                                          const int *__restrict__ piv, double *__restrict__ X) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  for (int k = 0; k < n; ++k) X[(size_t)k * n + j] = (k == j) ? 1.0 : 0.0;
+  // forward: everything above row j - kl is still zero
+  for (int k = max(0, j - kl); k < n; ++k) {
+    const int p = piv[k];
+    double yk = X[(size_t)k * n + j];
+    if (p != k) {
+      const double yp = X[(size_t)p * n + j];
+      X[(size_t)p * n + j] = yk;
+      X[(size_t)k * n + j] = yp;
+      yk = yp;
+    }
+    if (yk != 0.0) {
+      const int rhi = min(k + kl, n - 1);
+      for (int r = k + 1; r <= rhi; ++r) X[(size_t)r * n + j] -= band[(size_t)r * wp + (k - r + kl)] * yk;
+    }
+  }
+  // backward
+  for (int k = n - 1; k >= 0; --k) {
+    const int chi = min(k + ku + kl, n - 1);
+    const double *u = band + (size_t)k * wp + kl;  // u[c - k] = U[k][c]
+    double t0 = X[(size_t)k * n + j], t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    int c = k + 1;
+    for (; c + 3 <= chi; c += 4) {
+      t0 -= u[c - k] * X[(size_t)c * n + j];
+      t1 -= u[c + 1 - k] * X[(size_t)(c + 1) * n + j];
+      t2 -= u[c + 2 - k] * X[(size_t)(c + 2) * n + j];
+      t3 -= u[c + 3 - k] * X[(size_t)(c + 3) * n + j];
+    }
+    for (; c <= chi; ++c) t0 -= u[c - k] * X[(size_t)c * n + j];
+    X[(size_t)k * n + j] = ((t0 + t1) + (t2 + t3)) / u[0];
+  }
+}
+
+}  // namespace
+
+size_t band_workspace_doubles(int n, int kl, int ku) { return (size_t)n * (2 * kl + ku + 1) + (size_t)(n + 1) / 2 + 2; }
+
+// inv (n x n, row-major) = (A_L - shift I)^-1 through the banded LU.  work: band_workspace_doubles(n, kl, ku) doubles.
+cudaError_t launch_band_inverse2d(const LevelDev &L, double shift, double *inv, int *status, double *work, cudaStream_t s) {
+  const int n = L.nrows * L.ncols;
+  const int kl = (L.nrows > 1) ? min(L.ncols + 1, n - 1) : min(1, n - 1), ku = kl;
+  const int wp = 2 * kl + ku + 1;
+  double *band = work;
+  int *piv = reinterpret_cast<int *>(work + (size_t)n * wp);
+  const long long total = (long long)n * wp;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  band_build_kernel<<<blocks, 256, 0, s>>>(L, shift, n, kl, ku, wp, band);
+  const size_t smem = sizeof(double) * (size_t)(kl + 1) * wp;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(band_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  band_factor_kernel<<<1, 1024, smem, s>>>(n, kl, ku, wp, band, piv, status);
+  band_inverse_solve_kernel<<<(n + 63) / 64, 64, 0, s>>>(n, kl, ku, wp, band, piv, inv);
+  count_launch(3);
+  return cudaGetLastError();
+}
+
+bool band_inverse_fits(const LevelDev &L) {
+  const int n = L.nrows * L.ncols;
+  if (n < 4) return false;
+  const int kl = (L.nrows > 1) ? min(L.ncols + 1, n - 1) : 1;
+  return sizeof(double) * (size_t)(kl + 1) * (3 * kl + 1) <= 200 * 1024;
+}
+
 }  // namespace mgcmt

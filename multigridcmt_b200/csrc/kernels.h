@@ -94,6 +94,10 @@ cudaError_t launch_build_dense(const LevelDev &L, double shift, double *aug, cud
 cudaError_t launch_gauss_jordan(int n, double *aug, int *status, double *mult, cudaStream_t s);
 cudaError_t launch_extract_inverse(int n, const double *aug, double *inv, cudaStream_t s);
 cudaError_t launch_gemv(int n, const double *inv, const double *x, double *y, cudaStream_t s);
+// the same inverse through a banded LU with partial pivoting (coarsest levels of thousands of unknowns)
+size_t band_workspace_doubles(int n, int kl, int ku);
+bool band_inverse_fits(const LevelDev &L);
+cudaError_t launch_band_inverse2d(const LevelDev &L, double shift, double *inv, int *status, double *work, cudaStream_t s);
 
 // reduce.cu
 constexpr int kReduceBlocks = 592;  // 148 SMs x 4

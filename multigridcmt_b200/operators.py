@@ -159,32 +159,71 @@ class SeparableOperator:
         return (self.nrows, self.ncols, self.dimension)
 
 
-_RECOGNISED = {}
+_RECOGNISED = {}   # id(A) -> (weakref to A, fingerprint, operator)
 
 
 def data_fingerprint(A):
-    """(address, checksum) of a scipy matrix's value array: the whole array up to 2 M entries, a strided sample of
-    ~4096 entries beyond that -- enough to notice in-place edits (a potential added to the diagonal, a rescaling)
-    without paying an O(nnz) pass per call on the 84 M-entry matrices."""
+    """Position-sensitive fingerprint of a scipy matrix: CRC-32 of its value / index / pointer arrays -- whole arrays up
+    to 64 K entries, 64 evenly spaced blocks of 1024 entries (plus the ends) beyond that, so that the check stays well
+    under a millisecond on the 84 M-entry matrices the drivers build at 4096^2.  An in-place edit that keeps sums
+    (a potential moved along the diagonal with `setdiag`) changes the CRC; one confined to entries no block samples can
+    slip through on very large matrices -- call `invalidate(A)` after editing a matrix in place."""
+    import zlib
+    crc = 0
+    for name in ("data", "indices", "indptr", "offsets"):
+        arr = getattr(A, name, None)
+        if not isinstance(arr, np.ndarray) or arr.size == 0:
+            continue
+        flat = np.ascontiguousarray(arr).reshape(-1)
+        if flat.size <= (1 << 16):
+            crc = zlib.crc32(flat.view(np.uint8), crc)
+        else:
+            step = flat.size // 64
+            for b in range(64):
+                crc = zlib.crc32(flat[b * step:b * step + 1024].view(np.uint8), crc)
+            crc = zlib.crc32(flat[-1024:].view(np.uint8), crc)
+        crc = zlib.crc32(np.int64(flat.size).tobytes(), crc)
     data = getattr(A, "data", None)
-    if not isinstance(data, np.ndarray) or data.size == 0:
-        return (None, 0.0)
-    flat = data.reshape(-1)
-    if flat.size > (1 << 21):
-        flat = flat[::flat.size // 4096]
-    return (data.ctypes.data, complex(flat.sum()))
+    addr = data.ctypes.data if isinstance(data, np.ndarray) else None
+    return (addr, crc)
+
+
+def _cache_lookup(cache, A, fp):
+    hit = cache.get(id(A))
+    if hit is not None and hit[0]() is A and hit[1] == fp:
+        return hit[2]
+    return None
+
+
+def _cache_store(cache, A, fp, op):
+    import weakref
+    key = id(A)
+    if len(cache) > 64:
+        cache.clear()
+    try:
+        ref = weakref.ref(A, lambda _r, k=key, c=cache: c.pop(k, None))   # a recycled id can never hit a dead entry
+    except TypeError:
+        return
+    cache[key] = (ref, fp, op)
+
+
+def invalidate(A=None):
+    """Forget the operator recognised for the scipy matrix A (or all of them): call after editing a matrix in place."""
+    from . import banded
+    for cache in (_RECOGNISED, banded._RECOGNISED):
+        if A is None:
+            cache.clear()
+        else:
+            cache.pop(id(A), None)
 
 
 def recognise(A, dimension):
     """from_sparse with a small identity cache (drivers pass the same matrix object every call)."""
     if isinstance(A, SeparableOperator):
         return A
-    fp = (id(A), A.shape, dimension, getattr(A, "nnz", None)) + data_fingerprint(A)
-    hit = _RECOGNISED.get(id(A))
-    if hit is not None and hit[0] == fp:
-        return hit[1]
-    op = SeparableOperator.from_sparse(A, dimension)
-    if len(_RECOGNISED) > 64:
-        _RECOGNISED.clear()
-    _RECOGNISED[id(A)] = (fp, op)
+    fp = (A.shape, dimension, getattr(A, "nnz", None)) + data_fingerprint(A)
+    op = _cache_lookup(_RECOGNISED, A, fp)
+    if op is None:
+        op = SeparableOperator.from_sparse(A, dimension)
+        _cache_store(_RECOGNISED, A, fp, op)
     return op

@@ -308,22 +308,45 @@ def test_all_vcycle_paths_agree(T, prod):
             assert rel(b, a) < (1e-10 if i == 0 else 1e-11)
 
 
+@pytest.mark.parametrize("banded", [0, 1])   # dense Gauss-Jordan / banded LU (auto picks banded above 256 unknowns)
 @pytest.mark.parametrize("dim,N,low,shift", [("2d", 32, 8, 1.76659015), ("2d", 32, 8, 7.00620149), ("2d", 16, 2, 0.0),
-                                             ("1d", 64, 16, 3.9), ("2d", 64, 32, 4.38639582)])
-def test_coarse_solve_matches_spsolve(T, prod, o, dim, N, low, shift):
-    from multigridcmt_b200.hierarchy import get_hierarchy
+                                             ("1d", 64, 16, 3.9), ("2d", 64, 32, 4.38639582), ("1d", 2048, 1024, 3.9),
+                                             ("2d", 128, 64, 4.38639582), ("2d", 128, 64, 1.76659015)])
+def test_coarse_solve_matches_spsolve(T, prod, o, dim, N, low, shift, banded):
+    """the exact coarsest solve (`spsolve`, MGCMTSolver.py:305-308) up to lowest_level = 64 in 2-D (4096 unknowns: the
+    7-level hierarchy of BASELINE config 3), through both factorisations"""
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import Hierarchy
     from multigridcmt_b200.operators import recognise
     import scipy.sparse.linalg as spla
     sm = prod[0]
     H = (-1. / np.pi ** 2) * sm.laplacian(N, dim)
-    h = get_hierarchy(recognise(H, dim), low)
+    nco = low * low if dim == "2d" else low
+    if banded == 0 and nco > 1024:
+        pytest.skip("dense Gauss-Jordan on %d unknowns: 5 launches per pivot, covered by the banded route" % nco)
+    if banded == 1 and nco < 4:
+        pytest.skip("no band to speak of")
+    _lib.check(_lib.load().mgcmt_set_option(b"coarse_banded", banded))
+    try:
+        h = Hierarchy(recognise(H, dim), low)   # a fresh one: the inverse is cached per hierarchy and shift
+        _test_coarse(T, o, h, H, N, dim, shift, spla)
+    finally:
+        _lib.load().mgcmt_set_option(b"coarse_banded", 2)
+
+
+def _test_coarse(T, o, h, H, N, dim, shift, spla):
     mats, _, _ = oracle_levels(o, H, N, dim, h.num_levels)
     n = h.level_size(h.num_levels - 1)
     A = sp.csc_matrix(mats[-1] - sp.eye(n) * shift)
     f = rand(n, 5)
     got = h.coarse_solve(shift, dev(T, f), T.empty(n, dtype=T.float64, device="cuda")).cpu().numpy()
     want = spla.spsolve(A, f)
-    cond = np.linalg.cond(A.toarray())
+    if n <= 1024:
+        cond = np.linalg.cond(A.toarray())
+    else:   # 1-norm estimate (an SVD of a 4096^2 matrix would take a minute)
+        lu = spla.splu(A)
+        inv_op = spla.LinearOperator((n, n), matvec=lu.solve, rmatvec=lambda x: lu.solve(x, "T"))
+        cond = spla.onenormest(A) * spla.onenormest(inv_op)
     assert rel(got, want) < 50 * cond * np.finfo(float).eps, (rel(got, want), cond)
 
 

@@ -364,3 +364,26 @@ def test_plan_levels_invariants():
         l = nlev
         assert not ((n >> l) > gather and (own >> l) >= 64 and own % (1 << (l + 1)) == 0)
     check()
+
+
+def test_recognise_cache_notices_in_place_edits():
+    """an in-place edit that keeps the sum of the values (a well moved along the diagonal) must not return
+    the stale operator; a dead matrix's recycled id must not hit either."""
+    import scipy.sparse as sp
+    from multigridcmt_b200.operators import recognise, invalidate, _RECOGNISED
+    n = 64
+    V = np.zeros(n); V[10:20] = 5.0
+    A = sp.diags([np.ones(n - 1), -2.0 * np.ones(n) + V, np.ones(n - 1)], [-1, 0, 1], format="csc")
+    op1 = recognise(A, "1d")
+    assert recognise(A, "1d") is op1
+    A.setdiag(-2.0 * np.ones(n) + np.roll(V, 7))     # same sum, same nnz, same buffers
+    op2 = recognise(A, "1d")
+    assert op2 is not op1
+    assert np.allclose(op2.diagonal().reshape(-1), A.diagonal())
+    invalidate(A)
+    assert id(A) not in _RECOGNISED
+    op3 = recognise(A, "1d")
+    key = id(A)
+    del A
+    import gc; gc.collect()
+    assert key not in _RECOGNISED and op3 is not None
