@@ -558,6 +558,32 @@ static int build_hier(mgcmt_hier_t **out, int nrows_glob, int ncols, int coarsen
     }
   }
   CUB(cudaStreamSynchronize(s));
+  // Galerkin levels of a constant-coefficient operator: all four tridiagonal factors constant but for their last
+  // diagonal entry (the truncated last row of R)?  Then their legs run in fused_uni9.cu.
+  for (int l = 1; l < nlev && coarsen_rows; ++l) {
+    Level &L = h->lev[l];
+    const int nrl = L.dev.nrows_glob, ncl = L.dev.ncols;
+    if (nrl < 8 || ncl < 8) continue;
+    std::vector<double> hc(6 * (size_t)nrl + 6 * (size_t)ncl);
+    CUB(cudaMemcpy(hc.data(), L.coef, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
+    auto tri_uniform = [](const double *lo, const double *di, const double *up, int n, double *off, double *d0, double *dlast) {
+      const double o = up[0];
+      for (int i = 0; i < n; ++i) {
+        if (i > 0 && lo[i] != o) return false;
+        if (i + 1 < n && up[i] != o) return false;
+        if (i + 1 < n && di[i] != di[0]) return false;
+      }
+      *off = o; *d0 = di[0]; *dlast = di[n - 1];
+      return true;
+    };
+    const double *r = hc.data(), *c = hc.data() + 6 * (size_t)nrl;
+    double *u = L.dev.u9;
+    const bool ok = tri_uniform(r, r + nrl, r + 2 * nrl, nrl, &u[0], &u[1], &u[4]) &&
+                    tri_uniform(r + 3 * nrl, r + 4 * nrl, r + 5 * nrl, nrl, &u[2], &u[3], &u[5]) &&
+                    tri_uniform(c, c + ncl, c + 2 * ncl, ncl, &u[6], &u[7], &u[10]) &&
+                    tri_uniform(c + 3 * ncl, c + 4 * ncl, c + 5 * ncl, ncl, &u[8], &u[9], &u[11]);
+    if (ok) L.dev.uni = 2;
+  }
 #undef CUB
   *out = h;
   return MGCMT_OK;
@@ -773,6 +799,13 @@ int mgcmt_set_option(const char *name, int value) {
     return MGCMT_OK;
   }
   if (!strcmp(name, "fused_uni")) { mgcmt::g_fused_uni = value ? 1 : 0; return MGCMT_OK; }
+  if (!strcmp(name, "leg_min_rpc")) {
+    if (value < 2 || (value & 1)) return fail(MGCMT_ERR_ARG, "leg_min_rpc must be even and >= 2");
+    mgcmt::g_leg_min_rpc = value;
+    return MGCMT_OK;
+  }
+  if (!strcmp(name, "fused_skew_cols")) { mgcmt::g_fused_skew_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "fused_uni9")) { mgcmt::g_fused_uni9 = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_wfreg")) { mgcmt::g_uni_wfreg = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_minctas")) {
     if (value != 0 && value != 2 && value != 3) return fail(MGCMT_ERR_ARG, "uni_minctas must be 0 (default), 2 or 3");

@@ -17,7 +17,9 @@ struct LevelDev {
   int nrows_coarse;  // decomposed); rows of the coarse array the transfers address (0 => nrows / 2)
   int rq_lo, rq_hi;  // local rows [rq_lo, rq_hi) whose w^T A w, w^T w the fused Rayleigh stage sums (slab piece: the owned rows)
   int uni;           // 1: constant 5-point stencil (all off-diagonals == uni_c, ka_di + kb_di == uni_d on every point): fused_uni.cu
+                     // 2: 9-point level whose four tridiagonal factors are constant but for their last diagonal entry: fused_uni9.cu
   double uni_c, uni_d;
+  double u9[12];     // uni == 2: ka_off, ka_di, ma_off, ma_di, ka_di_last, ma_di_last, then the same of kb / mb
   const double *ka_lo, *ka_di, *ka_up, *ma_lo, *ma_di, *ma_up;  // length nrows_glob
   const double *kb_lo, *kb_di, *kb_up, *mb_lo, *mb_di, *mb_up;  // length ncols
 };

@@ -43,13 +43,11 @@ constexpr int kVRing = MGCMT_VRING;  // prefetch depth of the v ring (rows, powe
 // all stages of a step are independent of each other; the price is NSTAGE-1 extra rows of pipeline fill per chunk and
 // a deeper f queue.  Measured on B200 (4096^2): no gain (down leg 132 vs 131 us) -- the stage-to-stage chain is not
 // what limits the kernel -- so the default stays 1; the variant is kept for the next profiling round.
-#ifndef MGCMT_SKEW
-#define MGCMT_SKEW 1
-#endif
-constexpr int kSkew = MGCMT_SKEW;
-// f ring depth = prefetch depth + kSkew * NSTAGE + 2 rows of queue (per instantiation; not a power of two: slots
+// It is a template parameter (SKEW): 1 for the bandwidth-bound legs, 2 for the legs of small levels, which are bound by
+// the length of that serial chain (a 512^2 Gauss-Seidel leg: 8 stages x ~150 cycles per step, 20 us per launch).
+// f ring depth = prefetch depth + SKEW * NSTAGE + 2 rows of queue (per instantiation; not a power of two: slots
 // are tracked incrementally)
-__host__ __device__ constexpr int f_ring_slots(int nstage) { return kVRing + kSkew * nstage + 2; }
+__host__ __device__ constexpr int f_ring_slots(int nstage, int skew) { return kVRing + skew * nstage + 2; }
 constexpr int kERing = 4;    // coarse-row ring (PROLONG)
 constexpr int kWarps = 4;    // warps per CTA (independent strips)
 
@@ -87,7 +85,7 @@ struct Stage {
 // oracle Solver.rbgs).  A colour stage is a Jacobi stage that only writes the points of its colour and passes the others
 // through; which points those are is known at compile time (row parity from the unrolled step, column parity from the
 // lane's even first column), so the skipped half / three quarters of the arithmetic is simply not generated.
-template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS>
+template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS, int SKEW>
 __global__ void __launch_bounds__(kWarps * 32, (C == 4 ? MGCMT_MIN_CTAS : 1))
 fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v_in,
                  const double *__restrict__ f, double *__restrict__ v_out,
@@ -96,7 +94,8 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
   constexpr int WCOLS = 32 * C;
   constexpr int USEFUL = WCOLS - 2 * HALO;
   constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);  // pipeline stages after the input
-  constexpr int kFRing = f_ring_slots(NSTAGE);
+  constexpr int kSkew = SKEW;
+  constexpr int kFRing = f_ring_slots(NSTAGE, SKEW);
   constexpr int NCOL = FIVE ? 2 : 4;               // colours of the Gauss-Seidel ordering
   constexpr int CE = C / 2;                        // coarse columns per thread
   static_assert(C == 2 || C == 4, "C must be 2 or 4");
@@ -488,10 +487,10 @@ fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restric
 
 // ---------------------------------------------------------------------------------------------------
 template <int C>
-static size_t fused_smem_bytes(bool prolong, int rows_per_chunk, int nstage) {
-  size_t b = sizeof(double) * (size_t)(kVRing + f_ring_slots(nstage)) * kWarps * 32 * C;
+static size_t fused_smem_bytes(bool prolong, int rows_per_chunk, int nstage, int skew) {
+  size_t b = sizeof(double) * (size_t)(kVRing + f_ring_slots(nstage, skew)) * kWarps * 32 * C;
   if (prolong) b += sizeof(double) * (size_t)kERing * kWarps * 32 * (C / 2);
-  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 3 * kSkew * nstage + 16);  // rows t_begin-kSkew*NSTAGE-1 .. t_last+2
+  b += sizeof(RowCoef) * (size_t)(rows_per_chunk + 3 * skew * nstage + 16);  // rows t_begin-skew*NSTAGE-1 .. t_last+2
   return b;
 }
 
@@ -506,31 +505,45 @@ static void fused_geometry(const LevelDev &L, int ctas_per_sm, int nstage, int *
   *rpc_out = leg_rows_per_chunk(L.nrows, *gx, ctas_per_sm * num_sms(), nstage, 128);
 }
 
-template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS>
-static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega, const double *v_in,
+int g_fused_skew_cols = 0;     // 9-point levels at most this wide run the skew-2 pipeline (0 = never, the default: measured 6-17 % slower per RB-GS cycle on B200)
+
+template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS, int SKEW>
+static cudaError_t launch_fused_s(const LevelDev &L, double shift, double omega, const double *v_in,
                                   const double *f, double *v_out, const double *e_coarse, double *r_coarse,
-                                  cudaStream_t s, int *slots_out = nullptr) {
-  auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C, GS>;
+                                  cudaStream_t s, int *slots_out) {
+  auto kern = fused_leg_kernel<FIVE, NU, PROLONG, RESTRICT, ZEROV, C, GS, SKEW>;
   constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);
   static int occ = 0;  // per instantiation: resident CTAs per SM with a 128-row chunk's shared memory
   if (!occ) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, fused_smem_bytes<C>(PROLONG, 128, NSTAGE));
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarps * 32, fused_smem_bytes<C>(PROLONG, 128, NSTAGE, SKEW));
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
   }
   int gx, rpc;
-  fused_geometry<NU, C>(L, occ, NSTAGE, &gx, &rpc);
+  fused_geometry<NU, C>(L, occ, SKEW * NSTAGE, &gx, &rpc);
   if (slots_out) {
     *slots_out = gx * ((L.nrows + rpc - 1) / rpc) * kWarps;
     return cudaSuccess;
   }
-  const size_t smem = fused_smem_bytes<C>(PROLONG, rpc, NSTAGE);
+  const size_t smem = fused_smem_bytes<C>(PROLONG, rpc, NSTAGE, SKEW);
   dim3 grid(gx, (L.nrows + rpc - 1) / rpc);
   kern<<<grid, kWarps * 32, smem, s>>>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, rpc);
   count_launch();
   return cudaGetLastError();
+}
+
+template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS>
+static cudaError_t launch_fused_t(const LevelDev &L, double shift, double omega, const double *v_in,
+                                  const double *f, double *v_out, const double *e_coarse, double *r_coarse,
+                                  cudaStream_t s, int *slots_out = nullptr) {
+  // skew 2 (all stages of a step independent) for the 9-point legs of small levels with a real pipeline (>= 3 stages)
+  if constexpr (!FIVE && C == 2 && (NU + (RESTRICT ? 1 : 0)) >= 3) {
+    if (L.ncols <= g_fused_skew_cols)
+      return launch_fused_s<FIVE, NU, PROLONG, RESTRICT, ZEROV, C, GS, 2>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out);
+  }
+  return launch_fused_s<FIVE, NU, PROLONG, RESTRICT, ZEROV, C, GS, 1>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out);
 }
 
 template <bool FIVE, int NU, int C, int GS = 0>
@@ -562,6 +575,8 @@ cudaError_t launch_fused_gs_leg(const LevelDev &L, int mode, int sweeps, double 
                                 double *r_coarse, cudaStream_t s) {
   if (L.nrows < 2) return cudaErrorInvalidValue;
   if (uni5_available(L)) return launch_uni5_leg(L, 1, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  if (uni9_available(L) && mode != FUSED_UP_RQ && sweeps <= 2)
+    return launch_uni9_leg(L, 1, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
   if (sweeps == 0) {  // no smoothing (nu1 = 0 or nu2 = 0): the colour order does not matter, the Jacobi leg's transfer is the same
     return L.five ? dispatch_mode<true, 0, 2>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s)
                   : dispatch_mode<false, 0, 2>(L, mode, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
@@ -603,6 +618,8 @@ cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, 
                              double *r_coarse, cudaStream_t s) {
   if (L.nrows < 2) return cudaErrorInvalidValue;  // 2-D levels only
   if (uni5_available(L)) return launch_uni5_leg(L, 0, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  if (uni9_available(L) && mode != FUSED_UP_RQ)
+    return launch_uni9_leg(L, 0, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
 #define NU_CASE(NUV)                                                                                         \
   case NUV:                                                                                                  \
     if (L.five && g_fused_c5 == 4)                                                                           \

@@ -52,7 +52,7 @@ enum { FUSED_SMOOTH = 0,     // v_out = J^nu(v_in)
 #ifndef MGCMT_FUSED_C9
 #define MGCMT_FUSED_C9 2     // columns per lane, 9-point (Galerkin) levels
 #endif
-extern int g_fused_c5, g_fused_c9;
+extern int g_fused_c5, g_fused_c9, g_fused_skew_cols;
 int fused_rq_slots(const LevelDev &L, int gs = 0);
 // fused_uni.cu: the same legs for constant-coefficient 5-point levels (LevelDev::uni), half the fp64 instructions
 extern int g_fused_uni, g_uni_minctas, g_uni_wfreg;
@@ -61,9 +61,15 @@ cudaError_t launch_uni5_leg(const LevelDev &L, int gs, int mode, int nu, double 
                             const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s,
                             int *slots_out = nullptr);
 int uni5_rq_slots(const LevelDev &L, int gs);
+// fused_uni9.cu: the same for the Galerkin (9-point) levels with constant interior coefficients (LevelDev::uni == 2)
+extern int g_fused_uni9;
+bool uni9_available(const LevelDev &L);
+cudaError_t launch_uni9_leg(const LevelDev &L, int gs, int mode, int nu, double shift, double omega, const double *v_in,
+                            const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s);
 // chunk height of a streaming leg so that gx * chunks CTAs fill whole waves of `slots` resident CTAs
 int leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc);
 int num_sms();
+extern int g_leg_min_rpc;
 cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, double omega,
                              const double *v_in, const double *f, double *v_out, const double *e_coarse,
                              double *r_coarse, cudaStream_t s);

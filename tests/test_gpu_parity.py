@@ -150,9 +150,10 @@ def test_level_operators_match_oracle(T, prod, o, dim, N, shift):
 # fused legs (nu sweeps + transfer in one pass) against the single-operator kernels and the oracle
 # ---------------------------------------------------------------------------------------------------
 UNI_VARIANTS = {"general": dict(fused_uni=0), "uni": dict(fused_uni=1, uni_wfreg=1, uni_minctas=0),
+                "uni9": dict(fused_uni=1, fused_uni9=1),   # optional constant-coefficient 9-point legs (off by default)
                 "uni_wfreg3": dict(fused_uni=1, uni_wfreg=1, uni_minctas=3), "uni_smem2": dict(fused_uni=1, uni_wfreg=0, uni_minctas=2),
                 "uni_smem3": dict(fused_uni=1, uni_wfreg=0, uni_minctas=3)}
-UNI_DEFAULT = dict(fused_uni=1, uni_wfreg=1, uni_minctas=0)
+UNI_DEFAULT = dict(fused_uni=1, uni_wfreg=1, uni_minctas=0, fused_uni9=0)
 
 
 @pytest.fixture
@@ -215,7 +216,7 @@ def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift, impl, uni_var
             assert rel(out.cpu().numpy(), want_u) < RTOL, ("up", l, nu)
 
 
-@pytest.mark.parametrize("uni_variant", ["general", "uni"], indirect=True)
+@pytest.mark.parametrize("uni_variant", ["general", "uni", "uni9"], indirect=True)
 @pytest.mark.parametrize("N,shift", [(128, 4.38639582), (512, 0.0)])
 def test_fused_gauss_seidel_legs_match_colour_kernels(T, prod, o, N, shift, uni_variant):
     """colour-stage legs (mode | 32) == the one-kernel-per-colour smoother + the un-fused transfers, and the CPU twin"""
@@ -287,7 +288,8 @@ def test_all_vcycle_paths_agree(T, prod):
     H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
     v0 = rand(N * N, 1); f = rand(N * N, 2)
     configs = [dict(fused=0), dict(fused=1, tile_max_cols=0, tail_max_cols=0), dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_uni=0),
-               dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_uni=1, fused_c9=4),
+               dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_uni=1, fused_c9=4), dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_uni9=1),
+               dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_uni9=0, fused_skew_cols=2048),
                dict(fused=1, tile_max_cols=0, tail_max_cols=0, fused_c9=2, fused_c5=2), dict(fused=1, tile_max_cols=1024, tail_max_cols=0, fused_c5=4),
                dict(fused=1, tile_max_cols=1024, tail_max_cols=64), dict(fused=1, tile_max_cols=0, tail_max_cols=32)]
     try:
@@ -300,7 +302,7 @@ def test_all_vcycle_paths_agree(T, prod):
                          s.vcycle(np.zeros(64 * 64), f[:4096].copy(), (-1. / np.pi ** 2) * sm.laplacian(64, "2d"), sm,
                                   shift=1.7, lowest_level=4, dimension="2d")))
     finally:
-        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=32, fused_c9=0, fused_c5=4, fused_uni=1).items():
+        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=32, fused_c9=0, fused_c5=4, fused_uni=1, fused_uni9=0, fused_skew_cols=0).items():
             lib.mgcmt_set_option(k.encode(), v)
     # all paths share the operator-by-operator arithmetic up to the association of sums; the cycles contain the exact
     # solve of an indefinite coarsest operator (shift 4.386), which amplifies those last-bit differences: 1e-10 (see the

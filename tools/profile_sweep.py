@@ -16,7 +16,8 @@ for kv in sys.argv[3:]:   # option=value pairs for mgcmt_set_option
     _lib.check(_lib.load().mgcmt_set_option(k.encode(), int(v)))
 sm = MGCMTStencilMaker()
 H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
-h = get_hierarchy(H, 8)
+LOW = int(os.environ.get("LOWEST", "8"))
+h = get_hierarchy(H, LOW)
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 v = torch.rand(N * N, dtype=torch.float64, device="cuda", generator=g)
 f = torch.rand(N * N, dtype=torch.float64, device="cuda", generator=g)
@@ -35,6 +36,10 @@ for it in range(2):
             h.fused_leg(0, 1, 4, 1.7, 2.0 / 3.0, v, f, out, None, rc)
         elif what == "up":
             h.fused_leg(0, 3, 4, 1.7, 2.0 / 3.0, v, f, out, rc, None)
+        elif what == "vcycle_gs":
+            h.vcycle(1.7, 4, 4, _lib.SMOOTH_RBGS, 1.0, out, f, v0_is_zero=True)
+        elif what == "vcycle_wj":
+            h.vcycle(1.7, 4, 4, _lib.SMOOTH_WJACOBI, 2.0 / 3.0, out, f, v0_is_zero=True)
         elif what == "down0":
             h.fused_leg(0, 2, 4, 1.7, 2.0 / 3.0, None, f, out, None, rc)
         elif what == "gsdown":
