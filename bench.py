@@ -64,7 +64,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--replicas", action="store_true", help="multi-GPU: independent replicas instead of row slabs")
     ap.add_argument("--gather-cols", type=int, default=512, help="slab path: levels at most this wide are replicated")
-    ap.add_argument("--slab-stagger", type=int, default=0,
+    ap.add_argument("--slab-stagger", type=int, default=1,
                     help="native slab driver: run the block as two halves half a phase apart (exchange of one overlaps kernels of the other)")
     ap.add_argument("--slab-driver", choices=["native", "python"], default="native",
                     help="slab path: step issued from C++ with NCCL called directly (csrc/slab_block.cu), or from Python over torch.distributed")
@@ -814,14 +814,15 @@ def run_slab(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "2D infinite well %d^2 slab-decomposed over %d GPUs (rows), lowest 4 eigenpairs, shift method: "
-                                   "4 x V(4,4) + Rayleigh quotient + MGS per step" % (N, world),
-                       "smoother": "wjacobi", "lowest_level": lowest, "slab_levels": nlev_slab, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
-                       "driver": (("native: step issued from C++, NCCL called directly (csrc/slab_block.cu)"
-                                   + ("; two halves half a phase apart on two communicators" if args.slab_stagger else "; lock-step")) if native
-                                  else "python: torch.distributed"),
-                       "replicated_from": "%d^2" % (N >> nlev_slab), "parallelism": "row slabs x%d, NCCL send/recv halos + all-gather" % world,
-                       "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9)},
+            "config": dict(workload_config(N, "wjacobi", lowest, k), l2="per-rank working set >> 126 MB L2"),
+            "impl_detail": {"parallelism": "row slabs x%d, NCCL send/recv halos per fused leg + all-gather of the first replicated level" % world,
+                            "slab_levels": nlev_slab, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
+                            "driver": (("native: step issued from C++, NCCL called directly (csrc/slab_block.cu)"
+                                        + ("; two halves half a phase apart on two communicators (one half's exchange overlaps the other's kernels)"
+                                           if args.slab_stagger else "; lock-step")) if native else "python: torch.distributed"),
+                            "replicated_from": "%d^2" % (N >> nlev_slab),
+                            "l2": "per-rank working set %.1f GB >> 126 MB L2" % (12 * (own + 2 * HALO) * N * 8 / 1e9),
+                            "strong_scaling_base": "the --gpus 1 line carries the 1-GPU time of this workload as scaling_base"},
             "vcycles_per_s": k * args.steps / (ms * 1e-3), "host_issue_ms_per_step": host_issue_ms,
             "eigenvalues": lam_h, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam_h, exact)],
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,

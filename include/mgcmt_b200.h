@@ -219,6 +219,15 @@ int mgcmt_axpy_dev(long long n, const double *d_alpha, double sign, const double
  * ||H v - rho v|| of ShiftMethod.solve and the right-hand side of its correction form. */
 int mgcmt_eigen_residual(mgcmt_hier_t *h, int level, const double *d_x, const double *d_rq2, double *d_r,
                          double *d_out_sumsq, void *stream);
+/* `nu` steps of the Rayleigh-quotient minimisation `rqmin(A, v0, M, nu)` (MGCMTSolver.py:17-57) for the level operator
+ * A_level and the level mass matrix M_level = Ma (x) Mb (the identity on the finest level; use_mass = 0 treats it as the
+ * identity without reading it), entirely on the device: d_x is updated in place, d_rq2[0] = x^T A x, d_rq2[1] = x^T M x
+ * of the result (rho = their ratio).  d_work: 7 vectors of the level's size (4 when use_mass = 0) + 32 + 8 * 592 doubles.
+ * No host synchronisation; the 2 x 2 generalised eigenproblem of every step (scipy.linalg.eig in the reference, :48) is
+ * solved in closed form on the device. */
+int mgcmt_rqmin(mgcmt_hier_t *h, int level, int use_mass, double *d_x, int nu, double *d_work, long long work_doubles,
+                double *d_rq2, void *stream);
+long long mgcmt_rqmin_work_doubles(mgcmt_hier_t *h, int level, int use_mass);
 /* out = a*x + b*y with host scalars (the vector updates of rqmin, MGCMTSolver.py:34-36,51,54) */
 int mgcmt_axpby(long long n, double a, const double *d_x, double b, const double *d_y, double *d_out,
                 void *stream);

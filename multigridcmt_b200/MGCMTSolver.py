@@ -306,7 +306,7 @@ class MGCMTSolver:
             return None
         g = int(round(grid_dimension))
         low = int(lowest_level)
-        if g & (g - 1) or low & (low - 1) or low > g or low < 2:
+        if (dimension == "2d" and g * g != n) or g & (g - 1) or low & (low - 1) or low > g or low < 2:
             print("Length of start vector is not a power of 2")
             return None
         op = recognise(A, dimension)
@@ -383,57 +383,29 @@ class MGCMTSolver:
         return get_hierarchy(op, lowest)
 
     def _rqmin_level(self, h, level, x, nu):
-        """rqmin (MGCMTSolver.py:17-57) for the level operators A_l, M_l of hierarchy h; x: device vector."""
+        """rqmin (MGCMTSolver.py:17-57) for the level operators A_l, M_l of hierarchy h; x: device vector (updated in
+        place).  One C call (mgcmt_rqmin): the whole iteration -- mat-vecs, the 8 pencil sums in one pass, the 2 x 2
+        generalised eigenproblem, updates -- stays on the device; rho comes back as a device pair (x^T A x, x^T M x)."""
         torch = _lib.require_cuda()
-        from scipy.linalg import eig
         lib = _lib.load()
-        n = x.numel()
-        stream = _stream_ptr(torch)
-        scal = torch.zeros(16, dtype=torch.float64, device="cuda")
+        use_mass = 1 if level > 0 else 0          # M_0 = I (checked by _rq_hierarchy); coarser levels: M_l = R M P
+        need = int(lib.mgcmt_rqmin_work_doubles(h.handle, level, use_mass))
+        cache = self.__dict__.setdefault("_rq_work", {})
+        key = (id(h), level)
+        work = cache.get(key)
+        if work is None or work.numel() < need:
+            if len(cache) > 32:
+                cache.clear()
+            work = torch.empty(need + 2, dtype=torch.float64, device="cuda")
+            cache[key] = work
+        rq2 = torch.empty(2, dtype=torch.float64, device="cuda")
+        _lib.check(lib.mgcmt_rqmin(h.handle, level, use_mass, _ptr(x), int(nu), _ptr(work), work.numel(), _ptr(rq2), _stream_ptr(torch)))
+        return x, rq2
 
-        def A_(v):
-            return h.apply(level, 0.0, v, torch.empty_like(v))
-
-        def M_(v):
-            return h.apply_mass(level, v, torch.empty_like(v))
-
-        def dots(pairs):
-            for i, (a, b) in enumerate(pairs):
-                _lib.check(lib.mgcmt_dot(n, _ptr(a), _ptr(b), _ptr(scal[i:i + 1]), stream))
-            return scal[:len(pairs)].cpu().tolist()
-
-        def axpby(a, u, b, v):
-            out = torch.empty_like(u)
-            _lib.check(lib.mgcmt_axpby(n, float(a), _ptr(u), float(b), _ptr(v), _ptr(out), stream))
-            return out
-
-        Ax, Mx = A_(x), M_(x)
-        xax, xmx = dots([(x, Ax), (x, Mx)])
-        rho = xax / xmx
-        g = axpby(2.0, Ax, -2.0 * rho, Mx)
-        gold = x
-        p = x
-        for it in range(nu):
-            if it == 0:
-                p = axpby(-1.0, g, 0.0, g)
-            else:
-                gmg, omo = dots([(g, M_(g)), (gold, M_(gold))])
-                p = axpby(-1.0, g, gmg / omo, p)
-            Ap, Mp = A_(p), M_(p)
-            d = dots([(x, Ax), (x, Ap), (p, Ax), (p, Ap), (x, Mx), (x, Mp), (p, Mx), (p, Mp)])
-            R = np.array([[d[0], d[1]], [d[2], d[3]]])
-            RM = np.array([[d[4], d[5]], [d[6], d[7]]])
-            w, vecs = eig(R, b=RM)
-            rx = np.array(vecs[:, np.argmin(w)])
-            delta = rx[1] / rx[0]
-            delta = float(np.real(delta))
-            x = axpby(1.0, x, delta, p)
-            Ax, Mx = A_(x), M_(x)
-            xax, xmx = dots([(x, Ax), (x, Mx)])
-            rho = xax / xmx
-            gold = g
-            g = axpby(2.0, Ax, -2.0 * rho, Mx)
-        return x, rho
+    @staticmethod
+    def _rho(rq2):
+        r = rq2.cpu().tolist()
+        return r[0] / r[1]
 
     def rqmin(self, A, v0, M=None, nu=4):
         # MGCMTSolver.py:17-57 (M=None is unusable in the reference, quirk Q9; here it means the identity)
@@ -448,7 +420,8 @@ class MGCMTSolver:
             h = self._rq_hierarchy(op, M, n, self._any_lowest(op), "2d")
         else:
             h = self._rq_hierarchy(A, M, n, min(n, 4096))
-        x, rho = self._rqmin_level(h, 0, x, nu)
+        x, rq2 = self._rqmin_level(h, 0, x, nu)
+        rho = self._rho(rq2)
         if shape is None:
             return x, rho
         return to_host(x).reshape(shape), rho
@@ -484,17 +457,18 @@ class MGCMTSolver:
                 low //= 2
             h = self._rq_hierarchy(A, M, n, low, "2d")
             k, rho = self._rqmg_level(h, 0, k, nu1, nu2, max(int(nmin), low * low))
+            rho = self._rho(rho)
             if shape is None:
                 return k, rho
             return to_host(k).reshape(shape), rho
         if n < 2 or n & (n - 1):
             print("New gridsize isn't a power of 2 !")
             return None
-        low = max(2, int(nmin))
-        while low & (low - 1):
-            low += 1
+        # the reference recurses while n > nmin (MGCMTSolver.py:105): the coarsest size is the largest power of two <= nmin
+        low = 1 << (max(2, int(nmin)).bit_length() - 1)
         h = self._rq_hierarchy(A, M, n, min(low, n))
         k, rho = self._rqmg_level(h, 0, k, nu1, nu2, nmin)
+        rho = self._rho(rho)
         if shape is None:
             return k, rho
         return to_host(k).reshape(shape), rho
@@ -505,7 +479,7 @@ class MGCMTSolver:
         dev_in = is_device_tensor(x_matrix)
         xm = x_matrix if dev_in else np.asarray(x_matrix, dtype=np.float64)
         n, nv = xm.shape
-        low = max(2, int(nmin))
+        low = 1 << (max(2, int(nmin)).bit_length() - 1)   # largest power of two <= nmin, as in vcycle_rqmg
         h = self._rq_hierarchy(A, M, n, min(low, n))
         K = (xm.t().contiguous().clone() if dev_in
              else torch.from_numpy(np.ascontiguousarray(xm.T)).cuda())

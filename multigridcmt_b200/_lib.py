@@ -68,6 +68,8 @@ SIGNATURES = {
     "mgcmt_axpy_dev": (_I, [_LL, _P, _D, _P, _P, _P]),
     "mgcmt_eigen_residual": (_I, [_P, _I, _P, _P, _P, _P, _P]),
     "mgcmt_ortho_status": (_I, [C.POINTER(_I), _P]),
+    "mgcmt_rqmin": (_I, [_P, _I, _I, _P, _I, _P, _LL, _P, _P]),
+    "mgcmt_rqmin_work_doubles": (_LL, [_P, _I, _I]),
     "mgcmt_gramschmidt": (_I, [_LL, _I, _P, _I, _P]),
     "mgcmt_band_create": (_I, [_I, _I, _P, _P, _I, _P, C.POINTER(_P)]),
     "mgcmt_band_destroy": (_I, [_P]),

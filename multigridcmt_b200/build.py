@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmgcmt_b200.so")
-SOURCES = ["stencil.cu", "fused.cu", "fused_uni.cu", "fused_uni9.cu", "tile.cu", "transfer.cu", "gs.cu", "coarse.cu", "reduce.cu", "band.cu", "api.cu", "band_api.cu", "slab_block.cu"]
+SOURCES = ["stencil.cu", "fused.cu", "fused_uni.cu", "fused_uni9.cu", "tile.cu", "transfer.cu", "gs.cu", "coarse.cu", "reduce.cu", "rq.cu", "band.cu", "api.cu", "band_api.cu", "slab_block.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

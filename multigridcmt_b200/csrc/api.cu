@@ -1029,6 +1029,50 @@ int mgcmt_cholqr_apply(long long n, int k, double *d_V, long long stride, const 
   return MGCMT_OK;
 }
 
+long long mgcmt_rqmin_work_doubles(mgcmt_hier_t *h, int level, int use_mass) {
+  if (check_level(h, level)) return -1;
+  return (long long)(use_mass ? 7 : 4) * (long long)h->lev[level].n + 32 + 8 * kReduceBlocks;
+}
+
+int mgcmt_rqmin(mgcmt_hier_t *h, int level, int use_mass, double *d_x, int nu, double *d_work, long long work_doubles,
+                double *d_rq2, void *stream) {
+  int rc = check_level(h, level);
+  if (rc) return rc;
+  if (h->slab) return fail(MGCMT_ERR_STATE, "not available on slab pieces");
+  if (!d_work || !d_rq2 || nu < 0) return fail(MGCMT_ERR_ARG, "bad rqmin arguments");
+  if (work_doubles < mgcmt_rqmin_work_doubles(h, level, use_mass)) return fail(MGCMT_ERR_ARG, "rqmin work array too small");
+  NEED_ALIGNED(d_x, d_work);
+  Level &L = h->lev[level];
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = (long long)L.n;
+  const bool mass = use_mass != 0;
+  // carve the work array (vector sizes rounded up to keep 16-byte alignment)
+  const long long nn = (n + 1) & ~1LL;
+  double *Ax = d_work, *g = Ax + nn, *p = g + nn, *Ap = p + nn;
+  double *Mx = mass ? Ap + nn : d_x, *Mp = mass ? Mx + nn : p, *Mg = mass ? Mp + nn : g;
+  double *scal = d_work + (mass ? 7 : 4) * nn;
+  double *partials = scal + 32;
+  if ((mass ? 7 : 4) * nn + 32 + 8 * kReduceBlocks > work_doubles + 8) return fail(MGCMT_ERR_ARG, "rqmin work array too small");
+  auto apply_mass = [&](const double *x, double *y) -> int { return mgcmt_apply_mass(h, level, x, y, stream); };
+  CU(launch_apply(L.dev, 0.0, d_x, Ax, nullptr, nullptr, s));
+  if (mass) { rc = apply_mass(d_x, Mx); if (rc) return rc; }
+  CU(launch_rq_sums(n, d_x, Ax, Mx, partials, scal, s));
+  CU(cudaMemsetAsync(scal + 10, 0, 2 * sizeof(double), s));
+  CU(launch_rq_grad(n, mass, Ax, Mx, g, partials, scal, s));
+  if (mass) { rc = apply_mass(g, Mg); if (rc) return rc; CU(launch_dot(n, g, Mg, partials, scal + 10, s)); }
+  for (int it = 0; it < nu; ++it) {
+    CU(launch_rq_dir(n, it == 0, scal, g, p, s));
+    CU(launch_apply(L.dev, 0.0, p, Ap, nullptr, nullptr, s));
+    if (mass) { rc = apply_mass(p, Mp); if (rc) return rc; }
+    CU(launch_rq_pencil(n, d_x, p, Ax, Ap, Mx, Mp, partials, scal, s));
+    CU(launch_rq_update(n, mass, d_x, p, Ax, Ap, Mx, Mp, partials, scal, s));
+    CU(launch_rq_grad(n, mass, Ax, Mx, g, partials, scal, s));
+    if (mass) { rc = apply_mass(g, Mg); if (rc) return rc; CU(launch_dot(n, g, Mg, partials, scal + 10, s)); }
+  }
+  CU(cudaMemcpyAsync(d_rq2, scal + 12, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  return MGCMT_OK;
+}
+
 int mgcmt_ortho_status(int *h_flag, void *stream) {
   if (!h_flag) return fail(MGCMT_ERR_ARG, "null flag pointer");
   Scratch *sc;

@@ -226,7 +226,7 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
   double eprev[C], ecur[C];  // column-interpolated coarse rows I-1 and I (PROLONG)
 #pragma unroll
   for (int q = 0; q < C; ++q) eprev[q] = ecur[q] = 0.0;
-  double rq_num = 0.0, rq_den = 0.0;
+  double rq_num[C] = {0.0, 0.0, 0.0, 0.0}, rq_den[C] = {0.0, 0.0, 0.0, 0.0};  // one accumulator per column: no serial fma chain
   double racc[2] = {0.0, 0.0};  // running full-weighting row sums (RESTRICT)
 
   int vs = 0, fs = 0;  // ring slots of the current input row t
@@ -328,8 +328,8 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
         if (rho >= r0 && rho < r1 && rho >= L.rq_lo && rho < L.rq_hi && quadout) {  // each useful (owned) point once
 #pragma unroll
           for (int q = 0; q < C; ++q) {
-            rq_num = fma(st[k].xc[q], out[q], rq_num);
-            rq_den = fma(st[k].xc[q], st[k].xc[q], rq_den);
+            rq_num[q] = fma(st[k].xc[q], out[q], rq_num[q]);
+            rq_den[q] = fma(st[k].xc[q], st[k].xc[q], rq_den[q]);
           }
         }
       }
@@ -447,8 +447,8 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
   if (RQ) {
     // the stage summed x (w A_s x)' with (w A_s x)' = -(omega x + beta S4): undo sign and scale
     // w^T A_s w = c sum x (S4 - 4 x) + (d + 4 c - shift) sum x x
-    const double b = warp_sum(rq_den);
-    const double a = fma(L.uni_c, warp_sum(rq_num), K.drem * b);
+    const double b = warp_sum((rq_den[0] + rq_den[1]) + (rq_den[2] + rq_den[3]));
+    const double a = fma(L.uni_c, warp_sum((rq_num[0] + rq_num[1]) + (rq_num[2] + rq_num[3])), K.drem * b);
     if (lane == 0) { r_coarse[rq_slot] = a; r_coarse[rq_nslots + rq_slot] = b; }
   }
 }

@@ -131,6 +131,17 @@ cudaError_t launch_rq_unshift(double *out2, double shift, cudaStream_t s);
 cudaError_t launch_axpby(long long n, double a, const double *x, double b, const double *y, double *out, cudaStream_t s);
 cudaError_t launch_scale_to(long long n, const double *x, const double *sumsq, double *y, cudaStream_t s);
 
+// rq.cu: device-resident Rayleigh-quotient minimisation (MGCMTSolver.rqmin); scal: 32 device doubles, partials: 8 * kReduceBlocks
+cudaError_t launch_rq_pencil(long long n, const double *x, const double *p, const double *Ax, const double *Ap,
+                             const double *Mx, const double *Mp, double *partials, double *scal, cudaStream_t s);
+cudaError_t launch_rq_update(long long n, bool mass, double *x, const double *p, double *Ax, const double *Ap, double *Mx,
+                             const double *Mp, double *partials, double *scal, cudaStream_t s);
+cudaError_t launch_rq_sums(long long n, const double *x, const double *Ax, const double *Mx, double *partials, double *scal,
+                           cudaStream_t s);
+cudaError_t launch_rq_grad(long long n, bool mass, const double *Ax, const double *Mx, double *g, double *partials, double *scal,
+                           cudaStream_t s);
+cudaError_t launch_rq_dir(long long n, bool first, const double *scal, const double *g, double *p, cudaStream_t s);
+
 // band.cu: general banded complex128 operators (1-D multiband Hamiltonians); vectors are complex interleaved
 constexpr int kBandMaxCoarse = 512;  // largest coarsest level the dense complex solve takes
 constexpr int kBandMaxDiags = 96;

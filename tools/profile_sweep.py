@@ -36,6 +36,11 @@ for it in range(2):
             h.fused_leg(0, 1, 4, 1.7, 2.0 / 3.0, v, f, out, None, rc)
         elif what == "up":
             h.fused_leg(0, 3, 4, 1.7, 2.0 / 3.0, v, f, out, rc, None)
+        elif what in ("vcycle_rq_gs", "vcycle_rq_wj"):
+            gs = what.endswith("gs")
+            _lib.check(_lib.load().mgcmt_vcycle_rq(h.handle, 1.7, 4, 4, _lib.SMOOTH_RBGS if gs else _lib.SMOOTH_WJACOBI,
+                                                   1.0 if gs else 2.0 / 3.0, out.data_ptr(), f.data_ptr(), 1, rc.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream))
         elif what == "vcycle_gs":
             h.vcycle(1.7, 4, 4, _lib.SMOOTH_RBGS, 1.0, out, f, v0_is_zero=True)
         elif what == "vcycle_wj":
