@@ -33,6 +33,7 @@ int g_opt_fused = 1;
 int g_opt_fused_min_cols = 64;
 int g_opt_tile_max_cols = 256;   // levels this narrow (or narrower) use the shared-memory tile legs
 int g_opt_tail_max_cols = 32;    // levels this narrow are collapsed into the single-CTA tail kernel
+int g_opt_tile_gs_max_cols = 0;   // Gauss-Seidel legs of levels this narrow run on shared-memory tiles (one launch per leg); off: measured slower (shared-memory bound: 18 loads per update at 1/4 lane efficiency), see DESIGN.md
 int g_opt_coarse_banded = 2;     // coarsest inverse through the banded LU: 0 never, 1 whenever it fits, 2 = when n > 256
 
 void prof_mark(cudaStream_t s, int kind = MGCMT_PROF_SWEEP) {
@@ -270,14 +271,23 @@ bool use_fused(const mgcmt_hier *h, int l, int smoother) {
          L.dev.ncols >= 16 && (L.dev.ncols >= g_opt_fused_min_cols || use_tile(h, l)) && L.dev.row0 == 0;
 }
 
+bool use_tile_gs(const mgcmt_hier *h, int l);
 bool use_fused_gs(const mgcmt_hier *h, int l) {
   const Level &L = h->lev[l];
-  return g_opt_fused && h->coarsen_rows && L.dev.nrows >= 16 && L.dev.ncols >= 64 && L.dev.row0 == 0;
+  return g_opt_fused && h->coarsen_rows && L.dev.nrows >= 16 && (L.dev.ncols >= 64 || use_tile_gs(h, l)) && L.dev.row0 == 0;
 }
 
-// one fused pass of `nu` sweeps (Jacobi: streaming or tile legs; gs: colour-stage streaming legs)
+bool use_tile_gs(const mgcmt_hier *h, int l) {
+  const Level &L = h->lev[l];
+  return L.dev.ncols <= g_opt_tile_gs_max_cols && L.dev.nrows >= 16 && L.dev.ncols >= 16 && L.dev.row0 == 0 && !h->slab;
+}
+// colour sweeps one fused Gauss-Seidel pass takes on level l
+int gs_maxpass(const mgcmt_hier *h, int l) { return use_tile_gs(h, l) ? 4 : (h->lev[l].dev.five ? 4 : 2); }
+
+// one fused pass of `nu` sweeps (Jacobi: streaming or tile legs; gs: colour-stage streaming legs, tile legs on small levels)
 cudaError_t launch_pass(const mgcmt_hier *h, int l, bool gs, int mode, int nu, double shift, double omega,
                         const double *vin, const double *f, double *vout, const double *e, double *rc, cudaStream_t s) {
+  if (gs && use_tile_gs(h, l)) return launch_tile_gs_leg(h->lev[l].dev, mode, nu, shift, omega, vin, f, vout, e, rc, s);
   if (gs) return launch_fused_gs_leg(h->lev[l].dev, mode, nu, shift, omega, vin, f, vout, e, rc, s);
   return launch_leg(h, l, mode, nu, shift, omega, vin, f, vout, e, rc, s);
 }
@@ -288,7 +298,7 @@ int fused_down(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu
                bool v_zero, double **cur, cudaStream_t s) {
   Level &L = h->lev[l];
   Level &C = h->lev[l + 1];
-  const int maxpass = gs ? (L.dev.five ? 4 : 2) : 4;
+  const int maxpass = gs ? gs_maxpass(h, l) : 4;
   double *a = v, *b = L.tmp;
   int left = nu1;
   while (left > maxpass) {
@@ -315,14 +325,15 @@ int fused_down(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu
 int fused_up(mgcmt_hier *h, int l, bool gs, double shift, double omega, int nu2, double *v, const double *f, double *cur,
              const double *e, cudaStream_t s) {
   Level &L = h->lev[l];
-  const int maxpass = gs ? (L.dev.five ? 4 : 2) : 4;
+  const int maxpass = gs ? gs_maxpass(h, l) : 4;
   double *a = cur, *b = (cur == v) ? L.tmp : v;
   int left = nu2;
   const int first = left > maxpass ? maxpass : left;
   const int ukind = (l == 0 && h->rq_out) ? MGCMT_PROF_UP_RQ : MGCMT_PROF_UP;
   if (l == 0) prof_mark(s, ukind);
   // finest level, Rayleigh quotient requested and this pass is the last one: the up leg also leaves the partial sums
-  const int slots = (l == 0 && h->rq_out && first == 4 && left == 4 && !use_tile(h, l)) ? fused_rq_slots(L.dev, gs ? 1 : 0) : 0;
+  const int slots = (l == 0 && h->rq_out && first == 4 && left == 4 && !(gs ? use_tile_gs(h, l) : use_tile(h, l)))
+                        ? fused_rq_slots(L.dev, gs ? 1 : 0) : 0;
   if (slots > 0) {
     if (slots > h->rq_slots) {
       cudaFree(h->rq_partials);
@@ -793,6 +804,7 @@ int mgcmt_set_option(const char *name, int value) {
   if (!strcmp(name, "fused_min_cols")) { g_opt_fused_min_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tile_max_cols")) { g_opt_tile_max_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tail_max_cols")) { g_opt_tail_max_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "tile_gs_max_cols")) { g_opt_tile_gs_max_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "coarse_banded")) {
     if (value < 0 || value > 2) return fail(MGCMT_ERR_ARG, "coarse_banded must be 0, 1 or 2 (auto)");
     g_opt_coarse_banded = value;
@@ -838,14 +850,17 @@ int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, 
   const bool gs_leg = (mode & 32) != 0;      // bit 5: nu = Gauss-Seidel colour sweeps instead of Jacobi sweeps
   mode &= 15;
   if (nu < 0 || nu > 4 || mode < 0 || mode > 3) return fail(MGCMT_ERR_ARG, "bad fused leg mode / nu");
-  if (gs_leg && (force_tile || nu < 1 || nu > (h->lev[level].dev.five ? 4 : 2)))
-    return fail(MGCMT_ERR_ARG, "Gauss-Seidel legs: 1..4 sweeps per pass on the 5-point level, 1..2 on 9-point levels");
+  if (gs_leg && (nu < 1 || nu > ((h->lev[level].dev.five || force_tile) ? 4 : 2)))
+    return fail(MGCMT_ERR_ARG, "Gauss-Seidel legs: 1..4 sweeps per pass on the 5-point level and on tiles, 1..2 on streamed 9-point levels");
   if (d_vin == d_vout) return fail(MGCMT_ERR_ARG, "fused legs are out of place");
   NEED_ALIGNED(d_f, d_vout);
   if (mode != FUSED_DOWN_ZERO) NEED_ALIGNED(d_vin);
   if (mode == FUSED_UP) NEED_ALIGNED(d_ecoarse);
   if (mode == FUSED_DOWN || mode == FUSED_DOWN_ZERO) NEED_ALIGNED(d_rcoarse);
-  if (gs_leg)
+  if (gs_leg && force_tile)
+    CU(launch_tile_gs_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
+                          (cudaStream_t)stream));
+  else if (gs_leg)
     CU(launch_fused_gs_leg(h->lev[level].dev, mode, nu, shift, omega, d_vin, d_f, d_vout, d_ecoarse, d_rcoarse,
                            (cudaStream_t)stream));
   else if (force_tile)

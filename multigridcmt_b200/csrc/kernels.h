@@ -79,6 +79,9 @@ cudaError_t launch_fused_leg(const LevelDev &L, int mode, int nu, double shift, 
 cudaError_t launch_tile_leg(const LevelDev &L, int mode, int nu, double shift, double omega, const double *v_in,
                             const double *f, double *v_out, const double *e_coarse, double *r_coarse,
                             cudaStream_t s);
+// Gauss-Seidel / SOR legs on shared-memory tiles: up to 4 colour sweeps + transfer in one launch (small levels)
+cudaError_t launch_tile_gs_leg(const LevelDev &L, int mode, int sweeps, double shift, double omega, const double *v_in,
+                               const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s);
 constexpr int kTailMaxLevels = 12;
 constexpr size_t kTailMaxSmem = 216 * 1024;
 size_t tail_smem_bytes(const LevelDev *levels, int nlev);

@@ -216,6 +216,176 @@ cudaError_t launch_tile_leg(const LevelDev &L, int mode, int nu, double shift, d
                : launch_tile_t<false, 32>(L, mode, nu, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
 }
 
+// -----------------------------------------------------------------------------------------------------
+// Gauss-Seidel / SOR legs on a tile: `sweeps` colour sweeps (red-black on a 5-point level, the four colours
+// (0,0) (1,1) (0,1) (1,0) of gs.cu on 9-point levels) IN PLACE in shared memory, a barrier per colour stage -- points of
+// one colour only have neighbours of the other colours, so a stage has no read-write conflicts.  The halo covers all
+// stages of a whole leg (4 sweeps x 4 colours + residual = 17 points), so a leg is ONE launch; the streaming
+// colour-stage legs need two passes per leg on 9-point levels and ~20 us per launch on grids this small (one warp
+// walking down its strip), which made the 512^2 .. 128^2 levels a quarter of an RB-GS cycle at 4096^2.
+// -----------------------------------------------------------------------------------------------------
+constexpr int kTileHaloGS = 18;  // >= 4 * sweeps + 2 for sweeps <= 4, even
+
+template <bool FIVE, int T>
+__global__ void __launch_bounds__((T + 2 * kTileHaloGS) * 9)
+tile_gs_leg_kernel(LevelDev L, int mode, int sweeps, double shift, double omega, const double *__restrict__ v_in,
+                   const double *__restrict__ f, double *__restrict__ v_out, const double *__restrict__ e_coarse,
+                   double *__restrict__ r_coarse) {
+  constexpr int H = kTileHaloGS;
+  constexpr int E = T + 2 * H;
+  constexpr int P = E + 1;
+  constexpr int RPP = 9;
+  constexpr int NCOL = FIVE ? 2 : 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *A = reinterpret_cast<double *>(smem_raw);
+  double *F = A + E * P;
+  RowC *rows = reinterpret_cast<RowC *>(F + E * P);
+
+  const int tid = threadIdx.x;
+  const int c = tid % E;
+  const int rbase = tid / E;
+  const int i0 = blockIdx.y * T - H, j0 = blockIdx.x * T - H;
+  const int gj = j0 + c;
+  const bool cin = (gj >= 0 && gj < L.ncols);
+  const int gjc = min(max(gj, 0), L.ncols - 1);
+  const int ncc = L.ncols / 2, nrc = L.nrows / 2;
+
+  for (int r = tid; r < E; r += blockDim.x) {
+    const int gi = i0 + r;
+    const bool rin = (gi >= 0 && gi < L.nrows);
+    const int g = L.row0 + min(max(gi, 0), L.nrows - 1);
+    RowC rc;
+    rc.ka_lo = rin ? L.ka_lo[g] : 0.0; rc.ka_di = rin ? L.ka_di[g] : 0.0; rc.ka_up = rin ? L.ka_up[g] : 0.0;
+    if (FIVE) { rc.ma_lo = 0.0; rc.ma_di = rin ? 1.0 : 0.0; rc.ma_up = 0.0; }
+    else { rc.ma_lo = rin ? L.ma_lo[g] : 0.0; rc.ma_di = rin ? L.ma_di[g] : 0.0; rc.ma_up = rin ? L.ma_up[g] : 0.0; }
+    rc.inside = rin ? 1.0 : 0.0;
+    rc.pad = 0.0;
+    rows[r] = rc;
+  }
+  const double kbl = cin ? L.kb_lo[gjc] : 0.0, kbd = cin ? L.kb_di[gjc] : 0.0, kbu = cin ? L.kb_up[gjc] : 0.0;
+  const double mbl = (!FIVE && cin) ? L.mb_lo[gjc] : 0.0, mbd = FIVE ? 1.0 : (cin ? L.mb_di[gjc] : 0.0),
+               mbu = (!FIVE && cin) ? L.mb_up[gjc] : 0.0;
+  const double kbd_g = L.kb_di[gjc], mbd_g = FIVE ? 1.0 : L.mb_di[gjc];
+  const int gref = L.row0 + min(max(i0 + E / 2, 0), L.nrows - 1);
+  const double kad_ref = L.ka_di[gref], mad_ref = FIVE ? 1.0 : L.ma_di[gref];
+  const double wref = cin ? omega / ((mad_ref * kbd_g + kad_ref * mbd_g) - shift) : 0.0;
+
+  // stage the tile: A = v (+ P e), F = f
+  for (int r = rbase; r < E; r += RPP) {
+    const int gi = i0 + r;
+    const bool in = cin && gi >= 0 && gi < L.nrows;
+    double x = 0.0, ff = 0.0;
+    if (in) {
+      ff = f[(size_t)gi * L.ncols + gj];
+      if (mode != FUSED_DOWN_ZERO) x = v_in[(size_t)gi * L.ncols + gj];
+      if (mode == FUSED_UP) {
+        const int I = gi >> 1, J = gj >> 1;
+        auto E_ = [&](int ii, int jj) -> double {
+          return (ii >= 0 && ii < nrc && jj >= 0 && jj < ncc) ? e_coarse[(size_t)ii * ncc + jj] : 0.0;
+        };
+        double pe;
+        if (gi & 1) {
+          pe = (gj & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
+        } else {
+          const double top = (gj & 1) ? E_(I - 1, J) : 0.5 * (E_(I - 1, J - 1) + E_(I - 1, J));
+          const double bot = (gj & 1) ? E_(I, J) : 0.5 * (E_(I, J - 1) + E_(I, J));
+          pe = 0.5 * (top + bot);
+        }
+        x += pe;
+      }
+    }
+    A[r * P + c] = x;
+    F[r * P + c] = ff;
+  }
+  __syncthreads();
+
+  // colour stages, in place; the border ring of the extended tile is never updated (halo)
+  const bool cint = (c >= 1 && c <= E - 2);
+  const int pc = gj & 1;
+  for (int st = 0; st < sweeps * NCOL; ++st) {
+    const int colour = st % NCOL;
+    for (int r = rbase; r < E; r += RPP) {
+      const int pr = (i0 + r + L.row0) & 1;
+      bool mine;
+      if (FIVE) mine = ((pr + pc) & 1) == colour;
+      else mine = colour == 0 ? (pr == 0 && pc == 0) : colour == 1 ? (pr == 1 && pc == 1) : colour == 2 ? (pr == 0 && pc == 1) : (pr == 1 && pc == 0);
+      if (mine && cint && r >= 1 && r <= E - 2) {
+        const RowC rc = rows[r];
+        const double av = apply_point<FIVE>(A, P, r, c, rc, kbl, kbd, kbu, mbl, mbd, mbu, shift);
+        double w = wref;
+        if (rc.ka_di != kad_ref || rc.ma_di != mad_ref)
+          w = (cin && rc.inside != 0.0) ? omega / ((rc.ma_di * kbd_g + rc.ka_di * mbd_g) - shift) : 0.0;
+        A[r * P + c] += w * (F[r * P + c] - av);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (!((mode == FUSED_DOWN || mode == FUSED_DOWN_ZERO) && sweeps == 0)) {
+    if (c >= H && c < H + T && cin) {
+      for (int r = rbase; r < E; r += RPP) {
+        const int gi = i0 + r;
+        if (r >= H && r < H + T && gi < L.nrows) v_out[(size_t)gi * L.ncols + gj] = A[r * P + c];
+      }
+    }
+  }
+  if (mode != FUSED_DOWN && mode != FUSED_DOWN_ZERO) return;
+
+  // residual in place into F (a point's residual needs only its own f), then full weighting
+  for (int r = rbase; r < E; r += RPP) {
+    double res = 0.0;
+    if (cint && r >= 1 && r <= E - 2) {
+      const RowC rc = rows[r];
+      if (cin && rc.inside != 0.0)
+        res = F[r * P + c] - apply_point<FIVE>(A, P, r, c, rc, kbl, kbd, kbu, mbl, mbd, mbu, shift);
+    }
+    F[r * P + c] = res;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < (T / 2) * (T / 2); idx += blockDim.x) {
+    const int ci = idx / (T / 2), cj = idx - ci * (T / 2);
+    const int I = (blockIdx.y * T) / 2 + ci, J = (blockIdx.x * T) / 2 + cj;
+    if (I < nrc && J < ncc) {
+      const double *p = F + (H + 2 * ci) * P + (H + 2 * cj);
+      const double a0 = 0.25 * p[0] + 0.5 * p[1] + 0.25 * p[2];
+      const double a1 = 0.25 * p[P] + 0.5 * p[P + 1] + 0.25 * p[P + 2];
+      const double a2 = 0.25 * p[2 * P] + 0.5 * p[2 * P + 1] + 0.25 * p[2 * P + 2];
+      r_coarse[(size_t)I * ncc + J] = 0.25 * a0 + 0.5 * a1 + 0.25 * a2;
+    }
+  }
+}
+
+template <bool FIVE, int T>
+static cudaError_t launch_tile_gs_t(const LevelDev &L, int mode, int sweeps, double shift, double omega, const double *v_in,
+                                    const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s) {
+  constexpr int E = T + 2 * kTileHaloGS;
+  constexpr int threads = E * 9;
+  const size_t smem = sizeof(double) * 2 * E * (E + 1) + sizeof(RowC) * E;
+  auto kern = tile_gs_leg_kernel<FIVE, T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((L.ncols + T - 1) / T, (L.nrows + T - 1) / T);
+  kern<<<grid, threads, smem, s>>>(L, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// sweeps: 0..4 colour sweeps in one launch
+cudaError_t launch_tile_gs_leg(const LevelDev &L, int mode, int sweeps, double shift, double omega, const double *v_in,
+                               const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s) {
+  if (sweeps < 0 || sweeps > 4 || L.nrows < 2) return cudaErrorInvalidValue;
+  const bool small = (long long)L.nrows * L.ncols <= 256LL * 256;  // 32 x 32 tiles keep >= 64 CTAs busy
+  if (L.five)
+    return small ? launch_tile_gs_t<true, 32>(L, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s)
+                 : launch_tile_gs_t<true, 64>(L, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  return small ? launch_tile_gs_t<false, 32>(L, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s)
+               : launch_tile_gs_t<false, 64>(L, mode, sweeps, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+}
+
 // =====================================================================================================
 // tail kernel: levels first .. last (last = coarsest) of one hierarchy in one CTA.
 // Shared-memory arena per level: V and TMP with a one-point zero halo (pitch n+2: no bounds checks, and

@@ -216,13 +216,16 @@ def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift, impl, uni_var
             assert rel(out.cpu().numpy(), want_u) < RTOL, ("up", l, nu)
 
 
+@pytest.mark.parametrize("tile", [0, 16])   # 0: streaming colour-stage legs; 16: shared-memory tile legs (small levels)
 @pytest.mark.parametrize("uni_variant", ["general", "uni", "uni9"], indirect=True)
 @pytest.mark.parametrize("N,shift", [(128, 4.38639582), (512, 0.0)])
-def test_fused_gauss_seidel_legs_match_colour_kernels(T, prod, o, N, shift, uni_variant):
+def test_fused_gauss_seidel_legs_match_colour_kernels(T, prod, o, N, shift, uni_variant, tile):
     """colour-stage legs (mode | 32) == the one-kernel-per-colour smoother + the un-fused transfers, and the CPU twin"""
     from multigridcmt_b200 import _lib
     from multigridcmt_b200.hierarchy import get_hierarchy
     from multigridcmt_b200.operators import recognise
+    if tile and uni_variant != "uni":
+        pytest.skip("the tile legs do not depend on the streaming-leg variant")
     sm = prod[0]
     osolver = o[1]
     H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d")
@@ -234,29 +237,29 @@ def test_fused_gauss_seidel_legs_match_colour_kernels(T, prod, o, N, shift, uni_
         v = rand(n, 70 + l); f = rand(n, 80 + l); e = rand(nc, 90 + l)
         dv, df, de = dev(T, v), dev(T, f), dev(T, e)
         for om in (1.0, 1.3):
-            for nu in ((1, 2, 4) if l == 0 else (1, 2)):
+            for nu in ((1, 2, 4) if (l == 0 or tile) else (1, 2)):
                 want = dv.clone()
                 h.smooth(l, _lib.SMOOTH_RBGS, shift, om, nu, want, df)
                 wv = want.cpu().numpy()
                 if om == 1.0 and nu <= 2:
                     assert rel(wv, osolver.rbgs(v.copy(), f.copy(), A, nu=nu, omega=1.0, dimension="2d")) < 1e-11
                 out = T.full_like(dv, 7.0); rc = T.full((nc,), 7.0, dtype=T.float64, device="cuda")
-                h.fused_leg(l, 32 | 0, nu, shift, om, dv, df, out)
+                h.fused_leg(l, tile | 32 | 0, nu, shift, om, dv, df, out)
                 assert rel(out.cpu().numpy(), wv) < RTOL, ("gs smooth", l, nu, om)
                 out.fill_(7.0)
-                h.fused_leg(l, 32 | 1, nu, shift, om, dv, df, out, None, rc)
+                h.fused_leg(l, tile | 32 | 1, nu, shift, om, dv, df, out, None, rc)
                 assert rel(out.cpu().numpy(), wv) < RTOL, ("gs down v", l, nu, om)
                 assert rel(rc.cpu().numpy(), Rs[l] @ (f - A @ wv)) < 1e-11, ("gs down r", l, nu, om)
                 z = T.zeros_like(dv)
                 h.smooth(l, _lib.SMOOTH_RBGS, shift, om, nu, z, df)
                 out.fill_(7.0); rc.fill_(7.0)
-                h.fused_leg(l, 32 | 2, nu, shift, om, None, df, out, None, rc)
+                h.fused_leg(l, tile | 32 | 2, nu, shift, om, None, df, out, None, rc)
                 assert rel(out.cpu().numpy(), z.cpu().numpy()) < RTOL, ("gs down0", l, nu, om)
                 vc = dv.clone()
                 h.prolong_correct(l, de, vc)
                 h.smooth(l, _lib.SMOOTH_RBGS, shift, om, nu, vc, df)
                 out.fill_(7.0)
-                h.fused_leg(l, 32 | 3, nu, shift, om, dv, df, out, de, None)
+                h.fused_leg(l, tile | 32 | 3, nu, shift, om, dv, df, out, de, None)
                 assert rel(out.cpu().numpy(), vc.cpu().numpy()) < RTOL, ("gs up", l, nu, om)
 
 
