@@ -818,6 +818,7 @@ int mgcmt_set_option(const char *name, int value) {
   }
   if (!strcmp(name, "fused_skew_cols")) { mgcmt::g_fused_skew_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "fused_uni9")) { mgcmt::g_fused_uni9 = value ? 1 : 0; return MGCMT_OK; }
+  if (!strcmp(name, "uni_bulk")) { mgcmt::g_uni_bulk = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_wfreg")) { mgcmt::g_uni_wfreg = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_minctas")) {
     if (value != 0 && value != 2 && value != 3) return fail(MGCMT_ERR_ARG, "uni_minctas must be 0 (default), 2 or 3");

@@ -64,6 +64,28 @@ template <int N>
 __device__ __forceinline__ void ucpa_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// ---- bulk asynchronous copies (the TMA engine's 1-D form) with mbarrier completion: the BULK variant of the row ring ----
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  for (int spin = 0; spin < (1 << 26) && !done; ++spin) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+  if (!done) __trap();  // a lost copy must fail the launch, not hang the GPU
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void st_stream4(double *p, double a, double b, double c, double d) {
   asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
@@ -122,7 +144,9 @@ UniCoef uni_coef(double c, double du, double shift, double omega) {
 }  // namespace
 
 // NU: Jacobi sweeps (GS = 0) or colour stages (GS = 1, two per sweep).  PROLONG && RESTRICT = up leg + Rayleigh sums.
-template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, bool WFREG, int MINCTAS>
+// BULK: the row ring is filled by cp.async.bulk (one elected lane per warp and row, completion on an mbarrier per ring
+// slot, linear rows) instead of per-lane cp.async with the XOR swizzle -- the TMA A/B of DESIGN.md section 3.
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, bool WFREG, int MINCTAS, bool BULK = false>
 __global__ void __launch_bounds__(kWarpsU * 32, MINCTAS)
 uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
                 const double *__restrict__ f, double *__restrict__ v_out,
@@ -140,12 +164,13 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // per warp: v ring [kVR][64 granules], f ring [kFR][64], e ring [kERingU][32]; a granule is 16 bytes
-  constexpr int WARP_GRAN = (ZEROV ? 0 : kVR * 64) + kFR * 64 + (PROLONG ? kERingU * 32 : 0);
+  constexpr int WARP_GRAN = (ZEROV ? 0 : kVR * 64) + kFR * 64 + (PROLONG ? kERingU * 32 : 0) + (BULK ? 4 : 0);
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   double2 *ring_v = reinterpret_cast<double2 *>(smem_raw) + warp * WARP_GRAN;
   double2 *ring_f = ring_v + (ZEROV ? 0 : kVR * 64);
   double2 *ring_e = ring_f + kFR * 64;
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring_e + (PROLONG ? kERingU * 32 : 0));  // BULK: kVR (<= 8) barriers
 
   const int r0 = blockIdx.y * rows_per_chunk;
   const int r1 = min(r0 + rows_per_chunk, L.nrows);
@@ -186,18 +211,66 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int G = 32 * g + lane;
-    ldpos[g] = G ^ ((G >> 3) & 1);
+    ldpos[g] = BULK ? G : (G ^ ((G >> 3) & 1));
     const int j = cstart + 2 * G;
     ldin[g] = (j >= 0 && j < L.ncols);
   }
   // consumer: granules 2 lane, 2 lane + 1 (columns c0 .. c0+3)
-  const int pa = (2 * lane) ^ ((lane >> 2) & 1), pb = (2 * lane + 1) ^ ((lane >> 2) & 1);
+  const int pa = BULK ? 2 * lane : ((2 * lane) ^ ((lane >> 2) & 1)), pb = BULK ? 2 * lane + 1 : ((2 * lane + 1) ^ ((lane >> 2) & 1));
+  // BULK: the part of the strip row that lies inside the grid is one contiguous copy; the granules outside stay zero
+  const int bj0 = max(cstart, 0), bj1 = min(cstart + WCOLS, L.ncols);
+  const unsigned brow_bytes = (unsigned)(bj1 - bj0) * 8u;
+  const int bJ0 = bj0 >> 1, bJ1 = min((cstart + WCOLS) >> 1, ncc);
+  if (BULK) {
+    if (lane == 0)
+      for (int i = 0; i < kVR; ++i) mbar_init(bars + i, 1);
+    for (int i = lane; i < WARP_GRAN - 4; i += 32) ring_v[i] = make_double2(0.0, 0.0);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_proxy();
+    __syncwarp();
+  }
 
   // ---- asynchronous row fetch ---------------------------------------------------------------------
   auto issue = [&](int t, int vslot, int fslot) {
     // rows outside the slab array or outside the global grid are zero-filled
     const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last && (unsigned)(t + L.row0) < nglob;
     const size_t rowoff = (size_t)(rowin ? t : 0) * L.ncols;
+    if (BULK) {
+      // every lane first clears its granules of a slot that gets no data (row outside the grid), then lane 0 arms the
+      // slot's barrier with the bytes to come and issues the copies
+      bool ein = false;
+      int I = 0;
+      if (PROLONG && (t & 1) == 0) {
+        I = (t >> 1) + cs;
+        const int Gc = ((t + L.row0) >> 1);
+        ein = I >= 0 && I < nrc && t <= t_last && Gc >= 0 && Gc < (L.nrows_glob >> 1) && bJ1 > bJ0;
+        if (!ein) ring_e[(I & (kERingU - 1)) * 32 + lane] = make_double2(0.0, 0.0);
+      }
+      if (!rowin) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (!ZEROV) ring_v[vslot * 64 + 32 * g + lane] = make_double2(0.0, 0.0);
+          if (NSTAGE > 0) ring_f[fslot * 64 + 32 * g + lane] = make_double2(0.0, 0.0);
+        }
+      }
+      // generic-proxy writes into ring slots (the zero fills above; w f parked by the Gauss-Seidel stage 0) must be
+      // ordered before the async-proxy copy that reuses the slot
+      if ((!WFREG && NSTAGE > 1) || !rowin || (PROLONG && (t & 1) == 0 && !ein)) fence_async_proxy();
+      __syncwarp();
+      if (lane == 0) {
+        const bool any = rowin && brow_bytes > 0;
+        const unsigned bytes = (any ? brow_bytes * ((ZEROV ? 0u : 1u) + (NSTAGE > 0 ? 1u : 0u)) : 0u) + (ein ? (unsigned)(bJ1 - bJ0) * 8u : 0u);
+        mbar_expect_tx(bars + vslot, bytes);
+        if (any) {
+          if (!ZEROV) bulk_g2s(reinterpret_cast<double *>(ring_v + vslot * 64) + (bj0 - cstart), v_in + rowoff + bj0, brow_bytes, bars + vslot);
+          if (NSTAGE > 0) bulk_g2s(reinterpret_cast<double *>(ring_f + fslot * 64) + (bj0 - cstart), f + rowoff + bj0, brow_bytes, bars + vslot);
+        }
+        if (ein)
+          bulk_g2s(reinterpret_cast<double *>(ring_e + (I & (kERingU - 1)) * 32) + (bJ0 - (cstart >> 1)), e_coarse + (size_t)I * ncc + bJ0,
+                   (unsigned)(bJ1 - bJ0) * 8u, bars + vslot);
+      }
+      return;
+    }
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const bool ok = rowin && ldin[g];
@@ -233,8 +306,12 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
   auto step = [&](int t, auto odd_tag, auto slow_tag) {
     constexpr bool ODD = decltype(odd_tag)::value;
     constexpr bool SLOW = decltype(slow_tag)::value;
-    ucpa_wait<AHEAD - 1>();  // row t has landed (this lane's copies) ...
-    __syncwarp();            // ... and every lane's; all lanes are done reading the slots refilled below
+    if (BULK) {
+      mbar_wait(bars + vs, (unsigned)(((t - t_begin) / kVR) & 1));  // row t (and its coarse row) has landed
+    } else {
+      ucpa_wait<AHEAD - 1>();  // row t has landed (this lane's copies) ...
+    }
+    __syncwarp();              // ... and every lane's; all lanes are done reading the slots refilled below
     {
       int vnew = vs + AHEAD; vnew -= (vnew >= kVR) ? kVR : 0;
       int fnew = fs + AHEAD; fnew -= (fnew >= kFR) ? kFR : 0;
@@ -443,7 +520,7 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
       step(t + 1, TrueT{}, TrueT{});
     }
   }
-  ucpa_wait<0>();
+  if (!BULK) ucpa_wait<0>();
   if (RQ) {
     // the stage summed x (w A_s x)' with (w A_s x)' = -(omega x + beta S4): undo sign and scale
     // w^T A_s w = c sum x (S4 - 4 x) + (d + 4 c - shift) sum x x
@@ -456,8 +533,8 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
 // ---------------------------------------------------------------------------------------------------
 namespace {
 
-size_t uni_smem_bytes(bool prolong, bool zerov, int nstage, bool wfreg) {
-  size_t gran = (size_t)((zerov ? 0 : uni_vring(nstage)) + uni_fring(nstage, wfreg)) * 64 + (prolong ? kERingU * 32 : 0);
+size_t uni_smem_bytes(bool prolong, bool zerov, int nstage, bool wfreg, bool bulk) {
+  size_t gran = (size_t)((zerov ? 0 : uni_vring(nstage)) + uni_fring(nstage, wfreg)) * 64 + (prolong ? kERingU * 32 : 0) + (bulk ? 4 : 0);
   return gran * 16 * kWarpsU;
 }
 
@@ -502,14 +579,15 @@ int leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc) {
 
 int g_uni_minctas = 0;  // resident CTAs per SM the 4-sweep Jacobi legs are compiled for: 0 = default, 2 or 3 (A/B timing)
 int g_uni_wfreg = 1;    // 4-sweep Jacobi legs: w f carried in registers (1) or parked in the f ring (0)
+int g_uni_bulk = 0;     // 1: the 4-sweep legs fill their row ring with cp.async.bulk + mbarrier instead of per-lane cp.async
 
-template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, bool WFREG, int MINCTAS>
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, bool WFREG, int MINCTAS, bool BULK = false>
 static cudaError_t launch_uni_m(const LevelDev &L, double shift, double omega, const double *v_in, const double *f,
                                 double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s, int *slots_out) {
   constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);
   constexpr int USEFUL = 32 * kC - 2 * uni_halo(NU);
-  auto kern = uni5_leg_kernel<NU, PROLONG, RESTRICT, ZEROV, GS, WFREG, MINCTAS>;
-  const size_t smem = uni_smem_bytes(PROLONG, ZEROV, NSTAGE, WFREG);
+  auto kern = uni5_leg_kernel<NU, PROLONG, RESTRICT, ZEROV, GS, WFREG, MINCTAS, BULK>;
+  const size_t smem = uni_smem_bytes(PROLONG, ZEROV, NSTAGE, WFREG, BULK);
   static int occ = 0;  // per instantiation
   if (!occ) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -536,6 +614,14 @@ static cudaError_t launch_uni_t(const LevelDev &L, double shift, double omega, c
                                 double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s, int *slots_out) {
 #define UNI_GO(WF, MC) \
   return launch_uni_m<NU, PROLONG, RESTRICT, ZEROV, GS, WF, MC>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out)
+#define UNI_GO_BULK(WF) \
+  return launch_uni_m<NU, PROLONG, RESTRICT, ZEROV, GS, WF, 2, true>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s, slots_out)
+  if constexpr (GS == 0 && NU == 4) {
+    if (g_uni_bulk) UNI_GO_BULK(true);
+  } else if constexpr (GS == 1 && NU == 8) {
+    if (g_uni_bulk) UNI_GO_BULK(false);
+  }
+#undef UNI_GO_BULK
   if constexpr (GS == 0 && NU == 4) {
     // the hot Jacobi legs: both w f variants and both register budgets are built (mgcmt_set_option: uni_wfreg, uni_minctas)
     const int m = g_uni_minctas ? g_uni_minctas : 2;

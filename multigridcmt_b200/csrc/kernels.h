@@ -55,7 +55,7 @@ enum { FUSED_SMOOTH = 0,     // v_out = J^nu(v_in)
 extern int g_fused_c5, g_fused_c9, g_fused_skew_cols;
 int fused_rq_slots(const LevelDev &L, int gs = 0);
 // fused_uni.cu: the same legs for constant-coefficient 5-point levels (LevelDev::uni), half the fp64 instructions
-extern int g_fused_uni, g_uni_minctas, g_uni_wfreg;
+extern int g_fused_uni, g_uni_minctas, g_uni_wfreg, g_uni_bulk;
 bool uni5_available(const LevelDev &L);
 cudaError_t launch_uni5_leg(const LevelDev &L, int gs, int mode, int nu, double shift, double omega, const double *v_in,
                             const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s,

@@ -151,9 +151,10 @@ def test_level_operators_match_oracle(T, prod, o, dim, N, shift):
 # ---------------------------------------------------------------------------------------------------
 UNI_VARIANTS = {"general": dict(fused_uni=0), "uni": dict(fused_uni=1, uni_wfreg=1, uni_minctas=0),
                 "uni9": dict(fused_uni=1, fused_uni9=1),   # optional constant-coefficient 9-point legs (off by default)
+                "uni_bulk": dict(fused_uni=1, uni_bulk=1),  # row ring filled by cp.async.bulk + mbarrier (TMA 1-D copies)
                 "uni_wfreg3": dict(fused_uni=1, uni_wfreg=1, uni_minctas=3), "uni_smem2": dict(fused_uni=1, uni_wfreg=0, uni_minctas=2),
                 "uni_smem3": dict(fused_uni=1, uni_wfreg=0, uni_minctas=3)}
-UNI_DEFAULT = dict(fused_uni=1, uni_wfreg=1, uni_minctas=0, fused_uni9=0)
+UNI_DEFAULT = dict(fused_uni=1, uni_wfreg=1, uni_minctas=0, fused_uni9=0, uni_bulk=0)
 
 
 @pytest.fixture
@@ -217,7 +218,7 @@ def test_fused_legs_match_unfused_and_oracle(T, prod, o, N, shift, impl, uni_var
 
 
 @pytest.mark.parametrize("tile", [0, 16])   # 0: streaming colour-stage legs; 16: shared-memory tile legs (small levels)
-@pytest.mark.parametrize("uni_variant", ["general", "uni", "uni9"], indirect=True)
+@pytest.mark.parametrize("uni_variant", ["general", "uni", "uni9", "uni_bulk"], indirect=True)
 @pytest.mark.parametrize("N,shift", [(128, 4.38639582), (512, 0.0)])
 def test_fused_gauss_seidel_legs_match_colour_kernels(T, prod, o, N, shift, uni_variant, tile):
     """colour-stage legs (mode | 32) == the one-kernel-per-colour smoother + the un-fused transfers, and the CPU twin"""
