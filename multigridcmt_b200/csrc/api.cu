@@ -119,6 +119,7 @@ struct mgcmt_hier {
   bool slab = false;   // row-slab piece of a decomposed grid: only single-level operators are valid
   int halo = 0;        // halo rows above and below the owned rows of every slab level
   int first_work = 0;  // levels below this one have no work vectors (replicated coarse part of a slab solver)
+  double *small_partials = nullptr;  // reduction scratch of mgcmt_rayleigh on levels too small to hold their own partials
   double *rq_partials = nullptr;  // per-warp Rayleigh partial sums of the finest up leg (mgcmt_vcycle_rq)
   int rq_slots = 0;
   double *rq_out = nullptr;       // set for the duration of a mgcmt_vcycle_rq call
@@ -667,6 +668,7 @@ int mgcmt_hier_destroy(mgcmt_hier_t *h) {
   }
   for (auto &e : h->invs) cudaFree(e.inv);
   cudaFree(h->rq_partials);
+  cudaFree(h->small_partials);
   cudaFree(h->status);
   delete h;
   return MGCMT_OK;
@@ -984,10 +986,14 @@ int mgcmt_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2
   // one pass: the operator-apply kernel keeps x^T(Ax) and x^T x partial sums per CTA (L.tmp as scratch),
   // then one ordered finish
   const int nb = march_grid_blocks(L.dev);
-  if ((size_t)2 * nb > L.n) {  // tiny level: scratch too small for the partials, use the plain route
+  if ((size_t)2 * nb > L.n) {
+    // tiny level: L.tmp is too small for the per-CTA partials of the fused pass.  Plain route with partial sums that
+    // belong to this hierarchy (allocated on first use), so that concurrent calls on different hierarchies / streams
+    // (ShiftMethod runs one per stream) never share reduction scratch.
+    if (!h->small_partials) CU(cudaMalloc(&h->small_partials, sizeof(double) * 2 * kReduceBlocks));
     CU(launch_apply(L.dev, 0.0, d_x, L.tmp, nullptr, nullptr, s));
-    CU(launch_dot((long long)L.n, L.tmp, d_x, sc->partials, d_out2, s));
-    CU(launch_dot((long long)L.n, d_x, d_x, sc->partials, d_out2 + 1, s));
+    CU(launch_dot((long long)L.n, L.tmp, d_x, h->small_partials, d_out2, s));
+    CU(launch_dot((long long)L.n, d_x, d_x, h->small_partials + kReduceBlocks, d_out2 + 1, s));
     return MGCMT_OK;
   }
   CU(launch_rayleigh_partials(L.dev, d_x, L.tmp, nullptr, nullptr, s));

@@ -36,6 +36,9 @@ namespace {
 #ifndef MGCMT_MIN_CTAS
 #define MGCMT_MIN_CTAS 2
 #endif
+#ifndef MGCMT_GS9_CTAS
+#define MGCMT_GS9_CTAS 1   // resident CTAs the 8-stage Gauss-Seidel legs of 9-point levels are compiled for (3 = 168 registers: measured 3 % slower per cycle)
+#endif
 constexpr int kVRing = MGCMT_VRING;  // prefetch depth of the v ring (rows, power of two)
 // Pipeline skew: stage k works kSkew * k rows behind the input row.  With kSkew = 1 a stage consumes what its
 // predecessor produced in the SAME time step, so the stages of a step form one serial dependency chain.  With
@@ -86,7 +89,7 @@ struct Stage {
 // through; which points those are is known at compile time (row parity from the unrolled step, column parity from the
 // lane's even first column), so the skipped half / three quarters of the arithmetic is simply not generated.
 template <bool FIVE, int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int C, int GS, int SKEW>
-__global__ void __launch_bounds__(kWarps * 32, (C == 4 ? MGCMT_MIN_CTAS : 1))
+__global__ void __launch_bounds__(kWarps * 32, (C == 4 ? MGCMT_MIN_CTAS : (GS != 0 && !FIVE && NU == 8 ? MGCMT_GS9_CTAS : 1)))
 fused_leg_kernel(LevelDev L, double shift, double omega, const double *__restrict__ v_in,
                  const double *__restrict__ f, double *__restrict__ v_out,
                  const double *__restrict__ e_coarse, double *__restrict__ r_coarse, int rows_per_chunk) {
