@@ -208,7 +208,8 @@ def workload_config(N, smoother, lowest, k=4):
     return {"workload": "2D infinite well %d^2, lowest %d eigenpairs, shift method (2DPotGS.py:91-105): %d x V(4,4) + Rayleigh "
                         "quotient + modified Gram-Schmidt per step" % (N, k, k),
             "grid": N, "eigenpairs": k, "smoother": smoother, "lowest_level": lowest, "levels": levels,
-            "l2": "working set %.1f GB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (10 * N * N * 8 / 1e9)}
+            "l2": ("working set %.1f GB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (10 * N * N * 8 / 1e9)
+                   if 10 * N * N * 8 > 4 * 126e6 else "working set %.2f GB: NOT larger than the 126 MB L2 (non-default --n)" % (10 * N * N * 8 / 1e9))}
 
 
 def start_block_host(N):

@@ -109,7 +109,12 @@ class ShiftBlock:
 
     def __init__(self, n, lowest, shifts, smoother="wjacobi", omega=None):
         self.n, self.k = n, len(shifts)
-        self.hs = [WellHierarchy(n, lowest) for _ in shifts]
+        # a small coarsest operator is re-factored per cycle in microseconds: one hierarchy (its level vectors are
+        # 4/3 x 3 grids: 4.3 GB at 16384^2) serves every shift; a 64^2 coarsest level keeps one LU per shift
+        if lowest * lowest <= 1024:
+            self.hs = [WellHierarchy(n, lowest)] * len(shifts)
+        else:
+            self.hs = [WellHierarchy(n, lowest) for _ in shifts]
         self.shifts = np.ascontiguousarray(shifts, dtype=np.float64)
         self.code = {"wjacobi": 0, "rbgs": 1}[smoother]
         self.omega = (2.0 / 3.0 if self.code == 0 else 1.0) if omega is None else float(omega)
