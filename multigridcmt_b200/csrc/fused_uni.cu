@@ -402,12 +402,13 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
         for (int q = 0; q < C; ++q) out[q] = rin ? out[q] : 0.0;
       }
       if (RQ && is_res) {
-        if (rho >= r0 && rho < r1 && rho >= L.rq_lo && rho < L.rq_hi && quadout) {  // each useful (owned) point once
+        // each useful (owned) point exactly once; branch-free: rows / lanes outside contribute zeros
+        const bool mine = rho >= r0 && rho < r1 && rho >= L.rq_lo && rho < L.rq_hi && quadout;
 #pragma unroll
-          for (int q = 0; q < C; ++q) {
-            rq_num[q] = fma(st[k].xc[q], out[q], rq_num[q]);
-            rq_den[q] = fma(st[k].xc[q], st[k].xc[q], rq_den[q]);
-          }
+        for (int q = 0; q < C; ++q) {
+          const double xm_ = mine ? st[k].xc[q] : 0.0;
+          rq_num[q] = fma(xm_, out[q], rq_num[q]);
+          rq_den[q] = fma(xm_, xm_, rq_den[q]);
         }
       }
       // open row n: the part that needs no shuffle (old centre row = upper neighbour, a x, w f)
