@@ -33,12 +33,15 @@ namespace mgcmt {
 
 namespace {
 
+#ifndef U9_MINCTAS
+#define U9_MINCTAS 2
+#endif
 constexpr int k9C = 4;
 constexpr int k9Warps = 4;
 constexpr int k9ERing = 4;
 __host__ __device__ constexpr int u9_halo(int nu) { return (nu + 2 + 3) & ~3; }
 constexpr int k9VR = 4;
-__host__ __device__ constexpr int u9_fring(int nstage) { return k9VR + 2 * (nstage > 0 ? nstage - 1 : 0) + 1; }
+__host__ __device__ constexpr int u9_fring(int nstage, int lag) { return k9VR + lag * (nstage > 0 ? nstage - 1 : 0) + 1; }
 
 __device__ __forceinline__ void cpa16(void *smem, const void *gmem, bool valid) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -71,8 +74,11 @@ struct K9 {
 
 }  // namespace
 
-template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS>
-__global__ void __launch_bounds__(k9Warps * 32, 2)
+// LAG = 2: a stage consumes what its predecessor finished in the previous step (stages independent within a step, twice
+// the pipeline fill, one more row of state per stage); LAG = 1: in the same step (the shuffle of every stage is on the
+// step's dependency chain, half the fill, less state).
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, int LAG>
+__global__ void __launch_bounds__(k9Warps * 32, U9_MINCTAS)
 uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double *__restrict__ f,
                 double *__restrict__ v_out, const double *__restrict__ e_coarse, double *__restrict__ r_coarse,
                 int rows_per_chunk) {
@@ -82,7 +88,7 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
   constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);
   constexpr int NS1 = NSTAGE > 0 ? NSTAGE : 1;
   constexpr int kVR = k9VR;
-  constexpr int kFR = u9_fring(NSTAGE);
+  constexpr int kFR = u9_fring(NSTAGE, LAG);
   constexpr int AHEAD = kVR - 1;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -95,8 +101,8 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
 
   const int r0 = blockIdx.y * rows_per_chunk;
   const int r1 = min(r0 + rows_per_chunk, L.nrows);
-  // stage k's arriving row in step t is t - 2k; the row it finishes (t - 2k - 1) is correct from t_begin + k + 1 on
-  const int t_last = r1 + 2 * NU + (RESTRICT ? 1 : -1);
+  // stage k's arriving row in step t is t - LAG k; the row it finishes (t - LAG k - 1) is correct from t_begin + k + 1 on
+  const int t_last = r1 + LAG * NU + (RESTRICT ? 1 : -1);
   const int t_begin = (r0 - NU - 2 - (PROLONG ? 2 : 0)) & ~1;
   const int nrc = L.nrows_coarse ? L.nrows_coarse : L.nrows / 2, ncc = L.ncols / 2;
   const int cs = L.crow_shift;
@@ -174,7 +180,7 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
 
   int vs = 0, fs = 0;
   auto step = [&](int t, auto odd_tag, auto slow_tag) {
-    constexpr bool ODD = decltype(odd_tag)::value;   // parity of t == parity of every stage's arriving row t - 2k
+    constexpr bool ODD = decltype(odd_tag)::value;   // parity of t
     constexpr bool SLOW = decltype(slow_tag)::value;
     cpa_wait<AHEAD - 1>();
     __syncwarp();
@@ -204,12 +210,12 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
       }
     }
 #pragma unroll
-    for (int k = 1; k < NSTAGE; ++k) {  // w f of row t - 2k
+    for (int k = 1; k < NSTAGE; ++k) {  // w f of row t - LAG k
       const bool is_res = RESTRICT && (k == NSTAGE - 1);
       const bool gs_stage = (GS != 0) && !is_res;
       const int ci = k & 3, pr = ci & 1, pc = (ci == 1 || ci == 2) ? 1 : 0;
-      if (gs_stage && pr != (ODD ? 1 : 0)) continue;  // this stage opens no point in a row of this parity
-      int sl = fs - 2 * k;
+      if (gs_stage && pr != ((ODD ? 1 : 0) ^ ((LAG * k) & 1))) continue;  // this stage opens no point in a row of this parity
+      int sl = fs - LAG * k;
       sl += (sl < 0) ? kFR : 0;
       sl += (sl < 0) ? kFR : 0;
       if (!gs_stage || pc == 0) { const double2 g0 = ring_f[sl * 64 + pa]; wfq[k][0] = g0.x; wfq[k][2] = g0.y; }
@@ -238,19 +244,23 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
       }
     }
 
-    // ---- stages, last one first: a stage reads what its predecessor finished in the PREVIOUS step ----------
+    // ---- stages.  LAG 2: last one first, a stage reads what its predecessor finished in the PREVIOUS step;
+    // LAG 1: first one first, the finished row is handed on within the step ---------------------------------------
     double res[C];
+    double xflow[C];
+#pragma unroll
+    for (int q = 0; q < C; ++q) xflow[q] = x0[q];
 #pragma unroll
     for (int kk = 0; kk < NSTAGE; ++kk) {
-      const int k = NSTAGE - 1 - kk;
-      const int n = t - 2 * k;  // arriving row; n - 1 is finished
+      const int k = (LAG == 2) ? NSTAGE - 1 - kk : kk;
+      const int n = t - LAG * k;  // arriving row; n - 1 is finished
       const bool is_res = RESTRICT && (k == NSTAGE - 1);
       const bool gs_stage = (GS != 0) && !is_res;
       const int ci = k & 3, pr = ci & 1, pc = (ci == 1 || ci == 2) ? 1 : 0;   // colour order (0,0) (1,1) (0,1) (1,0)
-      const int pn = ODD ? 1 : 0;
+      const int pn = (ODD ? 1 : 0) ^ ((LAG * k) & 1);
       double x[C];
 #pragma unroll
-      for (int q = 0; q < C; ++q) x[q] = (k == 0) ? x0[q] : ready[k - 1][q];
+      for (int q = 0; q < C; ++q) x[q] = (LAG == 2) ? ((k == 0) ? x0[q] : ready[k - 1][q]) : xflow[q];
       const bool open_here = !gs_stage || (pn == pr);    // row n holds points of this stage's colour
       const bool finish_here = !gs_stage || (pn != pr);  // row n - 1 does
       const double xl = __shfl_up_sync(0xffffffffu, x[C - 1], 1);
@@ -284,6 +294,7 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
         if (SLOW && rc_up == 2) rdy = 0.0;
         ready[k][q] = rdy;
         xc[k][q] = x[q];
+        if (LAG == 1) xflow[q] = rdy;
       }
       const int rho = n - 1;
       if (!is_res && k == NU - 1 && rho >= r0 && rho < r1 && quadout) {
@@ -297,9 +308,9 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
       }
     }
     if (RESTRICT) {
-      // res = w * residual of row rho = t - 2 NU - 1 (zero outside the grid): full weighting, columns first
-      const int rho = t - 2 * NU - 1;
-      constexpr bool RHO_ODD = !ODD;
+      // res = w * residual of row rho = t - LAG NU - 1 (zero outside the grid): full weighting, columns first
+      const int rho = t - LAG * NU - 1;
+      constexpr bool RHO_ODD = (ODD != (((LAG * NU + 1) & 1) != 0));
       const double rnext = __shfl_down_sync(0xffffffffu, res[0], 1);
       double crr[2];
       crr[0] = fma(q4, res[0] + res[2], q2 * res[1]);
@@ -332,9 +343,9 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
   using TrueT = std::integral_constant<bool, true>;
   using FalseT = std::integral_constant<bool, false>;
   for (int t = t_begin; t <= t_last; t += 2) {
-    // rows t - 2 (NSTAGE - 1) - 1 .. t + 2 (global) all interior?
+    // rows t - LAG (NSTAGE - 1) - 1 .. t + 2 (global) all interior?
     const int g = t + L.row0;
-    const bool slow = (g - 2 * NSTAGE - 1 < 0) || (g + 2 >= nglob - 1);
+    const bool slow = (g - LAG * NSTAGE - 1 < 0) || (g + 2 >= nglob - 1);
     if (!slow) {
       step(t, FalseT{}, FalseT{});
       step(t + 1, TrueT{}, FalseT{});
@@ -406,20 +417,22 @@ K9 u9_coef(const LevelDev &L, double shift, double omega) {
   return K;
 }
 
-size_t u9_smem_bytes(bool prolong, bool zerov, int nstage) {
-  const size_t gran = (size_t)((zerov ? 0 : k9VR) + u9_fring(nstage)) * 64 + (prolong ? k9ERing * 32 : 0);
+size_t u9_smem_bytes(bool prolong, bool zerov, int nstage, int lag) {
+  const size_t gran = (size_t)((zerov ? 0 : k9VR) + u9_fring(nstage, lag)) * 64 + (prolong ? k9ERing * 32 : 0);
   return gran * 16 * k9Warps;
 }
 
 }  // namespace
 
-template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS>
-static cudaError_t launch_u9_t(const LevelDev &L, double shift, double omega, const double *v_in, const double *f,
+int g_uni9_lag = 1;
+
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS, int LAG>
+static cudaError_t launch_u9_l(const LevelDev &L, double shift, double omega, const double *v_in, const double *f,
                                double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s) {
   constexpr int NSTAGE = NU + (RESTRICT ? 1 : 0);
   constexpr int USEFUL = 32 * k9C - 2 * u9_halo(NU);
-  auto kern = uni9_leg_kernel<NU, PROLONG, RESTRICT, ZEROV, GS>;
-  const size_t smem = u9_smem_bytes(PROLONG, ZEROV, NSTAGE);
+  auto kern = uni9_leg_kernel<NU, PROLONG, RESTRICT, ZEROV, GS, LAG>;
+  const size_t smem = u9_smem_bytes(PROLONG, ZEROV, NSTAGE, LAG);
   static int occ = 0;
   if (!occ) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -430,11 +443,18 @@ static cudaError_t launch_u9_t(const LevelDev &L, double shift, double omega, co
   }
   const int strips = (L.ncols + USEFUL - 1) / USEFUL;
   const int gx = (strips + k9Warps - 1) / k9Warps;
-  const int rpc = leg_rows_per_chunk(L.nrows, gx, occ * num_sms(), 2 * NSTAGE, 1 << 20);
+  const int rpc = leg_rows_per_chunk(L.nrows, gx, occ * num_sms(), LAG * NSTAGE, 1 << 20);
   dim3 grid(gx, (L.nrows + rpc - 1) / rpc);
   kern<<<grid, k9Warps * 32, smem, s>>>(L, u9_coef(L, shift, omega), v_in, f, v_out, e_coarse, r_coarse, rpc);
   count_launch();
   return cudaGetLastError();
+}
+
+template <int NU, bool PROLONG, bool RESTRICT, bool ZEROV, int GS>
+static cudaError_t launch_u9_t(const LevelDev &L, double shift, double omega, const double *v_in, const double *f,
+                               double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s) {
+  if (g_uni9_lag == 2) return launch_u9_l<NU, PROLONG, RESTRICT, ZEROV, GS, 2>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
+  return launch_u9_l<NU, PROLONG, RESTRICT, ZEROV, GS, 1>(L, shift, omega, v_in, f, v_out, e_coarse, r_coarse, s);
 }
 
 template <int NU, int GS>
