@@ -824,7 +824,11 @@ int mgcmt_set_option(const char *name, int value) {
     mgcmt::g_uni9_lag = value;
     return MGCMT_OK;
   }
-  if (!strcmp(name, "fused_uni9")) { mgcmt::g_fused_uni9 = value ? 1 : 0; return MGCMT_OK; }
+  if (!strcmp(name, "fused_uni9")) {
+    if (value < 0 || value > 2) return fail(MGCMT_ERR_ARG, "fused_uni9 must be 0, 1 or 2 (auto)");
+    mgcmt::g_fused_uni9 = value;
+    return MGCMT_OK;
+  }
   if (!strcmp(name, "uni_bulk")) { mgcmt::g_uni_bulk = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_wfreg")) { mgcmt::g_uni_wfreg = value ? 1 : 0; return MGCMT_OK; }
   if (!strcmp(name, "uni_minctas")) {

@@ -474,10 +474,14 @@ static cudaError_t u9_dispatch_mode(const LevelDev &L, int mode, double shift, d
   return cudaErrorInvalidValue;
 }
 
-int g_fused_uni9 = 0;  // measured slower than the general legs on B200: kept as an option, parity-tested
+// 0: never; 1: every eligible 9-point level; 2 (default): levels at least 2048 wide (slab pieces included) -- the only
+// place where these legs beat the general kernel on B200 (8 % at 2048^2)
+int g_fused_uni9 = 2;
 
 bool uni9_available(const LevelDev &L) {
-  return g_fused_uni9 && L.uni == 2 && !L.five && L.nrows >= 16 && L.ncols >= 16 && (L.ncols & 3) == 0;
+  if (!g_fused_uni9 || L.uni != 2 || L.five || L.nrows < 16 || L.ncols < 16 || (L.ncols & 3)) return false;
+  if (g_fused_uni9 == 2) return L.ncols >= 2048;
+  return true;
 }
 
 // nu = Jacobi sweeps 0..4 (gs = 0) or four-colour sweeps 1..2 (gs = 1)

@@ -154,7 +154,7 @@ UNI_VARIANTS = {"general": dict(fused_uni=0), "uni": dict(fused_uni=1, uni_wfreg
                 "uni_bulk": dict(fused_uni=1, uni_bulk=1),  # row ring filled by cp.async.bulk + mbarrier (TMA 1-D copies)
                 "uni_wfreg3": dict(fused_uni=1, uni_wfreg=1, uni_minctas=3), "uni_smem2": dict(fused_uni=1, uni_wfreg=0, uni_minctas=2),
                 "uni_smem3": dict(fused_uni=1, uni_wfreg=0, uni_minctas=3)}
-UNI_DEFAULT = dict(fused_uni=1, uni_wfreg=1, uni_minctas=0, fused_uni9=0, uni_bulk=0)
+UNI_DEFAULT = dict(fused_uni=1, uni_wfreg=1, uni_minctas=0, fused_uni9=2, uni_bulk=0)
 
 
 @pytest.fixture
@@ -306,7 +306,7 @@ def test_all_vcycle_paths_agree(T, prod):
                          s.vcycle(np.zeros(64 * 64), f[:4096].copy(), (-1. / np.pi ** 2) * sm.laplacian(64, "2d"), sm,
                                   shift=1.7, lowest_level=4, dimension="2d")))
     finally:
-        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=32, fused_c9=0, fused_c5=4, fused_uni=1, fused_uni9=0, fused_skew_cols=0).items():
+        for k, v in dict(fused=1, tile_max_cols=256, tail_max_cols=32, fused_c9=0, fused_c5=4, fused_uni=1, fused_uni9=2, fused_skew_cols=0).items():
             lib.mgcmt_set_option(k.encode(), v)
     # all paths share the operator-by-operator arithmetic up to the association of sums; the cycles contain the exact
     # solve of an indefinite coarsest operator (shift 4.386), which amplifies those last-bit differences: 1e-10 (see the
@@ -750,8 +750,9 @@ def test_full_size_properties(T, prod, N):
 # ---------------------------------------------------------------------------------------------------
 # row-slab decomposition (multi-GPU path) emulated on one GPU: same kernels, halo copies instead of NCCL
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("uni_variant", ["uni", "uni9"], indirect=True)   # uni9: the 9-point slab levels run fused_uni9.cu too
 @pytest.mark.parametrize("N,world,gather", [(512, 2, 128), (1024, 4, 256), (1024, 8, 512)])
-def test_slab_vcycle_equals_single_gpu(T, prod, N, world, gather):
+def test_slab_vcycle_equals_single_gpu(T, prod, N, world, gather, uni_variant):
     from multigridcmt_b200.slab import LocalComm, SlabVCycle
     sm, s, _ = prod
     H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
