@@ -394,6 +394,9 @@ def run_ours(args):
     from multigridcmt_b200.hierarchy import _ptr, _stream_ptr
     from multigridcmt_b200.eigensolver import ShiftMethod
     lib = _lib.load()
+    for kv in filter(None, os.environ.get("MGCMT_OPTIONS", "").split(",")):   # A/B switches: MGCMT_OPTIONS=name=value,...
+        name, _, val = kv.partition("=")
+        _lib.check(lib.mgcmt_set_option(name.encode(), int(val)))
     sm, solver, proc = MGCMTStencilMaker(), MGCMTSolver(), MGCMTProcessor()
 
     N = args.n or 4096

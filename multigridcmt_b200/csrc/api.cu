@@ -819,6 +819,7 @@ int mgcmt_set_option(const char *name, int value) {
     return MGCMT_OK;
   }
   if (!strcmp(name, "fused_skew_cols")) { mgcmt::g_fused_skew_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "uni9_min_cols")) { mgcmt::g_uni9_min_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "uni9_lag")) {
     if (value != 1 && value != 2) return fail(MGCMT_ERR_ARG, "uni9_lag must be 1 or 2");
     mgcmt::g_uni9_lag = value;

@@ -556,7 +556,7 @@ int num_sms() {
 // Chunk height for a streaming leg: CTAs = gx * chunks should fill whole waves of `slots` resident CTAs (a grid a few
 // CTAs over a wave costs a whole extra pass at the tail), chunks no taller than 128 rows and, while the grid allows it,
 // no shorter than 32 (every chunk recomputes ~nstage rows of overlap).
-int g_leg_min_rpc = 8;  // smallest chunk height (even); measured: 8 is 2 % faster per RB-GS cycle than 16, 4 and 2 are not
+int g_leg_min_rpc = 16;  // smallest chunk height (even); measured in the 4-stream bench step: 16: 2.102 ms, 8: 2.110, 32: 2.168
 
 int leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc) {
   if (nrows <= 16) return nrows;

@@ -477,10 +477,11 @@ static cudaError_t u9_dispatch_mode(const LevelDev &L, int mode, double shift, d
 // 0: never; 1: every eligible 9-point level; 2 (default): levels at least 2048 wide (slab pieces included) -- the only
 // place where these legs beat the general kernel on B200 (8 % at 2048^2)
 int g_fused_uni9 = 2;
+int g_uni9_min_cols = 512;   // measured in the 4-stream bench step (what counts is SM time, not the latency of a lone leg): 2048: 2.25 ms, 1024: 2.14, 512: 2.11, all levels: 2.23
 
 bool uni9_available(const LevelDev &L) {
   if (!g_fused_uni9 || L.uni != 2 || L.five || L.nrows < 16 || L.ncols < 16 || (L.ncols & 3)) return false;
-  if (g_fused_uni9 == 2) return L.ncols >= 2048;
+  if (g_fused_uni9 == 2) return L.ncols >= g_uni9_min_cols;
   return true;
 }
 
