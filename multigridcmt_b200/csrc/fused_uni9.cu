@@ -481,7 +481,11 @@ int g_uni9_min_cols = 512;   // measured in the 4-stream bench step (what counts
 
 bool uni9_available(const LevelDev &L) {
   if (!g_fused_uni9 || L.uni != 2 || L.five || L.nrows < 16 || L.ncols < 16 || (L.ncols & 3)) return false;
-  if (g_fused_uni9 == 2) return L.ncols >= g_uni9_min_cols;
+  if (g_fused_uni9 == 2) {
+    // slab pieces (lock-step multi-GPU step, few rows per rank on the narrow levels): 2048 measured better than 512
+    const bool slab_piece = L.row0 != 0 || L.nrows != L.nrows_glob;
+    return L.ncols >= (slab_piece && g_uni9_min_cols < 2048 ? 2048 : g_uni9_min_cols);
+  }
   return true;
 }
 
