@@ -180,15 +180,20 @@ int mgcmt_slab_up_rq(mgcmt_hier_t *h, double shift, double omega, const double *
  * mode | 32: the nu sweeps are four-colour (red-black on the 5-point level) Gauss-Seidel/SOR sweeps instead of Jacobi
  *   sweeps (omega = SOR factor; 1..4 sweeps per pass on the 5-point level, 1..2 on the 9-point levels).
  * mode | 16 selects the shared-memory tile implementation (used for mid-size levels) instead of the
- * register-streaming one; both compute the same thing. */
+ * register-streaming one; both compute the same thing (mode | 16 | 32: Gauss-Seidel sweeps on tiles, 1..4 per pass). */
 int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, double omega,
                     const double *d_vin, const double *d_f, double *d_vout, const double *d_ecoarse,
                     double *d_rcoarse, void *stream);
 /* runtime switches, for tests and A/B timing: "fused" (1/0), "fused_min_cols" (smallest level width
  * that uses the fused legs), "tile_max_cols" (levels at most this wide use the tile legs),
  * "tail_max_cols" (levels at most this wide are collapsed into the single-CTA tail kernel; 0 = off),
- * "fused_c5" (2|4 columns per lane on the 5-point level), "band_gs_scan" (1/0: scan form of the in-chunk
- * recurrence of the banded Gauss-Seidel sweep), "band_gs_split" (1/0: old-value part of that sweep in its own launch) */
+ * "fused_c5" / "fused_c9" (columns per lane of the general legs), "leg_min_rpc" (smallest chunk height),
+ * "fused_uni" (1/0: constant-coefficient 5-point legs, fused_uni.cu) with its variants "uni_wfreg" (1/0), "uni_minctas"
+ * (0|2|3), "uni_bulk" (1/0: row ring fed by cp.async.bulk + mbarrier); "fused_uni9" (0 | 1 all | 2 auto: 9-point legs of
+ * fused_uni9.cu on levels >= "uni9_min_cols" wide), "uni9_lag" (1|2); "fused_skew_cols", "tile_gs_max_cols" (alternative
+ * Gauss-Seidel leg designs, 0 = off); "coarse_banded" (0 | 1 | 2 auto: coarsest inverse by banded LU);
+ * "band_gs_scan" (1/0: scan form of the in-chunk recurrence of the banded Gauss-Seidel sweep), "band_gs_split" (1/0:
+ * old-value part of that sweep in its own launch).  DESIGN.md sections 3 / 3c say what each one measured. */
 int mgcmt_set_option(const char *name, int value);
 
 /* ---- reductions / vector post-processing (MGCMTProcessor.py, Rayleigh quotients in the drivers) --

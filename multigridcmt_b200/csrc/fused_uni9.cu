@@ -10,10 +10,12 @@
 //
 // with the coefficients pre-multiplied by -w (c1..c4) this is 7 fp64 instructions per update instead of ~17 in the
 // general kernel, which matters because these levels are not HBM-bound there (2048^2: 55 us per leg against 12-17 us
-// of traffic) and the small ones are latency-bound (20 us for a 512^2 leg).  The pipeline along the rows has LAG 2:
-// the row a stage finishes in step t is consumed by the next stage in step t + 1, so within a step every stage works on
-// state of the previous step -- no stage waits for another one's shuffles, the dependent chain of a step is one
-// shuffle + four fp64 instructions whatever the number of stages.
+// of traffic).  Two pipeline forms (template LAG).  LAG = 1 (the one in use): the row a stage finishes is handed to the
+// next stage within the step, as in fused.cu.  LAG = 2: the row a stage finishes in step t is consumed by the next stage
+// in step t + 1, so within a step every stage works on state of the previous step and no stage waits for another one's
+// shuffles -- but twice the pipeline fill and one more row of state per stage; measured slower on every level.
+// Where it pays (measured inside the 4-stream bench step, where what counts is the SM time a leg takes from the other
+// cycles): levels >= 512 wide, 2.56 -> 2.11 ms per RB-GS step at 4096^2.
 //
 // State per stage and column: `pre1` (row n-1: everything but the contribution of row n), `uprev` (what row n-1
 // gives row n), `ready` (row n-1 finished, next stage's input in the next step); red-black (four-colour) Gauss-Seidel
