@@ -568,7 +568,22 @@ def run_ours(args):
             zeros_np.shape = (n,)
             return r
         v_zero_upload = with_zero_upload()
+        # what the copies alone cost: one pinned H2D + one D2H of a vector per call (the PCIe floor of this API)
+        dbuf = torch.empty(n, dtype=torch.float64, device="cuda")
+        hout = torch.empty(n, dtype=torch.float64).pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for c in range(k):
+            dbuf.copy_(Vh[c], non_blocking=True)
+            hout.copy_(dbuf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        copy_s = time.perf_counter() - t0
+        del dbuf, hout
         e2e = {"value": v_pinned, "unit": UNIT, "h2d_bytes_per_step": k * n * 8, "d2h_bytes_per_step": k * n * 8,
+               "copies_only": {"ms_per_step": 1e3 * copy_s, "GBs_h2d_plus_d2h": k * n * 8 / copy_s / 1e9 * 2,
+                               "value_if_compute_were_free": world * ups_step / copy_s,
+                               "note": "the call is synchronous (numpy in, numpy out), so the upload, the cycle and the download of a "
+                                       "call cannot overlap: this is the PCIe floor of the reference's API"},
                "steps": args.e2e_steps,
                "call": "MGCMTSolver.vcycle(ZeroVector(n), numpy f (pinned), H, sm, shift=, dimension='2d', lowest_level=%d%s)"
                        % (lowest, ", smoother=solver.rbgs" if smoother == "rbgs" else ""),
