@@ -195,6 +195,12 @@ int mgcmt_fused_leg(mgcmt_hier_t *h, int level, int mode, int nu, double shift, 
  * "band_gs_scan" (1/0: scan form of the in-chunk recurrence of the banded Gauss-Seidel sweep), "band_gs_split" (1/0:
  * old-value part of that sweep in its own launch).  DESIGN.md sections 3 / 3c say what each one measured. */
 int mgcmt_set_option(const char *name, int value);
+/* Host-only views of two decisions the legs make, so that they can be tested without a GPU:
+ * the coefficients of fused_uni.cu for a constant 5-point stencil (off-diagonal c, unshifted diagonal d):
+ * h_out7 = {1 - om_hi, -om_hi, -om_lo, -beta, beta / c, c / beta, d + 4c - shift} with om_hi + om_lo = beta (d - shift) / c to
+ * double-double accuracy ("Exact arithmetic"); and the chunk height chosen for a streaming leg. */
+int mgcmt_debug_uni_coefficients(double c, double d, double shift, double omega, double *h_out7);
+int mgcmt_debug_leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc);
 
 /* ---- reductions / vector post-processing (MGCMTProcessor.py, Rayleigh quotients in the drivers) --
  * Deterministic: fixed two-stage tree, independent of launch timing.  Results go to DEVICE memory. */

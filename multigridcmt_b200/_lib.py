@@ -59,6 +59,8 @@ SIGNATURES = {
     "mgcmt_vcycle": (_I, [_P, _D, _I, _I, _I, _D, _P, _P, _I, _P]),
     "mgcmt_fused_leg": (_I, [_P, _I, _I, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
     "mgcmt_set_option": (_I, [C.c_char_p, _I]),
+    "mgcmt_debug_uni_coefficients": (_I, [_D, _D, _D, _D, C.POINTER(_D)]),
+    "mgcmt_debug_leg_rows_per_chunk": (_I, [_I, _I, _I, _I, _I]),
     "mgcmt_dot": (_I, [_LL, _P, _P, _P, _P]),
     "mgcmt_rayleigh": (_I, [_P, _I, _P, _P, _P]),
     "mgcmt_normalize": (_I, [_LL, _P, _P]),

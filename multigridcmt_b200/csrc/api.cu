@@ -800,6 +800,16 @@ int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double 
   return MGCMT_OK;
 }
 
+int mgcmt_debug_uni_coefficients(double c, double d, double shift, double omega, double *h_out7) {
+  if (!h_out7) return fail(MGCMT_ERR_ARG, "null output");
+  mgcmt::uni5_coefficients(c, d, shift, omega, h_out7);
+  return MGCMT_OK;
+}
+
+int mgcmt_debug_leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc) {
+  return mgcmt::leg_rows_per_chunk(nrows, gx, slots, nstage, max_rpc);
+}
+
 int mgcmt_set_option(const char *name, int value) {
   if (!name) return fail(MGCMT_ERR_ARG, "null option name");
   if (!strcmp(name, "fused")) { g_opt_fused = value; return MGCMT_OK; }

@@ -660,6 +660,12 @@ static cudaError_t uni_dispatch_mode(const LevelDev &L, int mode, double shift, 
   return cudaErrorInvalidValue;
 }
 
+// host-only view of the coefficient choice (tests/test_host_logic.py checks the consistency it promises without a GPU)
+void uni5_coefficients(double c, double d, double shift, double omega, double *out7) {
+  const UniCoef k = uni_coef(c, d, shift, omega);
+  out7[0] = k.a_smooth; out7[1] = k.a_res; out7[2] = k.dlo; out7[3] = k.nbeta; out7[4] = k.wf; out7[5] = k.invw; out7[6] = k.drem;
+}
+
 int g_fused_uni = 1;  // 0: constant-coefficient levels use the general kernels of fused.cu too (A/B, parity)
 
 bool uni5_available(const LevelDev &L) { return g_fused_uni && L.uni == 1 && L.five && L.nrows >= 2 && (L.ncols & 1) == 0; }

@@ -61,6 +61,7 @@ cudaError_t launch_uni5_leg(const LevelDev &L, int gs, int mode, int nu, double 
                             const double *f, double *v_out, const double *e_coarse, double *r_coarse, cudaStream_t s,
                             int *slots_out = nullptr);
 int uni5_rq_slots(const LevelDev &L, int gs);
+void uni5_coefficients(double c, double d, double shift, double omega, double *out7);
 // fused_uni9.cu: the same for the Galerkin (9-point) levels with constant interior coefficients (LevelDev::uni == 2)
 extern int g_fused_uni9, g_uni9_lag, g_uni9_min_cols;
 bool uni9_available(const LevelDev &L);
