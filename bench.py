@@ -691,8 +691,6 @@ def run_slab(args):
     lib = _lib.load()
     N = args.n or 16384
     smoother_s, lowest = defaults(args, True)
-    if smoother_s != "wjacobi":
-        raise SystemExit("bench.py: the slab path runs the weighted-Jacobi legs")
     k = len(MODES)
     sm = MGCMTStencilMaker()
     H = (-1.0 / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
@@ -706,7 +704,7 @@ def run_slab(args):
         from multigridcmt_b200.slab import NativeSlabBlock
         with StdoutToStderr():
             nb = NativeSlabBlock(H, world, rank, k, lowest_level=lowest, gather_cols=args.gather_cols,
-                                 stagger=bool(args.slab_stagger))
+                                 stagger=bool(args.slab_stagger), smoother=smoother_s)
         own, begin, nlev_slab, lockstep = nb.own0, nb.begin0, nb.nlev, True
         owned = nb.owned
         bd = {"V": nb.new_block(), "W": nb.new_block()}
@@ -723,7 +721,8 @@ def run_slab(args):
         # one solver state (level buffers) per CUDA stream: the 4 independent V-cycles of a step overlap each other's
         # halo exchanges and replicated coarse parts
         nstreams = max(1, min(args.streams, k))
-        svs = [SlabVCycle(H, world, comm, [rank], lowest_level=lowest, gather_cols=args.gather_cols) for _ in range(nstreams)]
+        svs = [SlabVCycle(H, world, comm, [rank], lowest_level=lowest, gather_cols=args.gather_cols, smoother=smoother_s)
+               for _ in range(nstreams)]
         streams = [torch.cuda.Stream() for _ in range(nstreams)]
         sv = svs[0]
         st = sv.states[0]
@@ -822,6 +821,7 @@ def run_slab(args):
         e2e = {"value": ups_step * args.e2e_steps / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": k * own * N * 8 * world, "d2h_bytes_per_step": k * own * N * 8 * world,
                "steps": args.e2e_steps, "call": "slab block cycle (k V-cycles) on owned rows copied from / to pinned host memory"}
+    LEG_B = (18.0 + 26.0) * 4.0 / 3.0
     if rank == 0:
         peaks = {}
         try:
@@ -833,7 +833,7 @@ def run_slab(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(N, "wjacobi", lowest, k), l2="per-rank working set >> 126 MB L2"),
+            "config": dict(workload_config(N, smoother_s, lowest, k), l2="per-rank working set >> 126 MB L2"),
             "impl_detail": {"parallelism": "row slabs x%d, NCCL send/recv halos per fused leg + all-gather of the first replicated level" % world,
                             "slab_levels": nlev_slab, "halo_rows": HALO, "lockstep_block": lockstep, "cuda_graph": graphed,
                             "driver": (("native: step issued from C++, NCCL called directly (csrc/slab_block.cu)"
@@ -845,9 +845,13 @@ def run_slab(args):
             "vcycles_per_s": k * args.steps / (ms * 1e-3), "host_issue_ms_per_step": host_issue_ms,
             "eigenvalues": lam_h, "eigenvalue_abs_err": [abs(a - b) for a, b in zip(lam_h, exact)],
             "gpu_launches": int(launches), "clocks": clk, "e2e": e2e,
-            "roofline": {"bound": "hbm", "achieved": 304.0 * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world, "peak": peak,
-                         "unit": "GB/s", "frac": 304.0 * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
-                         "kernel": "whole step per GPU at 304 B per fine unknown and V-cycle (SURVEY 8d); per-kernel numbers: N=1 run",
+            "roofline": {"bound": "hbm", "achieved": LEG_B * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world, "peak": peak,
+                         "unit": "GB/s", "frac": LEG_B * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world / peak, "traffic": None,
+                         "kernel": "whole step per GPU at %.1f B per fine unknown and V-cycle = the fused legs' compulsory traffic "
+                                   "(18 B zero-start down leg + 26 B up leg per level, x 4/3 over the levels; halo exchanges, the "
+                                   "replicated coarse part and the orthonormalisation are inside the time, not the bytes); "
+                                   "per-kernel numbers: N=1 run" % LEG_B,
+                         "unfused_step_GBs_at_304B": 304.0 * N * N * k * args.steps / (ms * 1e-3) / 1e9 / world,
                          "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback"},
             "cpu_baseline": None,
         }

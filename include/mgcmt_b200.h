@@ -164,10 +164,10 @@ int mgcmt_vcycle_from(mgcmt_hier_t *h, int level, double shift, int smoother, do
 /* slab piece: d_out2[0] = x^T A x, d_out2[1] = x^T x summed over the OWNED rows of this rank only (the caller
  * all-reduces); d_x is the slab array including its halo rows */
 int mgcmt_slab_rayleigh(mgcmt_hier_t *h, int level, const double *d_x, double *d_out2, void *stream);
-/* slab piece, finest level: the up leg (mgcmt_fused_leg mode 3, nu = 4) with the Rayleigh sums of its result taken in
- * the same pass: d_out2[0] = w^T A w, d_out2[1] = w^T w over the OWNED rows of this rank (the caller all-reduces).
+/* slab piece, finest level: the up leg (mgcmt_fused_leg mode 3, nu = 4; gs != 0: four red-black sweeps) with the Rayleigh
+ * sums of its result taken in the same pass: d_out2[0] = w^T A w, d_out2[1] = w^T w over the OWNED rows of this rank (the caller all-reduces).
  * Needs no exchange of the result's halo rows: the leg already has the exact neighbouring rows in its pipeline. */
-int mgcmt_slab_up_rq(mgcmt_hier_t *h, double shift, double omega, const double *d_vin, const double *d_f, double *d_vout,
+int mgcmt_slab_up_rq(mgcmt_hier_t *h, int gs, double shift, double omega, const double *d_vin, const double *d_f, double *d_vout,
                      const double *d_ecoarse, double *d_out2, void *stream);
 
 /* One fused pass over a 2-D level (what mgcmt_vcycle is made of when the smoother is weighted Jacobi):
@@ -314,8 +314,12 @@ int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *
 /* instrumentation: with profiling on, the stages of every following cycle (lock-step form, comm2 == NULL) are bracketed
  * by CUDA events on the block's ordering stream; _read returns, for the last cycle, the milliseconds of each
  * communication stage and of the compute stage that follows it (stage order: down levels 0.., replicated coarse part,
- * up levels ..0, Rayleigh sums if with_lam); arrays of at least 2*nlev_slab + 2 doubles */
+ * up levels ..0, Rayleigh sums if with_lam); arrays of at least 4*nlev_slab + 2 doubles */
 int mgcmt_slabblock_profile(mgcmt_slabblock_t *b, int on);
+/* smoother of the block's cycles: MGCMT_SMOOTH_WJACOBI (default, omega 2/3) or MGCMT_SMOOTH_RBGS (red-black / four-colour
+ * Gauss-Seidel, the smoother of BASELINE config 3; on 9-point slab levels a leg is two passes of two sweeps with a halo
+ * exchange of the intermediate iterate in between: the profile then has 4*nlev_slab stages) */
+int mgcmt_slabblock_set_smoother(mgcmt_slabblock_t *b, int smoother, double omega);
 int mgcmt_slabblock_profile_read(mgcmt_slabblock_t *b, int with_lam, double *h_ms_comm, double *h_ms_comp, int *nstage);
 /* orthonormalise the k slab vectors d_block + c*stride (Gram-matrix form of MGCMTProcessor.gramschmidt: local packed
  * Gram matrix of the owned rows, one all-reduce, Q = W R^-1 locally) */

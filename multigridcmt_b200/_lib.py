@@ -41,7 +41,7 @@ SIGNATURES = {
     "mgcmt_vcycle_rq": (_I, [_P, _D, _I, _I, _I, _D, _P, _P, _I, _P, _P]),
     "mgcmt_vcycle_from": (_I, [_P, _I, _D, _I, _D, _P, _P, _P]),
     "mgcmt_slab_rayleigh": (_I, [_P, _I, _P, _P, _P]),
-    "mgcmt_slab_up_rq": (_I, [_P, _D, _D, _P, _P, _P, _P, _P, _P]),
+    "mgcmt_slab_up_rq": (_I, [_P, _I, _D, _D, _P, _P, _P, _P, _P, _P]),
     "mgcmt_hier_destroy": (_I, [_P]),
     "mgcmt_hier_num_levels": (_I, [_P]),
     "mgcmt_hier_level_shape": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I)]),
@@ -93,6 +93,7 @@ SIGNATURES = {
     "mgcmt_slabblock_cycle": (_I, [_P, _P, _P, _P, _P, _P]),
     "mgcmt_slabblock_gram": (_I, [_P, _P, _LL, _P]),
     "mgcmt_slabblock_profile": (_I, [_P, _I]),
+    "mgcmt_slabblock_set_smoother": (_I, [_P, _I, _D]),
     "mgcmt_slabblock_profile_read": (_I, [_P, _I, _P, _P, C.POINTER(_I)]),
 }
 

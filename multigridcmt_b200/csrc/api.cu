@@ -647,7 +647,7 @@ int mgcmt_hier_create_slab(mgcmt_hier_t **out, int nrows_glob, int ncols, int ro
   int rc = check_create_args(out, nrows_glob, ncols, 1, h_row_lo, h_row_di, h_row_up, h_col_lo, h_col_di, h_col_up);
   if (rc) return rc;
   if (nlevels < 1 || nlevels > 16) return fail(MGCMT_ERR_ARG, "bad number of slab levels");
-  if (halo < 6 || (halo & 1)) return fail(MGCMT_ERR_ARG, "halo must be even and >= 6 (NU + 2 rows for NU = 4)");
+  if (halo < 6 || (halo & 1)) return fail(MGCMT_ERR_ARG, "halo must be even and >= 6 (NU + 2 rows: 6 for 4 Jacobi sweeps, 10 for 8 Gauss-Seidel colour stages)");
   const int align = 1 << nlevels;  // slab cuts must stay on even rows on every distributed level
   if (row_begin < 0 || nrows_own <= 0 || row_begin + nrows_own > nrows_glob || (row_begin % align) || (nrows_own % align))
     return fail(MGCMT_ERR_ARG, "slab rows must be multiples of 2^nlevels inside the grid");
@@ -934,7 +934,7 @@ int mgcmt_vcycle_from(mgcmt_hier_t *h, int level, double shift, int smoother, do
   return vcycle_level(h, level, shift, 4, 4, smoother, omega, d_v, d_f, true, (cudaStream_t)stream);
 }
 
-int mgcmt_slab_up_rq(mgcmt_hier_t *h, double shift, double omega, const double *d_vin, const double *d_f, double *d_vout,
+int mgcmt_slab_up_rq(mgcmt_hier_t *h, int gs, double shift, double omega, const double *d_vin, const double *d_f, double *d_vout,
                      const double *d_ecoarse, double *d_out2, void *stream) {
   int rc = check_level(h, 0);
   if (rc) return rc;
@@ -944,7 +944,7 @@ int mgcmt_slab_up_rq(mgcmt_hier_t *h, double shift, double omega, const double *
   NEED_ALIGNED(d_vin, d_f, d_vout, d_ecoarse);
   Level &L = h->lev[0];
   cudaStream_t s = (cudaStream_t)stream;
-  const int slots = fused_rq_slots(L.dev);
+  const int slots = fused_rq_slots(L.dev, gs ? 1 : 0);
   if (slots <= 0) return fail(MGCMT_ERR_STATE, "the fused Rayleigh stage is not available for this level");
   if (slots > h->rq_slots) {
     cudaFree(h->rq_partials);
@@ -954,7 +954,8 @@ int mgcmt_slab_up_rq(mgcmt_hier_t *h, double shift, double omega, const double *
   }
   // halo rows 5 and own+6 of the output are exact (dependency cone of prolongation + 4 sweeps = 5 rows, 6 halo rows),
   // so (A w) on the first and last owned row is too: the sums over the owned rows need no second exchange
-  CU(launch_fused_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, d_vin, d_f, d_vout, d_ecoarse, h->rq_partials, s));
+  if (gs) CU(launch_fused_gs_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, d_vin, d_f, d_vout, d_ecoarse, h->rq_partials, s));
+  else CU(launch_fused_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, d_vin, d_f, d_vout, d_ecoarse, h->rq_partials, s));
   CU(launch_finish(2, slots, h->rq_partials, d_out2, s));
   CU(launch_rq_unshift(d_out2, shift, s));
   return MGCMT_OK;

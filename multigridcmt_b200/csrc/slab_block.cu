@@ -96,6 +96,7 @@ struct mgcmt_slabblock {
   std::vector<VecState> vec;
   cudaEvent_t fork = nullptr;
   double *scal = nullptr;  // 64 doubles
+  int smoother = MGCMT_SMOOTH_WJACOBI;  // or MGCMT_SMOOTH_RBGS (mgcmt_slabblock_set_smoother)
   bool fused_rq = true;            // Rayleigh sums inside the finest up leg (MGCMT_SLAB_FUSED_RQ=0: separate stage)
   bool profile = false;            // time every stage of the next cycles with CUDA events (lock-step form only)
   std::vector<cudaEvent_t> prof;   // 2 * nstage + 1 events of the last profiled cycle
@@ -103,7 +104,7 @@ struct mgcmt_slabblock {
 
 namespace {
 
-constexpr int kHalo = 6;  // multigridcmt_b200/slab.py: HALO
+constexpr int kHalo = 10;  // multigridcmt_b200/slab.py: HALO (cone of the longest fused leg: 8 Gauss-Seidel colour stages + transfer)
 
 size_t level_elems(const mgcmt_slabblock *b, int l) { return (size_t)((b->own0 >> l) + 2 * kHalo) * (size_t)(b->n >> l); }
 
@@ -146,59 +147,127 @@ int exchange(mgcmt_slabblock *b, Half &h, const std::vector<HaloItem> &items) {
   return MGCMT_OK;
 }
 
-// Stage i of a cycle for one half.  comm(i) precedes comp(i):
-//   i < nl        comm: halos of f[i]                               comp: down leg of level i
-//   i == nl       comm: all-gather of the restricted residual       comp: replicated coarse cycle
-//   nl < i <= 2nl comm: halos of tmp[l] (and v[l+1]), l = 2nl - i   comp: up leg of level l
-//   i == 2nl + 1  comm: halos of the result v[0]                    comp: Rayleigh sums   (only with d_lam when the
-//                                                                         sums are not taken inside the last up leg)
-int comm_stage(mgcmt_slabblock *b, Half &h, int i) {
+// The phases of a cycle for one half; comm(i) precedes comp(i).
+//   weighted Jacobi (and the 5-point level of the red-black smoother: one pass of 4 sweeps):
+//     DOWN(l)    comm: halos of f[l]                           comp: down leg of level l (zero start)      -> tmp[l], f[l+1]
+//     UP(l)      comm: halos of tmp[l] (and of v[l+1])         comp: up leg of level l                     -> v[l]
+//   red-black on the 9-point levels (two passes of two sweeps per leg, the intermediate iterate exchanged in between):
+//     DOWN_A(l)  comm: halos of f[l]                           comp: 2 sweeps from zero                    -> tmp[l]
+//     DOWN_B(l)  comm: halos of tmp[l]                         comp: 2 sweeps + residual + restriction     -> v[l], f[l+1]
+//     UP_A(l)    comm: halos of v[l] (and of v[l+1])           comp: correction + 2 sweeps                 -> tmp[l]
+//     UP_B(l)    comm: halos of tmp[l]                         comp: 2 sweeps                              -> v[l]
+//   COARSE       comm: all-gather of the restricted residual   comp: replicated coarse cycle
+//   RQ           comm: halos of the result v[0]                comp: Rayleigh sums (only when they are not taken inside
+//                                                                     the last up leg)
+enum PhaseKind { PH_DOWN, PH_DOWN_A, PH_DOWN_B, PH_COARSE, PH_UP, PH_UP_A, PH_UP_B, PH_RQ };
+struct Phase {
+  PhaseKind kind;
+  int level;
+};
+
+std::vector<Phase> build_phases(const mgcmt_slabblock *b, bool with_rq_stage) {
+  std::vector<Phase> ph;
   const int nl = b->nlev;
-  std::vector<HaloItem> items;
-  auto add = [&](std::vector<double *> VecState::*member, int l) {
-    for (int c = h.begin; c < h.end; ++c) items.push_back({(b->vec[c].*member)[l], l});
-  };
-  if (i < nl) {
-    add(&VecState::f, i);
-  } else if (i == nl) {
-    if (b->world == 1) return MGCMT_OK;
-    const size_t cnt = (size_t)(b->own0 >> nl) * (size_t)(b->n >> nl);
-    NC(g_nccl.GroupStart());
-    for (int c = h.begin; c < h.end; ++c) {
-      VecState &s = b->vec[c];
-      NC(g_nccl.AllGather(s.fg + (size_t)b->rank * cnt, s.fg, cnt, kNcclFloat64, h.comm, h.gs));
-    }
-    NC(g_nccl.GroupEnd());
-    return MGCMT_OK;
-  } else if (i <= 2 * nl) {
-    const int l = 2 * nl - i;
-    add(&VecState::tmp, l);
-    if (l + 1 < nl) add(&VecState::v, l + 1);
-  } else {
-    add(&VecState::v, 0);
+  const bool gs = (b->smoother == MGCMT_SMOOTH_RBGS);
+  for (int l = 0; l < nl; ++l) {
+    if (gs && l > 0) { ph.push_back({PH_DOWN_A, l}); ph.push_back({PH_DOWN_B, l}); }
+    else ph.push_back({PH_DOWN, l});
   }
+  ph.push_back({PH_COARSE, nl});
+  for (int l = nl - 1; l >= 0; --l) {
+    if (gs && l > 0) { ph.push_back({PH_UP_A, l}); ph.push_back({PH_UP_B, l}); }
+    else ph.push_back({PH_UP, l});
+  }
+  if (with_rq_stage) ph.push_back({PH_RQ, 0});
+  return ph;
+}
+
+int comm_stage(mgcmt_slabblock *b, Half &h, const Phase &p) {
+  const int nl = b->nlev, l = p.level;
+  const bool gs = (b->smoother == MGCMT_SMOOTH_RBGS);
+  std::vector<HaloItem> items;
+  auto add = [&](std::vector<double *> VecState::*member, int lev) {
+    for (int c = h.begin; c < h.end; ++c) items.push_back({(b->vec[c].*member)[lev], lev});
+  };
+  switch (p.kind) {
+    case PH_DOWN:
+    case PH_DOWN_A:
+      add(&VecState::f, l);
+      break;
+    case PH_DOWN_B:
+    case PH_UP_B:
+      add(&VecState::tmp, l);
+      break;
+    case PH_COARSE: {
+      if (b->world == 1) return MGCMT_OK;
+      const size_t cnt = (size_t)(b->own0 >> nl) * (size_t)(b->n >> nl);
+      NC(g_nccl.GroupStart());
+      for (int c = h.begin; c < h.end; ++c) {
+        VecState &s = b->vec[c];
+        NC(g_nccl.AllGather(s.fg + (size_t)b->rank * cnt, s.fg, cnt, kNcclFloat64, h.comm, h.gs));
+      }
+      NC(g_nccl.GroupEnd());
+      return MGCMT_OK;
+    }
+    case PH_UP:
+      add(&VecState::tmp, l);   // the smoothed iterate of the down leg (Jacobi; red-black on the 5-point level)
+      if (l + 1 < nl) add(&VecState::v, l + 1);
+      break;
+    case PH_UP_A:
+      add(&VecState::v, l);     // red-black, 9-point level: the down leg left its iterate in v[l]
+      if (l + 1 < nl) add(&VecState::v, l + 1);
+      break;
+    case PH_RQ:
+      add(&VecState::v, 0);
+      break;
+  }
+  (void)gs;
   return exchange(b, h, items);
 }
 
-int comp_stage(mgcmt_slabblock *b, Half &h, int i, const double *shifts, double *d_lam) {
-  const int nl = b->nlev;
+int comp_stage(mgcmt_slabblock *b, Half &h, const Phase &p, const double *shifts, double *d_lam) {
+  const int nl = b->nlev, l = p.level;
+  const bool gs = (b->smoother == MGCMT_SMOOTH_RBGS);
+  const int G = gs ? 32 : 0;  // mgcmt_fused_leg: Gauss-Seidel colour sweeps
   RC(fork_streams(b, h));
   for (int c = h.begin; c < h.end; ++c) {
     VecState &s = b->vec[c];
-    if (i < nl) {
-      RC(mgcmt_fused_leg(s.slab, i, 2 /* down, zero start */, 4, shifts[c], b->omega, nullptr, s.f[i], s.tmp[i], nullptr,
-                         (i + 1 == nl) ? s.fg : s.f[i + 1], s.stream));
-    } else if (i == nl) {
-      RC(mgcmt_vcycle_from(s.coarse, nl, shifts[c], MGCMT_SMOOTH_WJACOBI, b->omega, s.vg, s.fg, s.stream));
-    } else if (i <= 2 * nl) {
-      const int l = 2 * nl - i;
-      const double *e = (l + 1 == nl) ? s.vg : s.v[l + 1];
-      if (l == 0 && d_lam && b->fused_rq)   // the Rayleigh sums of the result are taken inside the last up leg
-        RC(mgcmt_slab_up_rq(s.slab, shifts[c], b->omega, s.tmp[0], s.f[0], s.v[0], e, d_lam + 2 * c, s.stream));
-      else
-        RC(mgcmt_fused_leg(s.slab, l, 3 /* up */, 4, shifts[c], b->omega, s.tmp[l], s.f[l], s.v[l], e, nullptr, s.stream));
-    } else {
-      RC(mgcmt_slab_rayleigh(s.slab, 0, s.v[0], d_lam + 2 * c, s.stream));
+    const double sh = shifts[c];
+    switch (p.kind) {
+      case PH_DOWN:
+        RC(mgcmt_fused_leg(s.slab, l, G | 2 /* down, zero start */, 4, sh, b->omega, nullptr, s.f[l], s.tmp[l], nullptr,
+                           (l + 1 == nl) ? s.fg : s.f[l + 1], s.stream));
+        break;
+      case PH_DOWN_A:
+        CU(cudaMemsetAsync(s.v[l], 0, sizeof(double) * level_elems(b, l), s.stream));
+        RC(mgcmt_fused_leg(s.slab, l, G | 0 /* smooth */, 2, sh, b->omega, s.v[l], s.f[l], s.tmp[l], nullptr, nullptr, s.stream));
+        break;
+      case PH_DOWN_B:
+        RC(mgcmt_fused_leg(s.slab, l, G | 1 /* down */, 2, sh, b->omega, s.tmp[l], s.f[l], s.v[l], nullptr,
+                           (l + 1 == nl) ? s.fg : s.f[l + 1], s.stream));
+        break;
+      case PH_COARSE:
+        RC(mgcmt_vcycle_from(s.coarse, nl, sh, b->smoother, b->omega, s.vg, s.fg, s.stream));
+        break;
+      case PH_UP: {
+        const double *e = (l + 1 == nl) ? s.vg : s.v[l + 1];
+        if (l == 0 && d_lam && b->fused_rq)   // the Rayleigh sums of the result are taken inside the last up leg
+          RC(mgcmt_slab_up_rq(s.slab, gs ? 1 : 0, sh, b->omega, s.tmp[0], s.f[0], s.v[0], e, d_lam + 2 * c, s.stream));
+        else
+          RC(mgcmt_fused_leg(s.slab, l, G | 3 /* up */, 4, sh, b->omega, s.tmp[l], s.f[l], s.v[l], e, nullptr, s.stream));
+        break;
+      }
+      case PH_UP_A: {
+        const double *e = (l + 1 == nl) ? s.vg : s.v[l + 1];
+        RC(mgcmt_fused_leg(s.slab, l, G | 3 /* up */, 2, sh, b->omega, s.v[l], s.f[l], s.tmp[l], e, nullptr, s.stream));
+        break;
+      }
+      case PH_UP_B:
+        RC(mgcmt_fused_leg(s.slab, l, G | 0 /* smooth */, 2, sh, b->omega, s.tmp[l], s.f[l], s.v[l], nullptr, nullptr, s.stream));
+        break;
+      case PH_RQ:
+        RC(mgcmt_slab_rayleigh(s.slab, 0, s.v[0], d_lam + 2 * c, s.stream));
+        break;
     }
   }
   RC(join_streams(b, h));
@@ -379,7 +448,9 @@ int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *
   }
   Half &A = b->half[0], &B = b->half[1];
   const bool two = B.end > B.begin;
-  const int nstage = 2 * nl + 1 + ((d_lam && !b->fused_rq) ? 1 : 0);
+  const std::vector<Phase> phases = build_phases(b, d_lam && !b->fused_rq);
+  const int nstage = (int)phases.size();
+  (void)nl;
   // both halves start after everything already on the caller's stream
   CU(cudaEventRecord(b->fork, main));
   CU(cudaStreamWaitEvent(A.gs, b->fork, 0));
@@ -393,20 +464,20 @@ int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *
     }
     CU(cudaEventRecord(b->prof[0], A.gs));
   }
-  RC(comm_stage(b, A, 0));
+  RC(comm_stage(b, A, phases[0]));
   if (prof) CU(cudaEventRecord(b->prof[1], A.gs));
-  if (two) RC(comm_stage(b, B, 0));
+  if (two) RC(comm_stage(b, B, phases[0]));
   for (int i = 0; i < nstage; ++i) {
     // A computes stage i (after B's stage i-1 kernels), then exchanges for stage i+1 while B computes stage i, ...
     if (two && i > 0) CU(cudaStreamWaitEvent(A.gs, B.comp_done, 0));
-    RC(comp_stage(b, A, i, h_shifts, d_lam));
+    RC(comp_stage(b, A, phases[i], h_shifts, d_lam));
     if (prof) CU(cudaEventRecord(b->prof[2 * i + 2], A.gs));
-    if (i + 1 < nstage) RC(comm_stage(b, A, i + 1));
+    if (i + 1 < nstage) RC(comm_stage(b, A, phases[i + 1]));
     if (prof && i + 1 < nstage) CU(cudaEventRecord(b->prof[2 * i + 3], A.gs));
     if (two) {
       CU(cudaStreamWaitEvent(B.gs, A.comp_done, 0));
-      RC(comp_stage(b, B, i, h_shifts, d_lam));
-      if (i + 1 < nstage) RC(comm_stage(b, B, i + 1));
+      RC(comp_stage(b, B, phases[i], h_shifts, d_lam));
+      if (i + 1 < nstage) RC(comm_stage(b, B, phases[i + 1]));
     }
   }
   // back to the caller's stream
@@ -421,6 +492,15 @@ int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *
   return MGCMT_OK;
 }
 
+int mgcmt_slabblock_set_smoother(mgcmt_slabblock_t *b, int smoother, double omega) {
+  if (!b) return set_error(MGCMT_ERR_ARG, "null argument");
+  if (smoother != MGCMT_SMOOTH_WJACOBI && smoother != MGCMT_SMOOTH_RBGS)
+    return set_error(MGCMT_ERR_ARG, "the slab block smooths with weighted Jacobi or red-black Gauss-Seidel");
+  b->smoother = smoother;
+  b->omega = omega;
+  return MGCMT_OK;
+}
+
 int mgcmt_slabblock_profile(mgcmt_slabblock_t *b, int on) {
   if (!b) return set_error(MGCMT_ERR_ARG, "null argument");
   b->profile = on != 0;
@@ -429,7 +509,7 @@ int mgcmt_slabblock_profile(mgcmt_slabblock_t *b, int on) {
 
 int mgcmt_slabblock_profile_read(mgcmt_slabblock_t *b, int with_lam, double *ms_comm, double *ms_comp, int *nstage_out) {
   if (!b || !ms_comm || !ms_comp || !nstage_out) return set_error(MGCMT_ERR_ARG, "null argument");
-  const int nstage = 2 * b->nlev + 1 + ((with_lam && !b->fused_rq) ? 1 : 0);
+  const int nstage = (int)build_phases(b, with_lam && !b->fused_rq).size();
   if ((int)b->prof.size() < 2 * nstage + 1) return set_error(MGCMT_ERR_STATE, "no profiled cycle (lock-step form, profile on)");
   CU(cudaDeviceSynchronize());
   for (int i = 0; i < nstage; ++i) {

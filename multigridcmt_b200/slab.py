@@ -1,7 +1,7 @@
 """Row-slab decomposition of the 2-D V-cycle across GPUs.
 
 One process per GPU.  Rank r owns the rows [r N/G, (r+1) N/G) of the finest grid and the matching rows of
-every *distributed* level; each slab array carries HALO = 6 rows above and below its owned rows.  A V(4,4)
+every *distributed* level; each slab array carries HALO = 10 rows above and below its owned rows.  A V(4,4)
 leg is ONE fused kernel per level (csrc/fused.cu: 4 sweeps + transfer), whose dependency cone is exactly
 those 6 rows -- so halos are exchanged once per leg, not once per sweep:
 
@@ -27,8 +27,8 @@ import numpy as np
 from . import _lib
 from .operators import SeparableOperator
 
-HALO = 6
-MODE_DOWN, MODE_DOWN_ZERO, MODE_UP = 1, 2, 3
+HALO = 10   # rows: the dependency cone of the longest fused leg (8 Gauss-Seidel colour stages + transfer = 10; Jacobi: 6)
+MODE_SMOOTH, MODE_DOWN, MODE_DOWN_ZERO, MODE_UP = 0, 1, 2, 3
 
 
 def plan_levels(n, world, gather_cols=2048, min_own_rows=64):
@@ -181,11 +181,18 @@ class SlabVCycle:
 
     states: one _RankState per rank handled by THIS process (all ranks with LocalComm, one with TorchDistComm)."""
 
-    def __init__(self, op: SeparableOperator, world, comm, ranks, lowest_level=8, gather_cols=2048, omega=2. / 3.):
+    def __init__(self, op: SeparableOperator, world, comm, ranks, lowest_level=8, gather_cols=2048, omega=None,
+                 smoother="wjacobi"):
+        """smoother: "wjacobi" (omega default 2/3) or "rbgs" (red-black / four-colour Gauss-Seidel, omega default 1: BASELINE
+        config 3's smoother).  Red-black legs: one pass of 4 sweeps on the 5-point level, two passes of 2 sweeps on the
+        9-point levels with a halo exchange of the intermediate iterate between them."""
         if op.nrows != op.ncols:
             raise ValueError("slab decomposition is for square 2-D grids")
+        if smoother not in ("wjacobi", "rbgs"):
+            raise ValueError("slab smoother must be wjacobi or rbgs")
         self.op, self.world, self.comm = op, world, comm
-        self.omega = omega
+        self.gs = (smoother == "rbgs")
+        self.omega = (1.0 if self.gs else 2. / 3.) if omega is None else omega
         self.nlev = plan_levels(op.ncols, world, gather_cols)
         if self.nlev < 1:
             raise ValueError("grid too small to decompose over %d ranks (use the single-GPU path)" % world)
@@ -196,10 +203,12 @@ class SlabVCycle:
             s.close()
 
     # -- helpers ------------------------------------------------------------------------------------
-    def _leg(self, st, l, mode, vin, f, vout, e=None, rc=None):
+    def _leg(self, st, l, mode, vin, f, vout, e=None, rc=None, nu=4):
         torch = _lib.require_cuda()
         p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
-        _lib.check(_lib.load().mgcmt_fused_leg(st.slab, l, mode, 4, float(self.shift), float(self.omega), p(vin), p(f),
+        if self.gs:
+            mode |= 32
+        _lib.check(_lib.load().mgcmt_fused_leg(st.slab, l, mode, nu, float(self.shift), float(self.omega), p(vin), p(f),
                                                p(vout), p(e), p(rc), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def _exchange(self, name, l):
@@ -240,34 +249,54 @@ class SlabVCycle:
         torch = _lib.require_cuda()
         lib = _lib.load()
         nl = self.nlev
+        gs = self.gs
+        st0 = self.states[0]
         self._exchange("f", 0)
         if not v0_is_zero:
             self._exchange("v", 0)
+        cur = [None] * nl     # name of the array that holds the smoothed iterate of level l after its down leg
         for l in range(nl):
             last = (l + 1 == nl)
-            for st in self.states:
-                mode = MODE_DOWN_ZERO if (l > 0 or v0_is_zero) else MODE_DOWN
-                self._leg(st, l, mode, None if mode == MODE_DOWN_ZERO else st.v[l], st.f[l], st.tmp[l],
-                          rc=(st.fg if last else st.f[l + 1]))
+            zero = (l > 0 or v0_is_zero)
+            if gs and l > 0:
+                # 9-point level, red-black: 2 sweeps from zero, exchange, 2 sweeps + residual + restriction
+                for st in self.states:
+                    st.v[l].zero_()
+                    self._leg(st, l, MODE_SMOOTH, st.v[l], st.f[l], st.tmp[l], nu=2)
+                self._exchange("tmp", l)
+                for st in self.states:
+                    self._leg(st, l, MODE_DOWN, st.tmp[l], st.f[l], st.v[l], rc=(st.fg if last else st.f[l + 1]), nu=2)
+                cur[l] = "v"
+            else:
+                for st in self.states:
+                    mode = MODE_DOWN_ZERO if zero else MODE_DOWN
+                    self._leg(st, l, mode, None if zero else st.v[l], st.f[l], st.tmp[l],
+                              rc=(st.fg if last else st.f[l + 1]))
+                cur[l] = "tmp"
             if last:
-                st0 = self.states[0]
                 self.comm.allgather_rows([st.fg for st in self.states], st0.own_rows(nl), st0.ncols(nl))
             else:
                 self._exchange("f", l + 1)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for st in self.states:   # replicated coarse part (identical on every rank)
-            _lib.check(lib.mgcmt_vcycle_from(st.coarse, nl, float(shift), _lib.SMOOTH_WJACOBI, float(self.omega),
-                                             C.c_void_p(st.vg.data_ptr()), C.c_void_p(st.fg.data_ptr()), stream))
-        st0 = self.states[0]
+            _lib.check(lib.mgcmt_vcycle_from(st.coarse, nl, float(shift), _lib.SMOOTH_RBGS if gs else _lib.SMOOTH_WJACOBI,
+                                             float(self.omega), C.c_void_p(st.vg.data_ptr()), C.c_void_p(st.fg.data_ptr()), stream))
         for l in range(nl - 1, -1, -1):
             last = (l + 1 == nl)
             # halos of the smoothed iterate and (below the last slab level) of the coarse correction: one NCCL group
-            items = [([st.tmp[l] for st in self.states], st0.own_rows(l), st0.ncols(l))]
+            items = [([getattr(st, cur[l])[l] for st in self.states], st0.own_rows(l), st0.ncols(l))]
             if not last:
                 items.append(([st.v[l + 1] for st in self.states], st0.own_rows(l + 1), st0.ncols(l + 1)))
             self.comm.exchange_many(items)
-            for st in self.states:
-                self._leg(st, l, MODE_UP, st.tmp[l], st.f[l], st.v[l], e=(st.vg if last else st.v[l + 1]))
+            if gs and l > 0:
+                for st in self.states:   # iterate is in v[l]: correction + 2 sweeps -> tmp[l]; exchange; 2 sweeps -> v[l]
+                    self._leg(st, l, MODE_UP, st.v[l], st.f[l], st.tmp[l], e=(st.vg if last else st.v[l + 1]), nu=2)
+                self._exchange("tmp", l)
+                for st in self.states:
+                    self._leg(st, l, MODE_SMOOTH, st.tmp[l], st.f[l], st.v[l], nu=2)
+            else:
+                for st in self.states:
+                    self._leg(st, l, MODE_UP, st.tmp[l], st.f[l], st.v[l], e=(st.vg if last else st.v[l + 1]))
 
     def rayleigh(self, x=None, sync=True):
         """x^T H x and x^T x of a finest-level slab vector (default st.v[0]); its halo rows are refreshed first.
@@ -399,6 +428,15 @@ def vcycle_block(svs, shifts, f0s, v0s, lam=None, streams=None):
 
     sv0 = svs[0]
     comm, nl, st0 = sv0.comm, sv0.nlev, sv0.states[0]
+    if sv0.gs:
+        # red-black legs: the lock-step phase table lives in the native driver (NativeSlabBlock); here one cycle at a time
+        for c, sv in enumerate(svs):
+            sv.vcycle(shifts[c], v0_is_zero=True, f0=f0s[c], v0=v0s[c])
+            if lam is not None:
+                sv.rayleigh(v0s[c], sync=False)
+                for i, st in enumerate(sv.states):
+                    lam[i][c].copy_(st.scal[:2])
+        return
     saved = []
     for c, sv in enumerate(svs):
         sv.shift = shifts[c]
@@ -485,14 +523,19 @@ class NativeSlabBlock:
     initialised (it carries the 128-byte NCCL id from rank 0 to the others, nothing else).  Bit-for-bit the same
     results as the Python-driven path (same kernels, same order): tools/check_native_slab.py."""
 
-    def __init__(self, op: SeparableOperator, world, rank, k, lowest_level=8, gather_cols=2048, omega=2. / 3.,
-                 stagger=False):
+    def __init__(self, op: SeparableOperator, world, rank, k, lowest_level=8, gather_cols=2048, omega=None,
+                 stagger=False, smoother="wjacobi"):
         torch = _lib.require_cuda()
         lib = _lib.load()
         if op.nrows != op.ncols:
             raise ValueError("slab decomposition is for square 2-D grids")
         self.op, self.world, self.rank, self.k = op, int(world), int(rank), int(k)
         self.N = op.ncols
+        if smoother not in ("wjacobi", "rbgs"):
+            raise ValueError("slab smoother must be wjacobi or rbgs")
+        self.smoother = smoother
+        if omega is None:
+            omega = 1.0 if smoother == "rbgs" else 2. / 3.
         self.nlev = plan_levels(self.N, world, gather_cols)
         if self.nlev < 1:
             raise ValueError("grid too small to decompose over %d ranks (use the single-GPU path)" % world)
@@ -518,6 +561,8 @@ class NativeSlabBlock:
         _lib.check(lib.mgcmt_slabblock_create(self.comm, self.comm2, self.world, self.rank, self.N, self.nlev, int(lowest_level),
                                               self.k, hp(op.row[0]), hp(op.row[1]), hp(op.row[2]), hp(op.col[0]), hp(op.col[1]),
                                               hp(op.col[2]), float(omega), stream, C.byref(self.handle)))
+        _lib.check(lib.mgcmt_slabblock_set_smoother(self.handle, _lib.SMOOTH_RBGS if smoother == "rbgs" else _lib.SMOOTH_WJACOBI,
+                                                    float(omega)))
         self._ptrs = (C.c_void_p * self.k)
         self._shifts = (C.c_double * self.k)
 
@@ -562,11 +607,17 @@ class NativeSlabBlock:
 
     def profile_read(self, with_lam=True):
         """per-stage milliseconds of the last profiled cycle: list of (stage name, comm ms, compute ms)"""
-        n = 2 * self.nlev + 2
+        n = 4 * self.nlev + 2
         comm, comp, ns = (C.c_double * n)(), (C.c_double * n)(), C.c_int()
         _lib.check(_lib.load().mgcmt_slabblock_profile_read(self.handle, 1 if with_lam else 0, comm, comp, C.byref(ns)))
-        names = (["down L%d" % l for l in range(self.nlev)] + ["coarse (replicated)"]
-                 + ["up L%d" % l for l in range(self.nlev - 1, -1, -1)] + ["rayleigh (separate pass)"])
+        two = lambda l: self.smoother == "rbgs" and l > 0      # 9-point red-black legs are two passes
+        names = []
+        for l in range(self.nlev):
+            names += ["down L%d pass 1" % l, "down L%d pass 2" % l] if two(l) else ["down L%d" % l]
+        names.append("coarse (replicated)")
+        for l in range(self.nlev - 1, -1, -1):
+            names += ["up L%d pass 1" % l, "up L%d pass 2" % l] if two(l) else ["up L%d" % l]
+        names.append("rayleigh (separate pass)")
         return [(names[i], comm[i], comp[i]) for i in range(ns.value)]
 
     def gram(self, W):

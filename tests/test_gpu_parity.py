@@ -1092,6 +1092,69 @@ def test_shift_method_object_1d_and_start_block(o):
     assert np.all(np.abs(lam[-1] - [well_eigenvalue_1d(N, k) for k in modes]) < 1e-3)
 
 
+@pytest.mark.parametrize("N,world,gather", [(512, 2, 128), (1024, 4, 256), (1024, 8, 512)])
+def test_slab_rbgs_vcycle_equals_single_gpu(T, prod, N, world, gather):
+    """Red-black Gauss-Seidel on the row-slab path (BASELINE config 3's smoother): 4 sweeps per leg on the 5-point level
+    in one pass (halo 10 rows = 8 colour stages + residual + restriction), two passes of 2 sweeps with an exchange in
+    between on the 9-point levels.  Same sweeps in the same order as the undecomposed cycle."""
+    from multigridcmt_b200.slab import LocalComm, SlabVCycle
+    sm, s, _ = prod
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    f = rand(N * N, 13)
+    v0 = rand(N * N, 14)
+    shift = 4.38639582
+    sv = SlabVCycle(H, world, LocalComm(world), range(world), lowest_level=8, gather_cols=gather, smoother="rbgs")
+    try:
+        sv.scatter("f", f)
+        sv.vcycle(shift, v0_is_zero=True)
+        got = sv.gather_local("v")
+        want = s.vcycle(np.zeros(N * N), f.copy(), H, sm, shift=shift, lowest_level=8, dimension="2d", smoother=s.rbgs)
+        assert rel(got, want) < 1e-12
+        sv.scatter("f", f); sv.scatter("v", v0)
+        sv.vcycle(shift, v0_is_zero=False)
+        got = sv.gather_local("v")
+        want = s.vcycle(v0.copy(), f.copy(), H, sm, shift=shift, lowest_level=8, dimension="2d", smoother=s.rbgs)
+        assert rel(got, want) < 1e-12
+    finally:
+        sv.close()
+
+
+def test_native_slab_block_rbgs_single_rank(T, prod):
+    """the native driver's red-black phase table (csrc/slab_block.cu build_phases): same results as the undecomposed
+    RB-GS cycle and as the Python-driven slab path, Rayleigh sums from the fused last up leg"""
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import get_hierarchy
+    from multigridcmt_b200.slab import LocalComm, NativeSlabBlock, SlabVCycle
+    sm, solver, proc = prod
+    N, k = 512, 4
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    shifts = [1.7, 4.3, 4.4, 7.0]
+    f_host = [rand(N * N, 60 + c) - 0.5 for c in range(k)]
+    h = get_hierarchy(H, 8)
+    for stagger in (False, True):
+        nb = NativeSlabBlock(H, 1, 0, k, lowest_level=8, gather_cols=128, smoother="rbgs", stagger=stagger)
+        F, W = nb.new_block(), nb.new_block()
+        lam = T.zeros(k, 2, dtype=T.float64, device="cuda")
+        for c in range(k):
+            nb.owned(F[c]).copy_(dev(T, f_host[c]).view(N, N))
+        nb.cycle(shifts, F, W, lam)
+        T.cuda.synchronize()
+        sv = SlabVCycle(H, 1, LocalComm(1), [0], lowest_level=8, gather_cols=128, smoother="rbgs")
+        for c in range(k):
+            v = T.zeros(N * N, dtype=T.float64, device="cuda")
+            h.vcycle(shifts[c], 4, 4, _lib.SMOOTH_RBGS, 1.0, v, dev(T, f_host[c]), v0_is_zero=True)
+            w = nb.owned(W[c]).reshape(-1)
+            assert rel(w.cpu().numpy(), v.cpu().numpy()) < 1e-13
+            out2 = T.zeros(2, dtype=T.float64, device="cuda")
+            h.rayleigh(0, v, out2)
+            assert np.allclose(lam[c].cpu().numpy(), out2.cpu().numpy(), rtol=1e-12)
+            sv.scatter("f", f_host[c])
+            sv.vcycle(shifts[c], v0_is_zero=True)
+            assert T.equal(nb.owned(W[c]), sv.states[0].owned(sv.states[0].v[0], 0))
+        sv.close()
+        nb.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # natively driven slab block (csrc/slab_block.cu), one rank: same numbers as the Python-driven slab path and as the
 # undecomposed V-cycle (the NCCL exchanges themselves are checked on 2+ GPUs by tools/check_native_slab.py)
@@ -1215,8 +1278,9 @@ def test_multi_gpu_slab_matches_single_gpu():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(root, "tools", "check_slab_vs_single.py"), "2048", "256"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    for smoother in ("wjacobi", "rbgs"):
+        r = subprocess.run(cmd + [smoother], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (smoother, r.stdout[-2000:], r.stderr[-2000:])
 
 
 def test_config1_rqmg_deflation_1024(prod, o):

@@ -1,7 +1,7 @@
 """Multi-GPU parity: the natively driven row-slab block (real NCCL halo exchange, one rank per GPU) against the
 undecomposed single-GPU V-cycle on identical inputs.  Exit code 0 iff every rank's owned rows agree to 1e-12 relative
 and the Rayleigh sums to 1e-12.
-  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/check_slab_vs_single.py [N] [gather_cols]"""
+  torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/check_slab_vs_single.py [N] [gather_cols] [wjacobi|rbgs]"""
 import json
 import os
 import sys
@@ -24,10 +24,12 @@ def main():
     lib = _lib.load()
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
     gather = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    smoother = sys.argv[3] if len(sys.argv) > 3 else "wjacobi"
+    code, omega = (_lib.SMOOTH_RBGS, 1.0) if smoother == "rbgs" else (_lib.SMOOTH_WJACOBI, 2. / 3.)
     k = 4
     H = (-1.0 / np.pi ** 2) * MGCMTStencilMaker().laplacian(N, "2d", matrix_free=True)
     shifts = [1.7665, 4.3863, 4.3864, 7.0062]
-    nb = NativeSlabBlock(H, world, rank, k, lowest_level=8, gather_cols=gather)
+    nb = NativeSlabBlock(H, world, rank, k, lowest_level=8, gather_cols=gather, smoother=smoother, stagger=True)
     g = torch.Generator(device="cuda"); g.manual_seed(11)          # the same full right-hand sides on every rank
     full = torch.rand(k, N, N, dtype=torch.float64, device="cuda", generator=g) - 0.5
     F, W = nb.new_block(), nb.new_block()
@@ -42,7 +44,7 @@ def main():
     for c in range(k):
         w = torch.zeros(N * N, dtype=torch.float64, device="cuda")
         out = torch.zeros(2, dtype=torch.float64, device="cuda")
-        _lib.check(lib.mgcmt_vcycle_rq(h.handle, shifts[c], 4, 4, _lib.SMOOTH_WJACOBI, 2. / 3., _ptr(w), _ptr(full[c].reshape(-1)), 1,
+        _lib.check(lib.mgcmt_vcycle_rq(h.handle, shifts[c], 4, 4, code, omega, _ptr(w), _ptr(full[c].reshape(-1)), 1,
                                        _ptr(out), _stream_ptr(torch)))
         mine = nb.owned(W[c])
         ref = w.view(N, N)[nb.begin0:nb.begin0 + nb.own0]
@@ -53,7 +55,7 @@ def main():
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     ok = bool(res[0] <= 1e-12 and res[1] <= 1e-12)
     if rank == 0:
-        print(json.dumps({"world": world, "N": N, "slab_levels": nb.nlev, "max_rel_diff_owned_rows": float(res[0]),
+        print(json.dumps({"world": world, "N": N, "smoother": smoother, "slab_levels": nb.nlev, "max_rel_diff_owned_rows": float(res[0]),
                           "max_rel_diff_rayleigh_sums": float(res[1]), "bit_identical": bool(res[2] == 0.0), "ok": ok}), flush=True)
     nb.close()
     dist.destroy_process_group()
