@@ -151,6 +151,15 @@ int mgcmt_coarse_solve(mgcmt_hier_t *h, double shift, const double *d_f, double 
 int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega,
                  double *d_v, const double *d_f, int v0_is_zero, void *stream);
 
+/* The loop body of the shift-method drivers for HOST vectors (2DPotGS.py:93-95: one zero-start V-cycle per eigenvector,
+ * numpy in, numpy out): v_host[c] = Vcycle(0, f_host[c]; shifts[c]) for c < k, all vectors of the finest level's length.
+ * The k cycles are independent, so their PCIe copies are pipelined against each other: the upload of vector c+1 and the
+ * download of vector c-1 run on two internal copy streams beside cycle c on `stream` (three rotating device slots owned
+ * by the hierarchy).  Host buffers may be pageable or page-locked; page-locked ones move at full PCIe rate in both
+ * directions at once.  Returns when every v_host[c] is complete (the call synchronises, like the reference's). */
+int mgcmt_vcycle_host_block(mgcmt_hier_t *h, int k, const double *shifts, int nu1, int nu2, int smoother, double omega,
+                            const double *const *f_host, double *const *v_host, void *stream);
+
 /* mgcmt_vcycle followed by the Rayleigh quotient of the result: d_out2[0] = w^T A_0 w, d_out2[1] = w^T w (the
  * `w/||w||` + `v^T H v` the drivers do after every cycle, 2DPotGS.py:96,103).  On 2-D Jacobi cycles with nu2 = 4 the
  * sums are taken inside the finest up leg (an extra pipeline stage evaluates A w on the final iterate), so no extra

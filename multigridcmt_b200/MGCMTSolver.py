@@ -30,7 +30,7 @@ import numpy as np
 from . import _lib
 from .MGCMTProcessor import MGCMTProcessor
 from .MGCMTStencilMaker import MGCMTStencilMaker
-from .hierarchy import (_ptr, _stream_ptr, get_hierarchy, is_device_tensor, to_device, to_host)
+from .hierarchy import (_ptr, _stream_ptr, get_hierarchy, is_device_tensor, pinned_result, to_device, to_host)
 from .operators import SeparableOperator, UnsupportedOperator, recognise
 from .banded import (BandedOperator, get_banded_hierarchy, recognise_banded, to_device_complex)
 
@@ -256,6 +256,13 @@ class MGCMTSolver:
         if isinstance(op, BandedOperator):
             return self._vcycle_banded(op, np.zeros(n) if zero_start else v0, f, nu1, nu2, code, omega, shift, low)
         h = get_hierarchy(op, low)
+        if zero_start and not dev_in and h.num_levels > 1 and n >= (1 << 16):
+            # host vector in, host vector out: one-vector form of the pipelined block call -- a pageable f (a plain numpy
+            # array) is staged to the device by several host threads instead of the driver's single-threaded bounce copy
+            f1 = np.ascontiguousarray(np.asarray(f, dtype=np.float64).reshape(-1))
+            buf, out = pinned_result(n)
+            h.vcycle_host_block([shift], nu1, nu2, code, omega, [f1], [out])
+            return out
         fd = to_device(f)
         if zero_start:
             v = _lib.require_cuda().empty(n, dtype=fd.dtype, device=fd.device)
@@ -271,6 +278,43 @@ class MGCMTSolver:
             return v.reshape(n, 1) if coarsest_direct else v
         out = to_host(v)
         return out.reshape(n, 1) if coarsest_direct else out
+
+    # ------------------------------------------------------------------------------------------
+    # the loop body of the shift-method drivers as one call (2DPotGS.py:93-95: `w0 = zeros; w = vcycle(w0, v_i, H, ...,
+    # shift=shifts[i])` for every eigenvector i).  The cycles are independent, so with host arrays the upload of vector
+    # i+1 and the download of vector i-1 ride beside cycle i (mgcmt_vcycle_host_block) instead of 2k serial PCIe copies.
+    # ------------------------------------------------------------------------------------------
+    def vcycle_many(self, fs, A, stencil_maker, shifts, nu1=4, nu2=4, smoother=None, lowest_level=2, dimension="1d"):
+        """[vcycle(ZeroVector(n), fs[i], A, stencil_maker, shift=shifts[i], ...) for i in range(len(fs))], same results
+        bit for bit.  fs: sequence of vectors (or the columns of an n x k array); returns a list of arrays."""
+        if isinstance(fs, np.ndarray) and fs.ndim == 2:
+            fs = [np.ascontiguousarray(fs[:, i]) for i in range(fs.shape[1])]
+        fs = list(fs)
+        shifts = [float(x) for x in np.asarray(shifts, dtype=float).reshape(-1)]
+        if len(shifts) != len(fs):
+            raise ValueError("vcycle_many: %d right-hand sides but %d shifts" % (len(fs), len(shifts)))
+        if not fs:
+            return []
+        n = int(np.prod(fs[0].shape))
+        code, omega = self._smoother_code(smoother)
+        one_by_one = lambda: [self.vcycle(ZeroVector(n), f, A, stencil_maker, nu1=nu1, nu2=nu2, smoother=smoother, shift=sh,
+                                          lowest_level=lowest_level, dimension=dimension) for f, sh in zip(fs, shifts)]
+        g = int(round(np.sqrt(n))) if dimension == "2d" else n
+        low = int(lowest_level)
+        if (any(is_device_tensor(f) for f in fs) or any(int(np.prod(f.shape)) != n for f in fs) or n < (1 << 16)
+                or (dimension == "2d" and g * g != n) or g < 2 or (g & (g - 1)) or (low & (low - 1)) or low > g or low < 2):
+            return one_by_one()      # device tensors, small or ill-sized input: nothing to pipeline / the checks of vcycle
+        self._check_stencil_maker(stencil_maker)
+        op = self._route(A, dimension, fs[0], fs[0])
+        if isinstance(op, BandedOperator):
+            return one_by_one()
+        h = get_hierarchy(op, low)
+        if h.num_levels == 1:
+            return one_by_one()
+        f_host = [np.ascontiguousarray(np.asarray(f, dtype=np.float64).reshape(-1)) for f in fs]
+        outs = [pinned_result(n) for _ in fs]
+        h.vcycle_host_block(shifts, nu1, nu2, code, omega, f_host, [o[1] for o in outs])
+        return [o[1] for o in outs]
 
     # ------------------------------------------------------------------------------------------
     # two-grid cycle (MGCMTSolver.py:331-371) == a 2-level V-cycle with exact coarse solve

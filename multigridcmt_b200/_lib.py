@@ -39,6 +39,7 @@ SIGNATURES = {
     "mgcmt_hier_create_slab": (_I, [C.POINTER(_P), _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "mgcmt_hier_level_buffers": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "mgcmt_vcycle_rq": (_I, [_P, _D, _I, _I, _I, _D, _P, _P, _I, _P, _P]),
+    "mgcmt_vcycle_host_block": (_I, [_P, _I, _P, _I, _I, _I, _D, _P, _P, _P]),
     "mgcmt_vcycle_from": (_I, [_P, _I, _D, _I, _D, _P, _P, _P]),
     "mgcmt_slab_rayleigh": (_I, [_P, _I, _P, _P, _P]),
     "mgcmt_slab_up_rq": (_I, [_P, _I, _D, _D, _P, _P, _P, _P, _P, _P]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmgcmt_b200.so")
-SOURCES = ["stencil.cu", "fused.cu", "fused_uni.cu", "fused_uni9.cu", "tile.cu", "transfer.cu", "gs.cu", "coarse.cu", "reduce.cu", "rq.cu", "band.cu", "api.cu", "band_api.cu", "slab_block.cu"]
+SOURCES = ["stencil.cu", "fused.cu", "fused_uni.cu", "fused_uni9.cu", "tile.cu", "transfer.cu", "gs.cu", "coarse.cu", "reduce.cu", "rq.cu", "band.cu", "api.cu", "band_api.cu", "slab_block.cu", "staging.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 print(log)
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"], capture_output=True, text=True)
+        r = subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl", "-lpthread"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     return LIB

@@ -128,6 +128,14 @@ struct mgcmt_hier {
   std::vector<InvEntry> invs;
   uint64_t clock = 0;
   int *status = nullptr;  // device flag for the Gauss-Jordan
+  // mgcmt_vcycle_host_block: three rotating (f, v) device slots, a copy-in and a copy-out stream, events per slot
+  struct HostPipe {
+    double *f[3] = {nullptr, nullptr, nullptr}, *v[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t uploaded[3] = {nullptr, nullptr, nullptr}, cycled[3] = {nullptr, nullptr, nullptr},
+                downloaded[3] = {nullptr, nullptr, nullptr};
+    bool ready = false;
+  } pipe;
 };
 
 namespace {
@@ -667,6 +675,15 @@ int mgcmt_hier_destroy(mgcmt_hier_t *h) {
     cudaFree(L.zrow);
   }
   for (auto &e : h->invs) cudaFree(e.inv);
+  for (int i = 0; i < 3; ++i) {
+    cudaFree(h->pipe.f[i]);
+    cudaFree(h->pipe.v[i]);
+    if (h->pipe.uploaded[i]) cudaEventDestroy(h->pipe.uploaded[i]);
+    if (h->pipe.cycled[i]) cudaEventDestroy(h->pipe.cycled[i]);
+    if (h->pipe.downloaded[i]) cudaEventDestroy(h->pipe.downloaded[i]);
+  }
+  if (h->pipe.in) cudaStreamDestroy(h->pipe.in);
+  if (h->pipe.out) cudaStreamDestroy(h->pipe.out);
   cudaFree(h->rq_partials);
   cudaFree(h->small_partials);
   cudaFree(h->status);
@@ -817,6 +834,8 @@ int mgcmt_set_option(const char *name, int value) {
   if (!strcmp(name, "tile_max_cols")) { g_opt_tile_max_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tail_max_cols")) { g_opt_tail_max_cols = value; return MGCMT_OK; }
   if (!strcmp(name, "tile_gs_max_cols")) { g_opt_tile_gs_max_cols = value; return MGCMT_OK; }
+  if (!strcmp(name, "stage_threads")) { g_stage_threads = value; return MGCMT_OK; }
+  if (!strcmp(name, "stage_chunk_kib")) { g_stage_chunk_kib = value; return MGCMT_OK; }
   if (!strcmp(name, "coarse_banded")) {
     if (value < 0 || value > 2) return fail(MGCMT_ERR_ARG, "coarse_banded must be 0, 1 or 2 (auto)");
     g_opt_coarse_banded = value;
@@ -903,6 +922,57 @@ int mgcmt_vcycle(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, 
   if (nu1 < 0 || nu2 < 0) return fail(MGCMT_ERR_ARG, "negative sweep count");
   if (h->slab || h->first_work > 0) return fail(MGCMT_ERR_STATE, "this hierarchy has no full finest level (slab piece / coarse part)");
   return vcycle_level(h, 0, shift, nu1, nu2, smoother, omega, d_v, d_f, v0_is_zero != 0, (cudaStream_t)stream);
+}
+
+int mgcmt_vcycle_host_block(mgcmt_hier_t *h, int k, const double *shifts, int nu1, int nu2, int smoother, double omega,
+                            const double *const *f_host, double *const *v_host, void *stream) {
+  if (!h) return fail(MGCMT_ERR_ARG, "null hierarchy");
+  if (k < 0 || (k > 0 && (!shifts || !f_host || !v_host))) return fail(MGCMT_ERR_ARG, "bad block arguments");
+  if (nu1 < 0 || nu2 < 0) return fail(MGCMT_ERR_ARG, "negative sweep count");
+  if (h->slab || h->first_work > 0) return fail(MGCMT_ERR_STATE, "this hierarchy has no full finest level (slab piece / coarse part)");
+  for (int c = 0; c < k; ++c)
+    if (!f_host[c] || !v_host[c] || f_host[c] == v_host[c]) return fail(MGCMT_ERR_ARG, "need distinct non-null host vectors");
+  if (k == 0) return MGCMT_OK;
+  const size_t n = (size_t)h->lev[0].dev.nrows * (size_t)h->lev[0].dev.ncols;
+  const size_t bytes = n * sizeof(double);
+  mgcmt_hier::HostPipe &P = h->pipe;
+  const int nslot = k < 3 ? k : 3;
+  if (!P.ready) {
+    CU(cudaStreamCreateWithFlags(&P.in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&P.out, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) {
+      CU(cudaEventCreateWithFlags(&P.uploaded[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&P.cycled[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&P.downloaded[i], cudaEventDisableTiming));
+    }
+    P.ready = true;
+  }
+  for (int i = 0; i < nslot; ++i) {
+    if (!P.f[i]) CU(cudaMalloc(&P.f[i], bytes));
+    if (!P.v[i]) CU(cudaMalloc(&P.v[i], bytes));
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  // upload of vector c+1 and download of vector c-1 run beside cycle c (PCIe is full duplex); a slot is reused once its
+  // previous result has left the device
+  for (int c = 0; c < k; ++c) {
+    const int i = c % 3;
+    if (c >= 3) CU(cudaStreamWaitEvent(P.in, P.downloaded[i], 0));
+    CU(staged_upload(P.f[i], f_host[c], bytes, P.in));   // pageable sources: threaded staging through page-locked chunks
+    CU(cudaEventRecord(P.uploaded[i], P.in));
+    CU(cudaStreamWaitEvent(s, P.uploaded[i], 0));
+    int rc = vcycle_level(h, 0, shifts[c], nu1, nu2, smoother, omega, P.v[i], P.f[i], true, s);
+    if (rc) {
+      cudaStreamSynchronize(P.in);
+      cudaStreamSynchronize(P.out);
+      return rc;
+    }
+    CU(cudaEventRecord(P.cycled[i], s));
+    CU(cudaStreamWaitEvent(P.out, P.cycled[i], 0));
+    CU(cudaMemcpyAsync(v_host[c], P.v[i], bytes, cudaMemcpyDeviceToHost, P.out));
+    CU(cudaEventRecord(P.downloaded[i], P.out));
+  }
+  CU(cudaStreamSynchronize(P.out));   // every result is in host memory (the last download follows all cycles)
+  return MGCMT_OK;
 }
 
 int mgcmt_vcycle_rq(mgcmt_hier_t *h, double shift, int nu1, int nu2, int smoother, double omega, double *d_v,

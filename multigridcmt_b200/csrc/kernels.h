@@ -164,4 +164,10 @@ cudaError_t launch_band_lower_solve(const BandDev &L, double shift, double wl, d
 cudaError_t launch_band_inverse(const BandDev &L, double shift, double *aug, int *status, cudaStream_t s);
 cudaError_t launch_band_gemv(int n, const double *aug, const double *f, double *y, cudaStream_t s);
 
+// staging.cu: upload of pageable host memory through page-locked chunks filled by several host threads (returns when every
+// chunk is enqueued on `stream`); page-locked sources go straight to cudaMemcpyAsync
+extern int g_stage_threads, g_stage_chunk_kib;
+bool host_pointer_is_pinned(const void *p);
+cudaError_t staged_upload(void *d_dst, const void *h_src, size_t bytes, cudaStream_t stream);
+
 }  // namespace mgcmt

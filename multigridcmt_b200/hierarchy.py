@@ -126,6 +126,21 @@ class Hierarchy:
                                             _stream_ptr(torch)))
         return v
 
+    def vcycle_host_block(self, shifts, nu1, nu2, smoother, omega, f_host, v_host):
+        """zero-start cycles for k HOST vectors with their PCIe copies pipelined against each other
+        (mgcmt_vcycle_host_block); f_host / v_host: lists of contiguous float64 numpy arrays of the finest level's length"""
+        import ctypes as C
+        torch = _lib.require_cuda()
+        k = len(f_host)
+        for a in list(f_host) + list(v_host):
+            if a.dtype != np.float64 or a.size != self.n or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("vcycle_host_block: vectors must be contiguous float64 of length %d" % self.n)
+        fp = (C.c_void_p * k)(*[a.ctypes.data for a in f_host])
+        vp = (C.c_void_p * k)(*[a.ctypes.data for a in v_host])
+        sh = (C.c_double * k)(*[float(x) for x in shifts])
+        _lib.check(_lib.load().mgcmt_vcycle_host_block(self.handle, k, sh, int(nu1), int(nu2), int(smoother), float(omega),
+                                                       fp, vp, _stream_ptr(torch)))
+
     def fused_leg(self, level, mode, nu, shift, omega, v_in, f, v_out, e_coarse=None, r_coarse=None):
         torch = _lib.require_cuda()
         _lib.check(_lib.load().mgcmt_fused_leg(self.handle, level, int(mode), int(nu), float(shift), float(omega),
@@ -214,6 +229,14 @@ def to_host(t):
     buf.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return np.asarray(_PinnedOwner(buf))
+
+
+def pinned_result(n):
+    """(tensor, numpy view the caller will own) of n float64 in page-locked memory, recycled like to_host's buffers"""
+    torch = _lib.require_cuda()
+    free = _PINNED_FREE.get(n)
+    buf = free.pop() if free else torch.empty(n, dtype=torch.float64, pin_memory=True)
+    return buf, np.asarray(_PinnedOwner(buf))
 
 
 def lowest_for_apply(op):

@@ -747,6 +747,64 @@ def test_full_size_properties(T, prod, N):
     assert abs(num / den - lam11) < 1e-6
 
 
+@pytest.mark.parametrize("smoother", ["wjacobi", "rbgs"])
+def test_vcycle_many_equals_separate_calls(T, prod, smoother):
+    """MGCMTSolver.vcycle_many / mgcmt_vcycle_host_block: the drivers' loop body for host vectors with the PCIe copies of
+    the k independent cycles pipelined (three rotating device slots: k = 5 reuses them).  Same kernels, same order per
+    vector: identical bits to one vcycle call per vector; pageable and page-locked inputs; inputs untouched."""
+    from multigridcmt_b200 import ZeroVector
+    sm, s, _ = prod
+    N = 512
+    n = N * N
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    kw = {"smoother": s.rbgs} if smoother == "rbgs" else {}
+    shifts = [1.7, 4.3, 4.4, 7.0, 9.1]
+    for k in (1, 2, 5):
+        fs = [rand(n, 70 + c) - 0.5 for c in range(k)]
+        keep = [f.copy() for f in fs]
+        want = [s.vcycle(ZeroVector(n), f.copy(), H, sm, shift=shifts[c], lowest_level=8, dimension="2d", **kw)
+                for c, f in enumerate(fs)]
+        got = s.vcycle_many(fs, H, sm, shifts[:k], lowest_level=8, dimension="2d", **kw)
+        assert len(got) == k
+        for c in range(k):
+            assert got[c].shape == (n,) and np.array_equal(got[c], want[c])
+            assert np.array_equal(fs[c], keep[c])
+        # page-locked inputs (the fast path of the pipeline) and the n x k array form
+        pinned = [T.from_numpy(f).pin_memory().numpy() for f in fs]
+        got2 = s.vcycle_many(pinned, H, sm, shifts[:k], lowest_level=8, dimension="2d", **kw)
+        got3 = s.vcycle_many(np.stack(fs, axis=1), H, sm, shifts[:k], lowest_level=8, dimension="2d", **kw)
+        for c in range(k):
+            assert np.array_equal(got2[c], want[c]) and np.array_equal(got3[c], want[c])
+    # pageable sources large enough to be staged by the host threads (staging.cu): shrink the chunk so that 2 MB vectors
+    # are many chunks with a ragged tail, several thread counts
+    lib = __import__("multigridcmt_b200")._lib
+    try:
+        lib.check(lib.load().mgcmt_set_option(b"stage_chunk_kib", 96))
+        for threads in (1, 3, 8):
+            lib.check(lib.load().mgcmt_set_option(b"stage_threads", threads))
+            got4 = s.vcycle_many(fs, H, sm, shifts, lowest_level=8, dimension="2d", **kw)
+            one = s.vcycle(ZeroVector(n), fs[1].copy(), H, sm, shift=shifts[1], lowest_level=8, dimension="2d", **kw)
+            for c in range(5):
+                assert np.array_equal(got4[c], want[c])
+            assert np.array_equal(one, want[1])
+    finally:
+        lib.check(lib.load().mgcmt_set_option(b"stage_chunk_kib", 4096))
+        lib.check(lib.load().mgcmt_set_option(b"stage_threads", 8))
+    # a second block call must not disturb results the caller still holds
+    again = s.vcycle_many(fs, H, sm, [2.0] * 5, lowest_level=8, dimension="2d", **kw)
+    for c in range(5):
+        assert np.array_equal(got[c], want[c]) and not np.array_equal(again[c], want[c])
+    with pytest.raises(ValueError):
+        s.vcycle_many(fs, H, sm, shifts[:2], lowest_level=8, dimension="2d")
+    # small / device inputs take one call per vector
+    small = [rand(64 * 64, 3), rand(64 * 64, 4)]
+    Hs = (-1. / np.pi ** 2) * sm.laplacian(64, "2d", matrix_free=True)
+    gs_ = s.vcycle_many(small, Hs, sm, [1.0, 2.0], lowest_level=8, dimension="2d")
+    for c in range(2):
+        assert np.array_equal(gs_[c], s.vcycle(ZeroVector(64 * 64), small[c].copy(), Hs, sm, shift=[1.0, 2.0][c], lowest_level=8,
+                                               dimension="2d"))
+
+
 # ---------------------------------------------------------------------------------------------------
 # row-slab decomposition (multi-GPU path) emulated on one GPU: same kernels, halo copies instead of NCCL
 # ---------------------------------------------------------------------------------------------------
