@@ -43,12 +43,46 @@ constexpr int k9Warps = 4;
 constexpr int k9ERing = 4;
 __host__ __device__ constexpr int u9_halo(int nu) { return (nu + 2 + 3) & ~3; }
 constexpr int k9VR = 4;
-__host__ __device__ constexpr int u9_fring(int nstage, int lag) { return k9VR + lag * (nstage > 0 ? nstage - 1 : 0) + 1; }
+// rows of the w f ring.  LAG 1: rounded up to a power of two, so that a stage's slot is one add and one mask away from the
+// newest row's; LAG 2 (twice the rows in flight) keeps the exact count, or the ring would cost a resident CTA
+__host__ __device__ constexpr int u9_fring(int nstage, int lag) {
+  const int need = k9VR + lag * (nstage > 0 ? nstage - 1 : 0) + 1;
+  if (lag != 1) return need;
+  int p = 1;
+  while (p < need) p <<= 1;
+  return p;
+}
+// byte offset of the ring row `back` bytes behind / `ahead` bytes in front of `cur` in a ring of R rows of 1024 bytes
+template <int R>
+__device__ __forceinline__ unsigned ring_back(unsigned cur, unsigned back) {
+  if ((R & (R - 1)) == 0) return (cur - back) & (unsigned)(R * 1024 - 1);
+  const int s = (int)cur - (int)back;
+  return (unsigned)(s + ((s < 0) ? R * 1024 : 0));
+}
+template <int R>
+__device__ __forceinline__ unsigned ring_fwd(unsigned cur, unsigned ahead) {
+  if ((R & (R - 1)) == 0) return (cur + ahead) & (unsigned)(R * 1024 - 1);
+  const unsigned s = cur + ahead;
+  return s - ((s >= (unsigned)(R * 1024)) ? (unsigned)(R * 1024) : 0u);
+}
 
 __device__ __forceinline__ void cpa16(void *smem, const void *gmem, bool valid) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   const int bytes = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+// the same with the destination as a 32-bit shared-space address
+__device__ __forceinline__ void cpa16s(unsigned s, const void *gmem, bool valid) {
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double2 lds2(unsigned s) {
+  double2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(s) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts2(unsigned s, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(s), "d"(a), "d"(b) : "memory");
 }
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -138,27 +172,37 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
   auto rowclass = [&](int row) { const int g = row + L.row0; return (g < 0 || g >= nglob) ? 2 : (g == nglob - 1 ? 1 : 0); };
   const double q4 = 0.25 * K.invw, q2 = 0.5 * K.invw;
 
-  int ldpos[2];
+  // Ring addressing: 32-bit shared-space addresses, one ring row = 64 double2 = 1024 bytes, the w f ring of the
+  // LAG 1 form a power of two of rows, so a slot is (newest + constant) & mask.  The copy of column pair G = 32 g + lane lands at position
+  // G ^ ((G >> 3) & 1) (g = 1: 512 bytes further); this lane's own four columns are the pairs 2 lane, 2 lane + 1.
+  static_assert(AHEAD < kVR && AHEAD + LAG * (NS1 - 1) < kFR, "rings too short");
+  const unsigned sm_v = (unsigned)__cvta_generic_to_shared(ring_v), sm_f = (unsigned)__cvta_generic_to_shared(ring_f);
   bool ldin[2];
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    const int G = 32 * g + lane;
-    ldpos[g] = G ^ ((G >> 3) & 1);
-    const int j = cstart + 2 * G;
+    const int j = cstart + 2 * (32 * g + lane);
     ldin[g] = (j >= 0 && j < L.ncols);
   }
-  const int pa = (2 * lane) ^ ((lane >> 2) & 1), pb = (2 * lane + 1) ^ ((lane >> 2) & 1);
+  const unsigned ld_off = (unsigned)(lane ^ ((lane >> 3) & 1)) * 16;
+  const unsigned pa_off = (unsigned)((2 * lane) ^ ((lane >> 2) & 1)) * 16, pb_off = pa_off ^ 16;
+  // rows the copies may touch: inside the array, inside the grid, not beyond what the last step needs
+  const int t_lo = max(0, -L.row0);
+  const int t_span = max(0, min(min(L.nrows, t_last + 1), nglob - L.row0) - t_lo);
+  // running source pointers of this lane's first column pair in the row the next issue() fetches (predicated-off copies
+  // read nothing, so rows before / after the array need no clamping)
+  const double *pv = ZEROV ? nullptr : v_in + ((ptrdiff_t)t_begin * L.ncols + cstart + 2 * lane);
+  const double *pf = f + ((ptrdiff_t)t_begin * L.ncols + cstart + 2 * lane);
 
-  auto issue = [&](int t, int vslot, int fslot) {
-    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last && (unsigned)(t + L.row0) < (unsigned)nglob;
-    const size_t rowoff = (size_t)(rowin ? t : 0) * L.ncols;
+  auto issue = [&](int t, unsigned vo, unsigned fo) {   // vo / fo: byte offsets of the ring rows to fill
+    const bool rowin = (unsigned)(t - t_lo) < (unsigned)t_span;
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const bool ok = rowin && ldin[g];
-      const size_t off = ok ? rowoff + cstart + 2 * (32 * g + lane) : 0;
-      if (!ZEROV) cpa16(ring_v + vslot * 64 + ldpos[g], v_in + off, ok);
-      if (NSTAGE > 0) cpa16(ring_f + fslot * 64 + ldpos[g], f + off, ok);
+      if (!ZEROV) cpa16s(sm_v + vo + ld_off + 512 * g, pv + 64 * g, ok);
+      if (NSTAGE > 0) cpa16s(sm_f + fo + ld_off + 512 * g, pf + 64 * g, ok);
     }
+    if (!ZEROV) pv += L.ncols;
+    pf += L.ncols;
     if (PROLONG && (t & 1) == 0) {
       const int I = (t >> 1) + cs;
       const int Gc = ((t + L.row0) >> 1);
@@ -180,35 +224,34 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
   for (int q = 0; q < C; ++q) eprev[q] = ecur[q] = 0.0;
   double racc[2] = {0.0, 0.0};
 
-  int vs = 0, fs = 0;
+  unsigned vso = 0, fso = 0;   // byte offsets of the ring rows that hold row t
+  // running destination of the row the last sweep finishes in this step (row t - LAG (NU - 1) - 1), this lane's columns
+  double *pout = v_out + ((ptrdiff_t)(t_begin - LAG * (NU - 1) - 1) * L.ncols + c0);
+  const unsigned out_rows = (unsigned)(r1 - r0);
   auto step = [&](int t, auto odd_tag, auto slow_tag) {
     constexpr bool ODD = decltype(odd_tag)::value;   // parity of t
     constexpr bool SLOW = decltype(slow_tag)::value;
     cpa_wait<AHEAD - 1>();
     __syncwarp();
-    {
-      int vnew = vs + AHEAD; vnew -= (vnew >= kVR) ? kVR : 0;
-      int fnew = fs + AHEAD; fnew -= (fnew >= kFR) ? kFR : 0;
-      issue(t + AHEAD, vnew, fnew);
-    }
+    issue(t + AHEAD, ring_fwd<kVR>(vso, AHEAD * 1024), ring_fwd<kFR>(fso, AHEAD * 1024));
     // ---- the input row t and its scaled right-hand side ------------------------------------------------
     double x0[C];
     if (ZEROV) {
 #pragma unroll
       for (int q = 0; q < C; ++q) x0[q] = 0.0;
     } else {
-      const double2 xa = ring_v[vs * 64 + pa], xb = ring_v[vs * 64 + pb];
+      const double2 xa = lds2(sm_v + vso + pa_off), xb = lds2(sm_v + vso + pb_off);
       x0[0] = xa.x; x0[1] = xa.y; x0[2] = xb.x; x0[3] = xb.y;
     }
     double wfq[NS1][C];
     if (NSTAGE > 0) {
-      const double2 fa = ring_f[fs * 64 + pa], fb = ring_f[fs * 64 + pb];
+      const double2 fa = lds2(sm_f + fso + pa_off), fb = lds2(sm_f + fso + pb_off);
       const int rc = SLOW ? rowclass(t) : 0;
       wfq[0][0] = cst(rc, 0).w * fa.x; wfq[0][1] = cst(rc, 1).w * fa.y;
       wfq[0][2] = cst(rc, 2).w * fb.x; wfq[0][3] = cst(rc, 3).w * fb.y;
       if (NSTAGE > 1) {  // parked for the later stages, de-interleaved by column parity
-        ring_f[fs * 64 + pa] = make_double2(wfq[0][0], wfq[0][2]);
-        ring_f[fs * 64 + pb] = make_double2(wfq[0][1], wfq[0][3]);
+        sts2(sm_f + fso + pa_off, wfq[0][0], wfq[0][2]);
+        sts2(sm_f + fso + pb_off, wfq[0][1], wfq[0][3]);
       }
     }
 #pragma unroll
@@ -217,11 +260,9 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
       const bool gs_stage = (GS != 0) && !is_res;
       const int ci = k & 3, pr = ci & 1, pc = (ci == 1 || ci == 2) ? 1 : 0;
       if (gs_stage && pr != ((ODD ? 1 : 0) ^ ((LAG * k) & 1))) continue;  // this stage opens no point in a row of this parity
-      int sl = fs - LAG * k;
-      sl += (sl < 0) ? kFR : 0;
-      sl += (sl < 0) ? kFR : 0;
-      if (!gs_stage || pc == 0) { const double2 g0 = ring_f[sl * 64 + pa]; wfq[k][0] = g0.x; wfq[k][2] = g0.y; }
-      if (!gs_stage || pc == 1) { const double2 g1 = ring_f[sl * 64 + pb]; wfq[k][1] = g1.x; wfq[k][3] = g1.y; }
+      const unsigned sl = ring_back<kFR>(fso, (unsigned)(LAG * k) * 1024u);
+      if (!gs_stage || pc == 0) { const double2 g0 = lds2(sm_f + sl + pa_off); wfq[k][0] = g0.x; wfq[k][2] = g0.y; }
+      if (!gs_stage || pc == 1) { const double2 g1 = lds2(sm_f + sl + pb_off); wfq[k][1] = g1.x; wfq[k][3] = g1.y; }
     }
     if (PROLONG) {
       if (!ODD) {
@@ -299,8 +340,8 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
         if (LAG == 1) xflow[q] = rdy;
       }
       const int rho = n - 1;
-      if (!is_res && k == NU - 1 && rho >= r0 && rho < r1 && quadout) {
-        double *dst = v_out + (size_t)rho * L.ncols + c0;
+      if (!is_res && k == NU - 1 && (unsigned)(rho - r0) < out_rows && quadout) {
+        double *dst = pout;
         if (st32) st4(dst, ready[k][0], ready[k][1], ready[k][2], ready[k][3]);
         else { st_stream2(dst, make_double2(ready[k][0], ready[k][1])); st_stream2(dst + 2, make_double2(ready[k][2], ready[k][3])); }
       }
@@ -335,12 +376,13 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
       if (st32) st4(dst, x0[0], x0[1], x0[2], x0[3]);
       else { st_stream2(dst, make_double2(x0[0], x0[1])); st_stream2(dst + 2, make_double2(x0[2], x0[3])); }
     }
-    vs = (vs + 1 == kVR) ? 0 : vs + 1;
-    fs = (fs + 1 == kFR) ? 0 : fs + 1;
+    vso = ring_fwd<kVR>(vso, 1024);
+    fso = ring_fwd<kFR>(fso, 1024);
+    if (NU > 0) pout += L.ncols;
   };
 
 #pragma unroll
-  for (int d = 0; d < AHEAD; ++d) issue(t_begin + d, d, d);
+  for (int d = 0; d < AHEAD; ++d) issue(t_begin + d, d * 1024, d * 1024);
 
   using TrueT = std::integral_constant<bool, true>;
   using FalseT = std::integral_constant<bool, false>;
