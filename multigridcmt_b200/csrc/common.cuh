@@ -52,4 +52,33 @@ __device__ __forceinline__ void st_stream2(double *p, double2 v) {
   asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
+// ---- per-warp row rings in shared memory (fused_uni.cu, fused_uni9.cu): one ring row = 64 double2 = 1024 bytes, addressed
+// as 32-bit shared-space byte offsets so that a slot costs an add and a mask (power-of-two rings) or an add, a compare
+// and a select (others) instead of an index multiply chain
+__device__ __forceinline__ void cpa16s(unsigned s, const void *gmem, bool valid) {
+  const int bytes = valid ? 16 : 0;   // 0: nothing is read from gmem, the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ double2 lds2(unsigned s) {
+  double2 r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(s) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts2(unsigned s, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(s), "d"(a), "d"(b) : "memory");
+}
+// byte offset of the ring row `back` bytes behind / `ahead` bytes in front of `cur` in a ring of R rows
+template <int R>
+__device__ __forceinline__ unsigned ring_back(unsigned cur, unsigned back) {
+  if ((R & (R - 1)) == 0) return (cur - back) & (unsigned)(R * 1024 - 1);
+  const int s = (int)cur - (int)back;
+  return (unsigned)(s + ((s < 0) ? R * 1024 : 0));
+}
+template <int R>
+__device__ __forceinline__ unsigned ring_fwd(unsigned cur, unsigned ahead) {
+  if ((R & (R - 1)) == 0) return (cur + ahead) & (unsigned)(R * 1024 - 1);
+  const unsigned s = cur + ahead;
+  return s - ((s >= (unsigned)(R * 1024)) ? (unsigned)(R * 1024) : 0u);
+}
+
 }  // namespace mgcmt

@@ -50,8 +50,14 @@ constexpr int kWarpsU = 4;   // warps per CTA (independent strips)
 constexpr int kERingU = 4;   // coarse-row ring (PROLONG)
 __host__ __device__ constexpr int uni_halo(int nu) { return (nu + 2 + 3) & ~3; }   // >= nu + 2, multiple of 4
 __host__ __device__ constexpr int uni_vring(int nstage) { return nstage > 5 ? 4 : 6; }
+// rows of the w f ring; when the later stages read it (no WFREG) it is rounded up to a power of two, so that a stage's
+// slot is one add and one mask away from the newest row's
 __host__ __device__ constexpr int uni_fring(int nstage, bool wfreg) {
-  return wfreg ? uni_vring(nstage) : uni_vring(nstage) + (nstage > 0 ? nstage - 1 : 0);
+  if (wfreg) return uni_vring(nstage);
+  const int need = uni_vring(nstage) + (nstage > 0 ? nstage - 1 : 0);
+  int p = 1;
+  while (p < need) p <<= 1;
+  return p;
 }
 
 __device__ __forceinline__ void ucpa16(void *smem, const void *gmem, bool valid) {
@@ -205,18 +211,27 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
   const double q4 = 0.25 * K.invw, q2 = 0.5 * K.invw;  // full weighting with the 1/w of the scaled residual folded in
   const bool st32 = ((reinterpret_cast<uintptr_t>(v_out) & 31) == 0);
 
-  // loader: granules lane and 32 + lane of the strip row; swizzled position G ^ ((G >> 3) & 1)
-  int ldpos[2];
+  // Ring addressing: 32-bit shared-space byte offsets, one ring row = 64 granules = 1024 bytes (common.cuh).
+  // loader: granules lane and 32 + lane of the strip row (512 bytes apart); swizzled position G ^ ((G >> 3) & 1)
+  const unsigned sm_v = (unsigned)__cvta_generic_to_shared(ring_v), sm_f = (unsigned)__cvta_generic_to_shared(ring_f);
   bool ldin[2];
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    const int G = 32 * g + lane;
-    ldpos[g] = BULK ? G : (G ^ ((G >> 3) & 1));
-    const int j = cstart + 2 * G;
+    const int j = cstart + 2 * (32 * g + lane);
     ldin[g] = (j >= 0 && j < L.ncols);
   }
+  const unsigned ld_off = (unsigned)(BULK ? lane : (lane ^ ((lane >> 3) & 1))) * 16;
   // consumer: granules 2 lane, 2 lane + 1 (columns c0 .. c0+3)
-  const int pa = BULK ? 2 * lane : ((2 * lane) ^ ((lane >> 2) & 1)), pb = BULK ? 2 * lane + 1 : ((2 * lane + 1) ^ ((lane >> 2) & 1));
+  const unsigned pa_off = (unsigned)(BULK ? 2 * lane : ((2 * lane) ^ ((lane >> 2) & 1))) * 16, pb_off = pa_off ^ 16;
+  // rows the copies may touch: inside the array, inside the grid, not beyond what the last step needs
+  const int t_lo = max(0, -L.row0);
+  const int t_span = max(0, min(min(L.nrows, t_last + 1), (int)nglob - L.row0) - t_lo);
+  // running source pointers of this lane's first granule in the row the next issue() fetches (a predicated-off copy reads
+  // nothing, so rows before / after the array need no clamping), and the destination of the row the last sweep finishes
+  const double *pv = ZEROV ? nullptr : v_in + ((ptrdiff_t)t_begin * L.ncols + cstart + 2 * lane);
+  const double *pf = f + ((ptrdiff_t)t_begin * L.ncols + cstart + 2 * lane);
+  double *pout = v_out + ((ptrdiff_t)(t_begin - NU) * L.ncols + c0);
+  const unsigned out_rows = (unsigned)(r1 - r0);
   // BULK: the part of the strip row that lies inside the grid is one contiguous copy; the granules outside stay zero
   const int bj0 = max(cstart, 0), bj1 = min(cstart + WCOLS, L.ncols);
   const unsigned brow_bytes = (unsigned)(bj1 - bj0) * 8u;
@@ -231,11 +246,12 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
   }
 
   // ---- asynchronous row fetch ---------------------------------------------------------------------
-  auto issue = [&](int t, int vslot, int fslot) {
+  auto issue = [&](int t, unsigned vo, unsigned fo) {   // vo / fo: byte offsets of the ring rows to fill
     // rows outside the slab array or outside the global grid are zero-filled
-    const bool rowin = (t >= 0 && t < L.nrows) && t <= t_last && (unsigned)(t + L.row0) < nglob;
-    const size_t rowoff = (size_t)(rowin ? t : 0) * L.ncols;
+    const bool rowin = (unsigned)(t - t_lo) < (unsigned)t_span;
     if (BULK) {
+      const int vslot = (int)(vo >> 10), fslot = (int)(fo >> 10);
+      const size_t rowoff = (size_t)(rowin ? t : 0) * L.ncols;
       // every lane first clears its granules of a slot that gets no data (row outside the grid), then lane 0 arms the
       // slot's barrier with the bytes to come and issues the copies
       bool ein = false;
@@ -274,10 +290,11 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const bool ok = rowin && ldin[g];
-      const size_t off = ok ? rowoff + cstart + 2 * (32 * g + lane) : 0;
-      if (!ZEROV) ucpa16(ring_v + vslot * 64 + ldpos[g], v_in + off, ok);
-      if (NSTAGE > 0) ucpa16(ring_f + fslot * 64 + ldpos[g], f + off, ok);
+      if (!ZEROV) cpa16s(sm_v + vo + ld_off + 512 * g, pv + 64 * g, ok);
+      if (NSTAGE > 0) cpa16s(sm_f + fo + ld_off + 512 * g, pf + 64 * g, ok);
     }
+    if (!ZEROV) pv += L.ncols;
+    pf += L.ncols;
     if (PROLONG && (t & 1) == 0) {
       // coarse row I = t/2 is first needed by fine row t (even); this lane's coarse columns c0/2, c0/2 + 1
       const int I = (t >> 1) + cs;
@@ -302,21 +319,17 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
   double rq_num[C] = {0.0, 0.0, 0.0, 0.0}, rq_den[C] = {0.0, 0.0, 0.0, 0.0};  // one accumulator per column: no serial fma chain
   double racc[2] = {0.0, 0.0};  // running full-weighting row sums (RESTRICT)
 
-  int vs = 0, fs = 0;  // ring slots of the current input row t
+  unsigned vso = 0, fso = 0;  // byte offsets of the ring rows that hold the current input row t
   auto step = [&](int t, auto odd_tag, auto slow_tag) {
     constexpr bool ODD = decltype(odd_tag)::value;
     constexpr bool SLOW = decltype(slow_tag)::value;
     if (BULK) {
-      mbar_wait(bars + vs, (unsigned)(((t - t_begin) / kVR) & 1));  // row t (and its coarse row) has landed
+      mbar_wait(bars + (vso >> 10), (unsigned)(((t - t_begin) / kVR) & 1));  // row t (and its coarse row) has landed
     } else {
       ucpa_wait<AHEAD - 1>();  // row t has landed (this lane's copies) ...
     }
     __syncwarp();              // ... and every lane's; all lanes are done reading the slots refilled below
-    {
-      int vnew = vs + AHEAD; vnew -= (vnew >= kVR) ? kVR : 0;
-      int fnew = fs + AHEAD; fnew -= (fnew >= kFR) ? kFR : 0;
-      issue(t + AHEAD, vnew, fnew);
-    }
+    issue(t + AHEAD, ring_fwd<kVR>(vso, AHEAD * 1024), ring_fwd<kFR>(fso, AHEAD * 1024));
 
     // ---- the input row t ---------------------------------------------------------------------------
     double x[C];
@@ -324,16 +337,16 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
 #pragma unroll
       for (int q = 0; q < C; ++q) x[q] = 0.0;
     } else {
-      const double2 xa = ring_v[vs * 64 + pa], xb = ring_v[vs * 64 + pb];
+      const double2 xa = lds2(sm_v + vso + pa_off), xb = lds2(sm_v + vso + pb_off);
       x[0] = xa.x; x[1] = xa.y; x[2] = xb.x; x[3] = xb.y;
     }
     if (NSTAGE > 0) {
-      double2 fa = ring_f[fs * 64 + pa], fb = ring_f[fs * 64 + pb];
+      const double2 fa = lds2(sm_f + fso + pa_off), fb = lds2(sm_f + fso + pb_off);
       wfq[0][0] = w * fa.x; wfq[0][1] = w * fa.y; wfq[0][2] = w * fb.x; wfq[0][3] = w * fb.y;
       if (!WFREG && NSTAGE > 1) {
         // later stages read w f from the slot, de-interleaved by column parity: a colour stage needs one granule
-        ring_f[fs * 64 + pa] = make_double2(wfq[0][0], wfq[0][2]);
-        ring_f[fs * 64 + pb] = make_double2(wfq[0][1], wfq[0][3]);
+        sts2(sm_f + fso + pa_off, wfq[0][0], wfq[0][2]);
+        sts2(sm_f + fso + pb_off, wfq[0][1], wfq[0][3]);
       }
     }
     if (!WFREG) {
@@ -342,13 +355,12 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
       for (int k = 1; k < NSTAGE; ++k) {
         const bool is_res = RESTRICT && (k == NSTAGE - 1);
         if (RQ && is_res) continue;
-        int sl = fs - k;
-        sl += (sl < 0) ? kFR : 0;
+        const unsigned sl = ring_back<kFR>(fso, (unsigned)k * 1024u);
         const bool gs_stage = (GS != 0) && !is_res;
         // columns this stage opens in row n = t - k: parity (colour + row parity); row parity of n = ODD ^ (k & 1)
         const int cpar = ODD ? 1 : 0;  // colour (k & 1) ^ parity of row t - k
-        if (!gs_stage || cpar == 0) { const double2 g0 = ring_f[sl * 64 + pa]; wfq[k][0] = g0.x; wfq[k][2] = g0.y; }
-        if (!gs_stage || cpar == 1) { const double2 g1 = ring_f[sl * 64 + pb]; wfq[k][1] = g1.x; wfq[k][3] = g1.y; }
+        if (!gs_stage || cpar == 0) { const double2 g0 = lds2(sm_f + sl + pa_off); wfq[k][0] = g0.x; wfq[k][2] = g0.y; }
+        if (!gs_stage || cpar == 1) { const double2 g1 = lds2(sm_f + sl + pb_off); wfq[k][1] = g1.x; wfq[k][3] = g1.y; }
       }
     }
     if (PROLONG) {
@@ -435,9 +447,9 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
 #pragma unroll
       for (int q = 0; q < C; ++q) { st[k].xc[q] = x[q]; x[q] = out[q]; }
 
-      if (!is_res && k == NU - 1 && rho >= r0 && rho < r1 && quadout) {
+      if (!is_res && k == NU - 1 && (unsigned)(rho - r0) < out_rows && quadout) {
         // x = row rho of the last sweep: the smoothed iterate
-        double *dst = v_out + (size_t)rho * L.ncols + c0;
+        double *dst = pout;
         if (st32) st_stream4(dst, x[0], x[1], x[2], x[3]);
         else { st_stream2(dst, make_double2(x[0], x[1])); st_stream2(dst + 2, make_double2(x[2], x[3])); }
       }
@@ -500,12 +512,13 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
 #pragma unroll
         for (int q = 0; q < C; ++q) wfq[k][q] = wfq[k - 1][q];
     }
-    vs = (vs + 1 == kVR) ? 0 : vs + 1;
-    fs = (fs + 1 == kFR) ? 0 : fs + 1;
+    vso = ring_fwd<kVR>(vso, 1024);
+    fso = ring_fwd<kFR>(fso, 1024);
+    if (NU > 0) pout += L.ncols;
   };
 
 #pragma unroll
-  for (int d = 0; d < AHEAD; ++d) issue(t_begin + d, d, d);
+  for (int d = 0; d < AHEAD; ++d) issue(t_begin + d, d * 1024, d * 1024);
 
   using TrueT = std::integral_constant<bool, true>;
   using FalseT = std::integral_constant<bool, false>;

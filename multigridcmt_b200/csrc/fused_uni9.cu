@@ -52,37 +52,10 @@ __host__ __device__ constexpr int u9_fring(int nstage, int lag) {
   while (p < need) p <<= 1;
   return p;
 }
-// byte offset of the ring row `back` bytes behind / `ahead` bytes in front of `cur` in a ring of R rows of 1024 bytes
-template <int R>
-__device__ __forceinline__ unsigned ring_back(unsigned cur, unsigned back) {
-  if ((R & (R - 1)) == 0) return (cur - back) & (unsigned)(R * 1024 - 1);
-  const int s = (int)cur - (int)back;
-  return (unsigned)(s + ((s < 0) ? R * 1024 : 0));
-}
-template <int R>
-__device__ __forceinline__ unsigned ring_fwd(unsigned cur, unsigned ahead) {
-  if ((R & (R - 1)) == 0) return (cur + ahead) & (unsigned)(R * 1024 - 1);
-  const unsigned s = cur + ahead;
-  return s - ((s >= (unsigned)(R * 1024)) ? (unsigned)(R * 1024) : 0u);
-}
-
 __device__ __forceinline__ void cpa16(void *smem, const void *gmem, bool valid) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   const int bytes = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
-}
-// the same with the destination as a 32-bit shared-space address
-__device__ __forceinline__ void cpa16s(unsigned s, const void *gmem, bool valid) {
-  const int bytes = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ double2 lds2(unsigned s) {
-  double2 r;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(s) : "memory");
-  return r;
-}
-__device__ __forceinline__ void sts2(unsigned s, double a, double b) {
-  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(s), "d"(a), "d"(b) : "memory");
 }
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
