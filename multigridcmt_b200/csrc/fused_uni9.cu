@@ -21,7 +21,8 @@
 // gives row n), `ready` (row n-1 finished, next stage's input in the next step); red-black (four-colour) Gauss-Seidel
 // stages also keep the row itself for the points that pass through.
 // Coefficient classes: rows {interior, last, outside} x columns {interior, last}; interior steps run on registers,
-// steps that touch the last row or rows outside the grid (SLOW) fetch per-class constants from the kernel parameters.
+// steps that touch the last row or rows outside the grid (SLOW) add warp-uniform row tests: zero rows outside, the last
+// row's constants from the kernel parameters for the one stage per step that works on it.
 // The interior diagonal weight is carried as hi + lo like in fused_uni.cu (consistent stencil row sum, no systematic
 // shift of the spectrum).  Data movement as in fused_uni.cu: coalesced cp.async ring with XOR swizzle, 32-byte stores.
 #include <math.h>
@@ -135,14 +136,21 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
     ki.c1 = ki.c2 = ki.c3 = ki.ares = ki.asm_ = ki.dlo = ki.w = ki.rs = 0.0;
     kl = ki;
   }
-  // constants for (row class rc, column q); fast = interior row
-  auto cst = [&](int rc, int q) -> C9 {
-    if (rc == 0) return (q == C - 1) ? kl : ki;
-    C9 z = K.c[rc][(q == C - 1 && lastq) ? 1 : 0];
+  // Boundary steps (SLOW) run the interior arithmetic on the register constants as well; what differs is decided by
+  // warp-uniform row tests, so the extra work is a few selects per stage plus, for the one stage per step whose row is
+  // the LAST grid row, that row's constants fetched from the kernel parameters:
+  //   * rows outside the grid: their inputs are zero (the loader fills zeros), so they give nothing to their neighbours;
+  //     what the interior constants compute FOR them is discarded (`up_out`: the finished row is forced to zero);
+  //   * the last row G: its own part (c3, a, w, rs) when it is opened, and what row G - 1 gives it (c1, c2).
+  //     What an outside row G + 1 gives it is zero whatever the constants.
+  auto cls1 = [&](int q) -> C9 {   // constants of the last row for this lane's column q
+    C9 z = K.c[1][(q == C - 1 && lastq) ? 1 : 0];
     if (!quadin) z.c1 = z.c2 = z.c3 = z.ares = z.asm_ = z.dlo = z.w = z.rs = 0.0;
     return z;
   };
-  auto rowclass = [&](int row) { const int g = row + L.row0; return (g < 0 || g >= nglob) ? 2 : (g == nglob - 1 ? 1 : 0); };
+  auto cls0 = [&](int q) -> const C9 & { return (q == C - 1) ? kl : ki; };
+  const int gl = nglob - 1 - L.row0;   // local index of the last grid row
+  const int go = -L.row0;              // local index of grid row 0
   const double q4 = 0.25 * K.invw, q2 = 0.5 * K.invw;
 
   // Ring addressing: 32-bit shared-space addresses, one ring row = 64 double2 = 1024 bytes, the w f ring of the
@@ -197,6 +205,8 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
   for (int q = 0; q < C; ++q) eprev[q] = ecur[q] = 0.0;
   double racc[2] = {0.0, 0.0};
 
+  using TrueT = std::integral_constant<bool, true>;
+  using FalseT = std::integral_constant<bool, false>;
   unsigned vso = 0, fso = 0;   // byte offsets of the ring rows that hold row t
   // running destination of the row the last sweep finishes in this step (row t - LAG (NU - 1) - 1), this lane's columns
   double *pout = v_out + ((ptrdiff_t)(t_begin - LAG * (NU - 1) - 1) * L.ncols + c0);
@@ -219,9 +229,13 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
     double wfq[NS1][C];
     if (NSTAGE > 0) {
       const double2 fa = lds2(sm_f + fso + pa_off), fb = lds2(sm_f + fso + pb_off);
-      const int rc = SLOW ? rowclass(t) : 0;
-      wfq[0][0] = cst(rc, 0).w * fa.x; wfq[0][1] = cst(rc, 1).w * fa.y;
-      wfq[0][2] = cst(rc, 2).w * fb.x; wfq[0][3] = cst(rc, 3).w * fb.y;
+      if (SLOW && t == gl) {   // (warp-uniform) the last grid row has its own weights
+        wfq[0][0] = cls1(0).w * fa.x; wfq[0][1] = cls1(1).w * fa.y;
+        wfq[0][2] = cls1(2).w * fb.x; wfq[0][3] = cls1(3).w * fb.y;
+      } else {                 // rows outside the grid arrive as zeros
+        wfq[0][0] = ki.w * fa.x; wfq[0][1] = ki.w * fa.y;
+        wfq[0][2] = ki.w * fb.x; wfq[0][3] = kl.w * fb.y;
+      }
       if (NSTAGE > 1) {  // parked for the later stages, de-interleaved by column parity
         sts2(sm_f + fso + pa_off, wfq[0][0], wfq[0][2]);
         sts2(sm_f + fso + pb_off, wfq[0][1], wfq[0][3]);
@@ -281,7 +295,13 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
       const bool finish_here = !gs_stage || (pn != pr);  // row n - 1 does
       const double xl = __shfl_up_sync(0xffffffffu, x[C - 1], 1);
       const double xr = __shfl_down_sync(0xffffffffu, x[0], 1);
-      const int rc_up = SLOW ? rowclass(n - 1) : 0, rc_me = SLOW ? rowclass(n) : 0, rc_dn = SLOW ? rowclass(n + 1) : 0;
+      // warp-uniform row tests of a boundary step: row n - 1 outside the grid; row n / n + 1 / n - 1 the last grid row.
+      // The stage body exists twice in a boundary step: without any last-row code (taken by all but at most three
+      // stages of a step) and with it; the choice is one uniform branch per stage.
+      const bool up_out = SLOW && (n - 1 < go || n - 1 > gl);
+      auto body = [&](auto last_tag) {
+      constexpr bool LASTROW = decltype(last_tag)::value;
+      const bool open_last = LASTROW && (n == gl), down_last = LASTROW && (n + 1 == gl), up_last = LASTROW && (n - 1 == gl);
 #pragma unroll
       for (int q = 0; q < C; ++q) {
         const bool colq = !gs_stage || ((q & 1) == pc);
@@ -289,25 +309,26 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
         double rdy = gs_stage ? xc[k][q] : 0.0;  // Gauss-Seidel: points of other colours pass through
         const double up_old = uprev[k][q];       // what row n - 1 gives row n
         if (colq && finish_here) {
-          const C9 cu = cst(rc_up, q);
+          const C9 &cu = cls0(q);
           const double un_up = fma(cu.c1, h, cu.c2 * x[q]);
           rdy = pre1[k][q] + un_up;
-          if (SLOW) {
-            const C9 cd = cst(rc_dn, q);
+          if (down_last) {   // what row n gives the last row
+            const C9 cd = cls1(q);
             uprev[k][q] = fma(cd.c1, h, cd.c2 * x[q]);
           } else {
             uprev[k][q] = un_up;
           }
         }
         if (colq && open_here) {
-          const C9 cm = cst(rc_me, q);
+          C9 cm = cls0(q);
+          if (open_last) cm = cls1(q);
           const double a = is_res ? cm.ares : cm.asm_;
           double base;
           if (is_res || k < (GS ? 4 : 1)) base = fma(a, x[q], fma(cm.dlo * (is_res ? 1.0 : (GS ? NU / 4 : NU)), x[q], wfq[k][q]));
           else base = fma(a, x[q], wfq[k][q]);
           pre1[k][q] = fma(cm.c3, h, base) + up_old;
         }
-        if (SLOW && rc_up == 2) rdy = 0.0;
+        if (up_out) rdy = 0.0;
         ready[k][q] = rdy;
         xc[k][q] = x[q];
         if (LAG == 1) xflow[q] = rdy;
@@ -320,8 +341,12 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
       }
       if (is_res) {
 #pragma unroll
-        for (int q = 0; q < C; ++q) res[q] = (SLOW || q == C - 1) ? ready[k][q] * cst(rc_up, q).rs : ready[k][q];
+        for (int q = 0; q < C; ++q)
+          res[q] = up_last ? ready[k][q] * cls1(q).rs : ((q == C - 1) ? ready[k][q] * kl.rs : ready[k][q]);
       }
+      };  // body
+      if (SLOW && (unsigned)(n - gl + 1) <= 2u) body(TrueT{});   // n - 1, n or n + 1 is the last grid row
+      else body(FalseT{});
     }
     if (RESTRICT) {
       // res = w * residual of row rho = t - LAG NU - 1 (zero outside the grid): full weighting, columns first
@@ -357,8 +382,6 @@ uni9_leg_kernel(LevelDev L, K9 K, const double *__restrict__ v_in, const double 
 #pragma unroll
   for (int d = 0; d < AHEAD; ++d) issue(t_begin + d, d * 1024, d * 1024);
 
-  using TrueT = std::integral_constant<bool, true>;
-  using FalseT = std::integral_constant<bool, false>;
   for (int t = t_begin; t <= t_last; t += 2) {
     // rows t - LAG (NSTAGE - 1) - 1 .. t + 2 (global) all interior?
     const int g = t + L.row0;

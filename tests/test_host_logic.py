@@ -425,3 +425,19 @@ def test_leg_chunk_height_fills_whole_waves():
         # the last wave is at least 80 % full unless the whole grid is smaller than one wave
         assert ctas <= slots or ctas >= (waves - 1) * slots + 0.8 * slots or rpc == 16, (nrows, gx, slots, rpc, ctas)
         assert lib.mgcmt_debug_leg_rows_per_chunk(nrows, gx, slots, nstage, 128) <= 128
+
+
+def test_vcycle_many_argument_checks_need_no_gpu():
+    """MGCMTSolver.vcycle_many (the drivers' loop body as one call): argument errors are raised before anything touches
+    the device, and the product path still refuses to run without CUDA (no CPU fallback)."""
+    from multigridcmt_b200 import MGCMTSolver, MGCMTStencilMaker
+    s, sm = MGCMTSolver(), MGCMTStencilMaker()
+    H = (-1. / np.pi ** 2) * sm.laplacian(512, "2d", matrix_free=True)
+    fs = [np.zeros(512 * 512), np.zeros(512 * 512)]
+    with pytest.raises(ValueError):
+        s.vcycle_many(fs, H, sm, [1.0], lowest_level=8, dimension="2d")          # one shift for two vectors
+    assert s.vcycle_many([], H, sm, [], lowest_level=8, dimension="2d") == []
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            s.vcycle_many(fs, H, sm, [1.0, 2.0], lowest_level=8, dimension="2d")
