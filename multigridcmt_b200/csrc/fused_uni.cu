@@ -414,12 +414,15 @@ uni5_leg_kernel(LevelDev L, UniCoef K, const double *__restrict__ v_in,
         for (int q = 0; q < C; ++q) out[q] = rin ? out[q] : 0.0;
       }
       if (RQ && is_res) {
-        // each useful (owned) point exactly once; branch-free: rows / lanes outside contribute zeros
+        // each useful (owned) point exactly once; branch-free: rows / lanes outside contribute zeros.  BOTH factors are
+        // selected: rows in front of a chunk are computed from ring rows nobody has filled yet (whatever bits the last
+        // kernel left in shared memory: after an NCCL kernel that can be a NaN pattern), and 0 * NaN is NaN
         const bool mine = rho >= r0 && rho < r1 && rho >= L.rq_lo && rho < L.rq_hi && quadout;
 #pragma unroll
         for (int q = 0; q < C; ++q) {
           const double xm_ = mine ? st[k].xc[q] : 0.0;
-          rq_num[q] = fma(xm_, out[q], rq_num[q]);
+          const double om_ = mine ? out[q] : 0.0;
+          rq_num[q] = fma(xm_, om_, rq_num[q]);
           rq_den[q] = fma(xm_, xm_, rq_den[q]);
         }
       }
