@@ -94,7 +94,7 @@ int mgcmt_hier_create2(mgcmt_hier_t **out, int nrows, int ncols, int coarsen_row
                        const double *h_col_lo, const double *h_col_di, const double *h_col_up,
                        int lowest_level, int first_work_level, void *stream);
 /* Row-slab piece of an nrows_glob x ncols grid for multi-GPU runs: levels 0..nlevels-1
- * hold the rows [row_begin >> l, (row_begin + nrows_own) >> l) of level l plus `halo` (even, >= 6) rows above
+ * hold the rows [row_begin >> l, (row_begin + nrows_own) >> l) of level l plus `halo` (even; >= 6 for the Jacobi legs, >= 10 for the red-black ones) rows above
  * and below, as one dense (own + 2 halo) x ncols array; halo rows outside the global grid stay zero.  The
  * operator factors are the full global ones.  Valid calls on such a handle: the single-level operators,
  * mgcmt_fused_leg (streaming implementation; restriction from the last slab level writes into / prolongation
@@ -304,7 +304,7 @@ int mgcmt_nccl_load(const char *path);
 int mgcmt_nccl_unique_id(void *out128);
 int mgcmt_nccl_comm_create(const void *id128, int world, int rank, void **out_comm);
 int mgcmt_nccl_comm_destroy(void *comm);
-/* k vectors of an n x n grid, rows [rank n/world, (rank+1) n/world) + 6 halo rows on both sides on this rank;
+/* k vectors of an n x n grid, rows [rank n/world, (rank+1) n/world) + 10 halo rows on both sides on this rank;
  * levels 0..nlev_slab-1 stay decomposed, coarser ones are replicated after an all-gather.  Coefficient arrays as in
  * mgcmt_hier_create (host, length n).  comm may be NULL when world == 1.  comm2: a second communicator over the same
  * ranks (or NULL): with it the vectors run as two halves half a phase apart, one half's halo exchange overlapping the
@@ -315,7 +315,7 @@ int mgcmt_slabblock_create(void *comm, void *comm2, int world, int rank, int n, 
                            void *stream, mgcmt_slabblock_t **out);
 int mgcmt_slabblock_destroy(mgcmt_slabblock_t *b);
 /* k V(4,4) weighted-Jacobi cycles in lock-step, zero start: (H - h_shifts[c]) w = f_c; h_f0[c] / h_v0[c] are device
- * pointers to finest-level slab arrays ((n/world + 12) x n doubles; owned rows of f in, owned rows of w out, halo rows
+ * pointers to finest-level slab arrays ((n/world + 20) x n doubles; owned rows of f in, owned rows of w out, halo rows
  * are scratch).  d_lam != NULL: d_lam[2c], d_lam[2c+1] = w_c^T H w_c, w_c^T w_c, summed over all ranks.
  * (the drivers' loop body, 2DPotGS.py:93-103, for all k vectors) */
 int mgcmt_slabblock_cycle(mgcmt_slabblock_t *b, const double *h_shifts, double *const *h_f0, double *const *h_v0,

@@ -1022,8 +1022,9 @@ int mgcmt_slab_up_rq(mgcmt_hier_t *h, int gs, double shift, double omega, const 
     CU(cudaMalloc(&h->rq_partials, sizeof(double) * 2 * slots));
     h->rq_slots = slots;
   }
-  // halo rows 5 and own+6 of the output are exact (dependency cone of prolongation + 4 sweeps = 5 rows, 6 halo rows),
-  // so (A w) on the first and last owned row is too: the sums over the owned rows need no second exchange
+  // the halo row next to the owned rows is exact in the output (dependency cone of prolongation + 4 Jacobi sweeps = 5 rows,
+  // + 8 colour stages = 9 rows; the slab arrays carry 10 halo rows), so (A w) on the first and last owned row is too:
+  // the sums over the owned rows need no second exchange
   if (gs) CU(launch_fused_gs_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, d_vin, d_f, d_vout, d_ecoarse, h->rq_partials, s));
   else CU(launch_fused_leg(L.dev, FUSED_UP_RQ, 4, shift, omega, d_vin, d_f, d_vout, d_ecoarse, h->rq_partials, s));
   CU(launch_finish(2, slots, h->rq_partials, d_out2, s));
