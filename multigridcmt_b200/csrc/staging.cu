@@ -115,8 +115,18 @@ cudaError_t staged_upload(void *d_dst, const void *h_src, size_t bytes, cudaStre
   };
   std::vector<std::thread> th;
   th.reserve(nthreads - 1);
-  for (int t = 1; t < nthreads; ++t) th.emplace_back(work, t);
+  int started = 1;   // thread 0 is the caller
+  try {
+    for (int t = 1; t < nthreads; ++t) {
+      th.emplace_back(work, t);
+      ++started;
+    }
+  } catch (...) {
+    // the process may start no more threads: the caller takes over the chunks of the workers that never started
+    // (no exception may cross the C ABI)
+  }
   work(0);
+  for (int t = started; t < nthreads; ++t) work(t);
   for (auto &x : th) x.join();
   for (cudaError_t le : err)
     if (le != cudaSuccess) return le;
