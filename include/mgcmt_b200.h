@@ -210,6 +210,12 @@ int mgcmt_set_option(const char *name, int value);
  * double-double accuracy ("Exact arithmetic"); and the chunk height chosen for a streaming leg. */
 int mgcmt_debug_uni_coefficients(double c, double d, double shift, double omega, double *h_out7);
 int mgcmt_debug_leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc);
+/* the phase table of one native slab-block cycle (csrc/slab_block.cu: build_phases) for nlev_slab distributed levels:
+ * h_kinds[i] = 0 down leg, 1 / 2 first / second pass of a two-pass (red-black, 9-point) down leg, 3 replicated coarse
+ * part, 4 up leg, 5 / 6 first / second pass of a two-pass up leg, 7 separate Rayleigh pass; h_levels[i] its level.
+ * Every phase is one halo exchange followed by one leg per vector.  Returns the number of phases (-1: bad arguments or
+ * capacity too small).  Host only. */
+int mgcmt_debug_slab_phases(int nlev_slab, int smoother, int with_rq_stage, int *h_kinds, int *h_levels, int capacity);
 
 /* ---- reductions / vector post-processing (MGCMTProcessor.py, Rayleigh quotients in the drivers) --
  * Deterministic: fixed two-stage tree, independent of launch timing.  Results go to DEVICE memory. */

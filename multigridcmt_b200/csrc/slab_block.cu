@@ -165,10 +165,8 @@ struct Phase {
   int level;
 };
 
-std::vector<Phase> build_phases(const mgcmt_slabblock *b, bool with_rq_stage) {
+std::vector<Phase> build_phases(int nl, bool gs, bool with_rq_stage) {
   std::vector<Phase> ph;
-  const int nl = b->nlev;
-  const bool gs = (b->smoother == MGCMT_SMOOTH_RBGS);
   for (int l = 0; l < nl; ++l) {
     if (gs && l > 0) { ph.push_back({PH_DOWN_A, l}); ph.push_back({PH_DOWN_B, l}); }
     else ph.push_back({PH_DOWN, l});
@@ -180,6 +178,9 @@ std::vector<Phase> build_phases(const mgcmt_slabblock *b, bool with_rq_stage) {
   }
   if (with_rq_stage) ph.push_back({PH_RQ, 0});
   return ph;
+}
+std::vector<Phase> build_phases(const mgcmt_slabblock *b, bool with_rq_stage) {
+  return build_phases(b->nlev, b->smoother == MGCMT_SMOOTH_RBGS, with_rq_stage);
 }
 
 int comm_stage(mgcmt_slabblock *b, Half &h, const Phase &p) {
@@ -499,6 +500,17 @@ int mgcmt_slabblock_set_smoother(mgcmt_slabblock_t *b, int smoother, double omeg
   b->smoother = smoother;
   b->omega = omega;
   return MGCMT_OK;
+}
+
+int mgcmt_debug_slab_phases(int nlev_slab, int smoother, int with_rq_stage, int *h_kinds, int *h_levels, int capacity) {
+  if (nlev_slab < 1 || !h_kinds || !h_levels) return -1;
+  const std::vector<Phase> ph = build_phases(nlev_slab, smoother == MGCMT_SMOOTH_RBGS, with_rq_stage != 0);
+  if ((int)ph.size() > capacity) return -1;
+  for (size_t i = 0; i < ph.size(); ++i) {
+    h_kinds[i] = (int)ph[i].kind;
+    h_levels[i] = ph[i].level;
+  }
+  return (int)ph.size();
 }
 
 int mgcmt_slabblock_profile(mgcmt_slabblock_t *b, int on) {

@@ -441,3 +441,36 @@ def test_vcycle_many_argument_checks_need_no_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             s.vcycle_many(fs, H, sm, [1.0, 2.0], lowest_level=8, dimension="2d")
+
+
+def test_native_slab_phase_table():
+    """csrc/slab_block.cu build_phases: the order of (halo exchange, leg) phases of one multi-GPU cycle.  Weighted Jacobi:
+    one phase per level and direction.  Red-black Gauss-Seidel: the 5-point level still one phase per direction, every
+    9-point level two (two passes of two sweeps with an exchange of the intermediate iterate in between)."""
+    import ctypes as C
+    from multigridcmt_b200 import _lib
+    lib = _lib.load()
+    DOWN, DOWN_A, DOWN_B, COARSE, UP, UP_A, UP_B, RQ = range(8)
+
+    def phases(nlev, smoother, rq):
+        kinds, levels = (C.c_int * 64)(), (C.c_int * 64)()
+        n = lib.mgcmt_debug_slab_phases(nlev, smoother, rq, kinds, levels, 64)
+        assert n > 0
+        return [(kinds[i], levels[i]) for i in range(n)]
+
+    for nlev in (1, 2, 5):
+        wj = phases(nlev, _lib.SMOOTH_WJACOBI, 0)
+        assert wj == ([(DOWN, l) for l in range(nlev)] + [(COARSE, nlev)] + [(UP, l) for l in range(nlev - 1, -1, -1)])
+        assert phases(nlev, _lib.SMOOTH_WJACOBI, 1) == wj + [(RQ, 0)]
+        gs = phases(nlev, _lib.SMOOTH_RBGS, 0)
+        want = [(DOWN, 0)]
+        for l in range(1, nlev):
+            want += [(DOWN_A, l), (DOWN_B, l)]
+        want.append((COARSE, nlev))
+        for l in range(nlev - 1, 0, -1):
+            want += [(UP_A, l), (UP_B, l)]
+        want.append((UP, 0))
+        assert gs == want
+        assert len(gs) == 4 * nlev - 1          # what NativeSlabBlock.profile_read sizes its arrays for (<= 4 nlev + 2)
+    kinds, levels = (C.c_int * 2)(), (C.c_int * 2)()
+    assert lib.mgcmt_debug_slab_phases(5, _lib.SMOOTH_RBGS, 0, kinds, levels, 2) == -1
