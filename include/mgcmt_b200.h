@@ -210,6 +210,10 @@ int mgcmt_set_option(const char *name, int value);
  * double-double accuracy ("Exact arithmetic"); and the chunk height chosen for a streaming leg. */
 int mgcmt_debug_uni_coefficients(double c, double d, double shift, double omega, double *h_out7);
 int mgcmt_debug_leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc);
+/* Test hook: one kernel that fills the shared memory of every SM with NaN bit patterns (shared memory is not cleared
+ * between kernels).  The streaming legs read ring rows in front of a chunk before anything has filled them; whatever
+ * they compute from those must never reach a result (tests/test_gpu_parity.py: Rayleigh sums after a poisoning). */
+int mgcmt_debug_poison_shared_memory(void *stream);
 /* the phase table of one native slab-block cycle (csrc/slab_block.cu: build_phases) for nlev_slab distributed levels:
  * h_kinds[i] = 0 down leg, 1 / 2 first / second pass of a two-pass (red-black, 9-point) down leg, 3 replicated coarse
  * part, 4 up leg, 5 / 6 first / second pass of a two-pass up leg, 7 separate Rayleigh pass; h_levels[i] its level.

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mgcmt_debug_uni_coefficients": (_I, [_D, _D, _D, _D, C.POINTER(_D)]),
     "mgcmt_debug_leg_rows_per_chunk": (_I, [_I, _I, _I, _I, _I]),
     "mgcmt_debug_slab_phases": (_I, [_I, _I, _I, _P, _P, _I]),
+    "mgcmt_debug_poison_shared_memory": (_I, [_P]),
     "mgcmt_dot": (_I, [_LL, _P, _P, _P, _P]),
     "mgcmt_rayleigh": (_I, [_P, _I, _P, _P, _P]),
     "mgcmt_normalize": (_I, [_LL, _P, _P]),

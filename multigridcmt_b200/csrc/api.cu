@@ -823,6 +823,29 @@ int mgcmt_debug_uni_coefficients(double c, double d, double shift, double omega,
   return MGCMT_OK;
 }
 
+namespace {
+// fills the shared memory of every SM with NaN bit patterns and leaves (shared memory is not cleared between kernels)
+__global__ void poison_shared_kernel(int granules, double *sink) {
+  extern __shared__ double2 poison_smem[];
+  const double nan = __longlong_as_double(0x7ff8dead7ff8deadLL);
+  for (int i = threadIdx.x; i < granules; i += blockDim.x) poison_smem[i] = make_double2(nan, nan);
+  __syncthreads();
+  if (sink && poison_smem[(threadIdx.x * 7) % granules].x == 0.0) *sink = 1.0;   // keeps the stores alive; never true
+}
+}  // namespace
+
+int mgcmt_debug_poison_shared_memory(void *stream) {
+  const int bytes = 100 * 1024;   // two such CTAs are resident per SM
+  static bool ready = false;
+  if (!ready) {
+    CU(cudaFuncSetAttribute(poison_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ready = true;
+  }
+  poison_shared_kernel<<<4 * num_sms(), 128, bytes, (cudaStream_t)stream>>>(bytes / 16, nullptr);
+  CU(cudaGetLastError());
+  return MGCMT_OK;
+}
+
 int mgcmt_debug_leg_rows_per_chunk(int nrows, int gx, int slots, int nstage, int max_rpc) {
   return mgcmt::leg_rows_per_chunk(nrows, gx, slots, nstage, max_rpc);
 }

@@ -662,6 +662,34 @@ def test_vcycle_rq_fused_stage(T, prod):
         assert abs(o[1] - r[1]) <= 1e-13 * abs(r[1]) and abs(o[0] - r[0]) <= 1e-12 * abs(r[0]), (N, smoother, o, r)
 
 
+def test_results_do_not_depend_on_stale_shared_memory(T, prod):
+    """The streaming legs read `w f` ring rows in front of a chunk before anything has filled them (the rows they compute
+    from those lie outside every dependency cone).  Found on 8 GPUs: after an NCCL kernel those bits can be NaN patterns,
+    and the Rayleigh stage of the red-black up leg masked its sums by zeroing ONE factor -- 0 * NaN.  Here every SM's
+    shared memory is filled with NaNs before each call: iterate and Rayleigh sums must be the bits of a clean run."""
+    from multigridcmt_b200 import _lib
+    from multigridcmt_b200.hierarchy import _ptr, _stream_ptr, get_hierarchy
+    sm, s, _ = prod
+    lib = _lib.load()
+    N = 1024
+    H = (-1. / np.pi ** 2) * sm.laplacian(N, "2d", matrix_free=True)
+    h = get_hierarchy(H, 8)
+    f = dev(T, rand(N * N, 35) - 0.5)
+    for smoother, om in ((_lib.SMOOTH_RBGS, 1.0), (_lib.SMOOTH_WJACOBI, 2. / 3.)):
+        runs = []
+        for poison in (False, True, True):
+            w = T.zeros(N * N, dtype=T.float64, device="cuda")
+            out = T.zeros(2, dtype=T.float64, device="cuda")
+            if poison:
+                _lib.check(lib.mgcmt_debug_poison_shared_memory(_stream_ptr(T)))
+            _lib.check(lib.mgcmt_vcycle_rq(h.handle, 4.38639582, 4, 4, smoother, om, _ptr(w), _ptr(f), 1, _ptr(out), _stream_ptr(T)))
+            T.cuda.synchronize()
+            runs.append((w, out))
+        for w, out in runs[1:]:
+            assert bool(T.isfinite(out).all()), (smoother, out)
+            assert T.equal(w, runs[0][0]) and T.equal(out, runs[0][1]), (smoother, out, runs[0][1])
+
+
 def test_rayleigh_quotient(prod):
     sm, s, _ = prod
     N = 128
